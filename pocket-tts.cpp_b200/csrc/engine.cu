@@ -1,0 +1,821 @@
+// engine.cu — device layer of the B200 Pocket-TTS engine: weights, per-utterance slots, ragged prefill and the
+// batched per-frame step (FlowLM backbone -> LSD flow head -> Mimi decoder -> 1920 PCM samples).
+// C ABI declared in include/ptts_b200.h. No CPU fallback: everything below runs on the device or aborts.
+#include "../../include/ptts_b200.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+#include <cstring>
+
+using namespace ptts;
+
+namespace {
+
+struct HostTensor { std::vector<float> f; std::vector<int64_t> shape; int dtype; };
+
+inline float h_bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+inline float h_silu(float x) { return x / (1.0f + expf(-x)); }
+
+struct LinW { __nv_bfloat16* w = nullptr; float* b = nullptr; int out = 0, in = 0; };
+struct ConvW { __half* w = nullptr; float* b = nullptr; int N = 0, K = 0; };
+
+}  // namespace
+
+struct b200_engine {
+    b200_config cfg{};
+    cudaStream_t stream = nullptr;
+    std::map<std::string, HostTensor> host;
+    std::vector<void*> allocs;
+    bool finalized = false;
+    long long launches = 0;
+    uint64_t seed = 0;
+    int n_voices = 0;
+    std::vector<int> voice_len;
+    int total_slots = 0;       // max_slots + max_voices (voice prefixes live in the extra KV slots)
+    int max_rows = 0;          // scratch rows for the FlowLM forward (decode: slots, prefill: chunk rows)
+    int n_embed = 0;
+
+    // ---- weights ----
+    __nv_bfloat16* embed = nullptr;
+    float *emb_std = nullptr, *emb_mean = nullptr;
+    std::vector<float> h_bos; float* d_bos = nullptr;
+    LinW input_linear, cond_embed, input_proj, ada_all, final_lin;
+    float *onw = nullptr, *onb = nullptr; __nv_bfloat16* w_eos = nullptr; float* b_eos = nullptr;
+    struct { LinW in_proj, out_proj, lin1, lin2; float *n1w, *n1b, *n2w, *n2b; } fl[N_LAYERS];
+    struct { float *lnw, *lnb; LinW mlp0, mlp2; } rb[N_RES];
+    float *fnw = nullptr, *fnb = nullptr, *t_combined = nullptr;
+    __half* wq = nullptr; float *wup = nullptr, *bup = nullptr;
+    struct { LinW in_proj, out_proj, lin1, lin2; float *n1w, *n1b, *n2w, *n2b, *ls1, *ls2; } ml[M_LAYERS];
+    ConvW c0, t2, r3a, r3b, t5, r6a, r6b, t8, r9a, r9b, c11;
+    float *freq_flow = nullptr, *freq_mimi = nullptr;
+
+    // ---- per-slot state ----
+    void *kc = nullptr, *vc = nullptr;                 // FlowLM KV [layer][total_slots][cap][1024]
+    long long kv_slot_stride = 0, kv_layer_stride = 0; // elements
+    __nv_bfloat16 *mkc = nullptr, *mvc = nullptr;      // Mimi ring [layer][max_slots][250][512]
+    long long mkv_slot_stride = 0, mkv_layer_stride = 0;
+    int *cur_len = nullptr, *mimi_off = nullptr, *gen_step = nullptr, *eos_step = nullptr, *max_gen = nullptr, *fae = nullptr, *active = nullptr;
+    float* temp = nullptr;
+    __nv_bfloat16* lat_in_bf16 = nullptr; float* lat_f32 = nullptr;   // [slot][32] backbone input / last latent
+    float* e_prev = nullptr;                                          // upsampler state [slot][512]
+    std::vector<int> h_cur_len;                                       // host mirror of cur_len
+
+    // ---- scratch ----
+    float *h = nullptr, *q = nullptr; __nv_bfloat16 *n_bf = nullptr, *att_bf = nullptr, *ff_bf = nullptr;
+    int *row_slot = nullptr, *row_pos = nullptr, *tok = nullptr; float2* cs = nullptr;
+    __nv_bfloat16 *c_bf = nullptr, *sy_bf = nullptr, *hn_bf = nullptr, *h1_bf = nullptr, *noise_bf = nullptr;
+    float *eos = nullptr, *ycond = nullptr, *mod = nullptr, *xh = nullptr, *noise_f32 = nullptr, *noise_inj = nullptr, *latent = nullptr;
+    int* produced = nullptr; float* eos_out = nullptr;
+    // Mimi
+    float* mx = nullptr; __nv_bfloat16 *mn_bf = nullptr, *mq_bf = nullptr, *matt_bf = nullptr, *mff_bf = nullptr;
+    int *mrow_slot = nullptr, *mrow_pos = nullptr; float2* mcs = nullptr;
+    __half *buf0 = nullptr, *buf2 = nullptr, *buf3a = nullptr, *buf3b = nullptr, *buf5 = nullptr, *buf6a = nullptr, *buf6b = nullptr,
+           *buf8 = nullptr, *buf9a = nullptr, *buf9b = nullptr, *buf11 = nullptr;
+    float *y3 = nullptr, *y6 = nullptr, *y9 = nullptr, *pcm = nullptr;
+    int C2 = 512, C5 = 256, C8 = 128;
+    ShiftAll shifts{};
+    // pinned staging
+    float* pin_f = nullptr; int* pin_i = nullptr; size_t pin_f_n = 0, pin_i_n = 0;
+    TcPlanCache* tc = nullptr;
+    // optional per-segment device timing (bench.py roofline leg): event pairs recorded on the engine stream
+    bool profiling = false;
+    struct Seg { int cat; cudaEvent_t a, b; };
+    std::vector<Seg> segs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+    cudaEvent_t next_event() {
+        if (ev_used == ev_pool.size()) { cudaEvent_t ev; PTTS_CUDA_CHECK(cudaEventCreate(&ev)); ev_pool.push_back(ev); }
+        return ev_pool[ev_used++];
+    }
+    int seg_begin(int cat) {
+        if (!profiling) return -1;
+        Seg sg; sg.cat = cat; sg.a = next_event(); sg.b = next_event();
+        PTTS_CUDA_CHECK(cudaEventRecord(sg.a, stream));
+        segs.push_back(sg); return (int)segs.size() - 1;
+    }
+    void seg_end(int id) { if (id >= 0) PTTS_CUDA_CHECK(cudaEventRecord(segs[id].b, stream)); }
+
+    template <typename T> T* dalloc(size_t n, bool zero = true) {
+        void* p = nullptr;
+        PTTS_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+        if (zero) PTTS_CUDA_CHECK(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), stream));
+        allocs.push_back(p);
+        return (T*)p;
+    }
+    template <typename T> T* upload(const std::vector<T>& v) {
+        T* p = dalloc<T>(v.size(), false);
+        PTTS_CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return p;
+    }
+    const HostTensor* find(const std::string& k, bool required = true) {
+        auto it = host.find(k);
+        if (it == host.end()) {
+            if (required) { fprintf(stderr, "ptts_b200: error: missing tensor %s\n", k.c_str()); exit(1); }
+            return nullptr;
+        }
+        return &it->second;
+    }
+    float* up_f32(const std::string& k, bool required = true) {
+        auto* t = find(k, required);
+        return t ? upload(t->f) : nullptr;
+    }
+    static std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
+        std::vector<__nv_bfloat16> o(v.size());
+        for (size_t i = 0; i < v.size(); i++) o[i] = __float2bfloat16_rn(v[i]);
+        return o;
+    }
+    LinW up_lin(const std::string& p, int out, int in) {
+        auto* w = find(p + ".weight");
+        if ((int64_t)w->f.size() != (int64_t)out * in) { fprintf(stderr, "ptts_b200: error: bad shape for %s\n", p.c_str()); exit(1); }
+        LinW L; L.out = out; L.in = in;
+        L.w = upload(to_bf16(w->f));
+        L.b = up_f32(p + ".bias", false);
+        return L;
+    }
+    // causal conv (torch [co][ci][k]) -> f16 [co][k*ci]  (loader policy: ggml_conv_1d weights F16, src/loader.h:209)
+    ConvW up_conv(const std::string& p, int co, int ci, int k) {
+        auto* w = find(p + ".conv.weight");
+        std::vector<__half> o((size_t)co * k * ci);
+        for (int a = 0; a < co; a++) for (int b = 0; b < ci; b++) for (int c = 0; c < k; c++)
+            o[((size_t)a * k + c) * ci + b] = __float2half_rn(w->f[((size_t)a * ci + b) * k + c]);
+        ConvW C; C.N = co; C.K = k * ci; C.w = upload(o); C.b = up_f32(p + ".conv.bias", false);
+        return C;
+    }
+    // transposed conv K = 2s (torch [ci][co][k]) as a 2-tap GEMM over [prev row | current row]:
+    //   out[t*s + j][co] = x[t-1] . W[:, co, j+s] + x[t] . W[:, co, j]     (see DESIGN.md "transposed convs")
+    // row width Cc = ci (plain f16 activations) or 2*ci (hi | lo split).
+    ConvW up_convt(const std::string& p, int ci, int co, int k, int s, int Cc) {
+        auto* w = find(p + ".convtr.weight");
+        const int N = s * co, Kw = 2 * Cc;
+        std::vector<__half> o((size_t)N * Kw);
+        for (int j = 0; j < s; j++) for (int c = 0; c < co; c++) for (int kk = 0; kk < Kw; kk++) {
+            const bool cur = kk >= Cc; const int cin = (kk % Cc) % ci; const int tap = cur ? j : j + s;
+            o[((size_t)(j * co + c)) * Kw + kk] = __float2half_rn(w->f[((size_t)cin * co + c) * k + tap]);
+        }
+        ConvW C; C.N = N; C.K = Kw; C.w = upload(o);
+        auto* b = find(p + ".convtr.bias", false);
+        if (b) { std::vector<float> bb(N); for (int j = 0; j < s; j++) for (int c = 0; c < co; c++) bb[j * co + c] = b->f[c]; C.b = upload(bb); }
+        return C;
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    template <typename T>
+    void gemm(const T* A, RowMap amap, int a_rps, const T* W, int R, int N, int K, const Epi& epi) {
+        if (R <= 0) return;
+        if (cfg.gemm_path == 0 && tc_gemm_supported<T>(R, N, K, amap, a_rps)) {
+            launches += tc_gemm_launch<T>(tc, A, amap, a_rps, W, R, N, K, epi, stream);
+            return;
+        }
+        if (R <= 8) {
+            const int warps = (N + 1) / 2, blocks = (warps + 7) / 8;
+            gemv_small_kernel<T, 8><<<blocks, 256, 0, stream>>>(A, amap, a_rps, W, R, N, K, epi);
+        } else {
+            dim3 grid((N + 63) / 64, (R + 63) / 64);
+            gemm_ffma_kernel<T><<<grid, 256, 0, stream>>>(A, amap, a_rps, W, R, N, K, epi);
+        }
+        launches++;
+    }
+    static RowMap rows(long long ld) { RowMap m; m.row_stride = ld; return m; }
+    static RowMap smap(long long slot_stride, long long row_stride, long long base) { RowMap m; m.slot_stride = slot_stride; m.row_stride = row_stride; m.base = base; return m; }
+    void lin(const __nv_bfloat16* A, const LinW& L, int R, Epi epi) {
+        if (!epi.bias) epi.bias = L.b;
+        gemm<__nv_bfloat16>(A, rows(L.in), 1 << 30, L.w, R, L.out, L.in, epi);
+    }
+
+    // FlowLM transformer over R rows held in `h` (reference modules/transformer.h:253-278,363-374).
+    void flow_forward(int R) {
+        const int BIG = 1 << 30;
+        for (int l = 0; l < N_LAYERS; l++) {
+            auto& L = fl[l];
+            layernorm_kernel<D_MODEL><<<(R + 7) / 8, 256, 0, stream>>>(h, rows(D_MODEL), BIG, R, 1e-5f, L.n1w, L.n1b, nullptr, nullptr, 0, n_bf, nullptr);
+            Epi e; e.mode = EPI_FLOW_QKV; e.row_slot = row_slot; e.row_pos = row_pos; e.cs = cs; e.kv_f32 = cfg.kv_f32;
+            e.kv_slot_stride = kv_slot_stride; e.q_out_f32 = q;
+            if (cfg.kv_f32) { e.kcache = (float*)kc + l * kv_layer_stride; e.vcache = (float*)vc + l * kv_layer_stride; }
+            else { e.kcache = (__nv_bfloat16*)kc + l * kv_layer_stride; e.vcache = (__nv_bfloat16*)vc + l * kv_layer_stride; }
+            lin(n_bf, L.in_proj, R, e);
+            const size_t smem = (size_t)cfg.kv_capacity * sizeof(float);
+            const int sg = seg_begin(0);
+            if (cfg.kv_f32) attn_flow_kernel<float><<<dim3(R, N_HEADS), 128, smem, stream>>>(q, (const float*)e.kcache, (const float*)e.vcache, kv_slot_stride, row_slot, row_pos, att_bf);
+            else attn_flow_kernel<__nv_bfloat16><<<dim3(R, N_HEADS), 128, smem, stream>>>(q, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, kv_slot_stride, row_slot, row_pos, att_bf);
+            seg_end(sg);
+            Epi eo; eo.resid = h; eo.resid_map = rows(D_MODEL); eo.out = h; eo.out_map = rows(D_MODEL);
+            lin(att_bf, L.out_proj, R, eo);
+            layernorm_kernel<D_MODEL><<<(R + 7) / 8, 256, 0, stream>>>(h, rows(D_MODEL), BIG, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, n_bf, nullptr);
+            Epi e1; e1.out2 = ff_bf; e1.out2_map = rows(D_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
+            lin(n_bf, L.lin1, R, e1);
+            Epi e2; e2.resid = h; e2.resid_map = rows(D_MODEL); e2.out = h; e2.out_map = rows(D_MODEL);
+            lin(ff_bf, L.lin2, R, e2);
+            launches += 3;
+        }
+    }
+
+    // out_norm + EOS + 1-step LSD head over R rows of `h` (reference models/flow_lm.h:114-142, modules/mlp.h:233-251).
+    void flow_head(int R) {
+        const int BIG = 1 << 30;
+        head_pre_kernel<<<(R + 7) / 8, 256, 0, stream>>>(h, R, onw, onb, w_eos, b_eos, c_bf, eos);
+        // y = t_combined + cond_embed(c); sy = silu(y)
+        Epi ec; ec.resid = t_combined; ec.resid_map = RowMap{}; ec.out2 = sy_bf; ec.out2_map = rows(D_FLOW); ec.out2_type = OUT2_BF16; ec.act = ACT_SILU;
+        lin(c_bf, cond_embed, R, ec);
+        // all seven adaLN projections of silu(y) in one GEMM: [6 x (shift|scale|gate)] + [shift|scale]
+        Epi em; em.out = mod; em.out_map = rows(ada_all.out);
+        lin(sy_bf, ada_all, R, em);
+        Epi ei; ei.out = xh; ei.out_map = rows(D_FLOW);
+        lin(noise_bf, input_proj, R, ei);
+        for (int r = 0; r < N_RES; r++) {
+            const float* m = mod + r * 3 * D_FLOW;
+            layernorm_kernel<D_FLOW><<<(R + 7) / 8, 256, 0, stream>>>(xh, rows(D_FLOW), BIG, R, 1e-6f, rb[r].lnw, rb[r].lnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
+            Epi e0; e0.out2 = h1_bf; e0.out2_map = rows(D_FLOW); e0.out2_type = OUT2_BF16; e0.act = ACT_SILU;
+            lin(hn_bf, rb[r].mlp0, R, e0);
+            Epi e2; e2.rowmul = m + 2 * D_FLOW; e2.rowmul_ld = ada_all.out; e2.resid = xh; e2.resid_map = rows(D_FLOW); e2.out = xh; e2.out_map = rows(D_FLOW);
+            lin(h1_bf, rb[r].mlp2, R, e2);
+        }
+        const float* m = mod + N_RES * 3 * D_FLOW;
+        layernorm_kernel<D_FLOW><<<(R + 7) / 8, 256, 0, stream>>>(xh, rows(D_FLOW), BIG, R, 1e-6f, fnw, fnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
+        Epi ef; ef.resid = noise_f32; ef.resid_map = rows(LDIM); ef.out = latent; ef.out_map = rows(LDIM);
+        lin(hn_bf, final_lin, R, ef);
+        launches += 2 + N_RES;
+    }
+
+    // Mimi decoder for slots [slot0, slot0+n) from lat_f32 (reference models/mimi.h:85-104).
+    void mimi(int slot0, int n) {
+        const int BIG = 1 << 30, R = n * M_T;
+        mimi_front_kernel<<<n, M_DIM, 0, stream>>>(slot0, lat_f32, emb_std, emb_mean, wq, wup, bup, e_prev, mx);
+        float* x = mx + (long long)slot0 * M_T * M_DIM;
+        const int s_mtf = seg_begin(3);
+        for (int l = 0; l < M_LAYERS; l++) {
+            auto& L = ml[l];
+            layernorm_kernel<M_DIM><<<(R + 7) / 8, 256, 0, stream>>>(x, rows(M_DIM), BIG, R, 0.0f, L.n1w, L.n1b, nullptr, nullptr, 0, mn_bf, nullptr);
+            Epi e; e.mode = EPI_MIMI_QKV; e.row_slot = mrow_slot; e.row_pos = mrow_pos; e.cs = mcs; e.kv_slot_stride = mkv_slot_stride;
+            e.kcache = mkc + l * mkv_layer_stride; e.vcache = mvc + l * mkv_layer_stride; e.q_out_bf16 = mq_bf;
+            lin(mn_bf, L.in_proj, R, e);
+            attn_mimi_kernel<<<dim3(n, M_HEADS), 128, 0, stream>>>(mq_bf, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, mimi_off, cfg.mimi_mask_mode, matt_bf);
+            Epi eo; eo.colscale = L.ls1; eo.resid = x; eo.resid_map = rows(M_DIM); eo.out = x; eo.out_map = rows(M_DIM);
+            lin(matt_bf, L.out_proj, R, eo);
+            layernorm_kernel<M_DIM><<<(R + 7) / 8, 256, 0, stream>>>(x, rows(M_DIM), BIG, R, 0.0f, L.n2w, L.n2b, nullptr, nullptr, 0, mn_bf, nullptr);
+            Epi e1; e1.out2 = mff_bf; e1.out2_map = rows(M_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
+            lin(mn_bf, L.lin1, R, e1);
+            Epi e2; e2.colscale = L.ls2; e2.resid = x; e2.resid_map = rows(M_DIM); e2.out = x; e2.out_map = rows(M_DIM);
+            lin(mff_bf, L.lin2, R, e2);
+            launches += 3;
+        }
+        seg_end(s_mtf);
+        const int s_sea = seg_begin(4);
+        // SEANet (reference modules/seanet.h:187-211); every conv is a GEMM over overlapping channel-last rows.
+        const int T0 = 16, T1 = 96, T2 = 480, T3 = 1920;
+        const long long s0 = 22LL * 512, s2 = 17LL * C2, s3a = 98LL * 256, s3b = 96LL * 128, s5 = 97LL * C5, s6a = 482LL * 128, s6b = 480LL * 64,
+                        s8 = 481LL * C8, s9a = 1922LL * 64, s9b = 1920LL * 32, s11 = 1922LL * 64;
+        const int o2t = cfg.convt_split ? OUT2_F16_SPLIT : OUT2_F16;
+        {
+            const long long tot = (long long)R * M_DIM;
+            cast_f16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(x, smap(16LL * 512, 512, 0), buf0 + slot0 * s0, smap(s0, 512, 6 * 512), T0, R, M_DIM);
+        }
+        { Epi e; e.rps = T0; e.bias = c0.b; e.act = ACT_ELU; e.out2 = buf2 + slot0 * s2; e.out2_map = smap(s2, C2, C2); e.out2_type = o2t; e.split_off = 512;
+          gemm<__half>(buf0 + slot0 * s0, smap(s0, 512, 0), T0, c0.w, n * T0, c0.N, c0.K, e); }
+        { Epi e; e.rps = T0; e.bias = t2.b; e.out = y3 + slot0 * 96LL * 256; e.out_map = smap(96LL * 256, 1536, 0);
+          e.act = ACT_ELU; e.out2 = buf3a + slot0 * s3a; e.out2_map = smap(s3a, 1536, 2 * 256); e.out2_type = OUT2_F16;
+          gemm<__half>(buf2 + slot0 * s2, smap(s2, C2, 0), T0, t2.w, n * T0, t2.N, t2.K, e); }
+        { Epi e; e.rps = T1; e.bias = r3a.b; e.act = ACT_ELU; e.out2 = buf3b + slot0 * s3b; e.out2_map = smap(s3b, 128, 0); e.out2_type = OUT2_F16;
+          gemm<__half>(buf3a + slot0 * s3a, smap(s3a, 256, 0), T1, r3a.w, n * T1, r3a.N, r3a.K, e); }
+        { Epi e; e.rps = T1; e.bias = r3b.b; e.resid = y3 + slot0 * 96LL * 256; e.resid_map = smap(96LL * 256, 256, 0);
+          e.act = ACT_ELU; e.out2 = buf5 + slot0 * s5; e.out2_map = smap(s5, C5, C5); e.out2_type = o2t; e.split_off = 256;
+          gemm<__half>(buf3b + slot0 * s3b, smap(s3b, 128, 0), T1, r3b.w, n * T1, r3b.N, r3b.K, e); }
+        { Epi e; e.rps = T1; e.bias = t5.b; e.out = y6 + slot0 * 480LL * 128; e.out_map = smap(480LL * 128, 640, 0);
+          e.act = ACT_ELU; e.out2 = buf6a + slot0 * s6a; e.out2_map = smap(s6a, 640, 2 * 128); e.out2_type = OUT2_F16;
+          gemm<__half>(buf5 + slot0 * s5, smap(s5, C5, 0), T1, t5.w, n * T1, t5.N, t5.K, e); }
+        { Epi e; e.rps = T2; e.bias = r6a.b; e.act = ACT_ELU; e.out2 = buf6b + slot0 * s6b; e.out2_map = smap(s6b, 64, 0); e.out2_type = OUT2_F16;
+          gemm<__half>(buf6a + slot0 * s6a, smap(s6a, 128, 0), T2, r6a.w, n * T2, r6a.N, r6a.K, e); }
+        { Epi e; e.rps = T2; e.bias = r6b.b; e.resid = y6 + slot0 * 480LL * 128; e.resid_map = smap(480LL * 128, 128, 0);
+          e.act = ACT_ELU; e.out2 = buf8 + slot0 * s8; e.out2_map = smap(s8, C8, C8); e.out2_type = o2t; e.split_off = 128;
+          gemm<__half>(buf6b + slot0 * s6b, smap(s6b, 64, 0), T2, r6b.w, n * T2, r6b.N, r6b.K, e); }
+        { Epi e; e.rps = T2; e.bias = t8.b; e.out = y9 + slot0 * 1920LL * 64; e.out_map = smap(1920LL * 64, 256, 0);
+          e.act = ACT_ELU; e.out2 = buf9a + slot0 * s9a; e.out2_map = smap(s9a, 256, 2 * 64); e.out2_type = OUT2_F16;
+          gemm<__half>(buf8 + slot0 * s8, smap(s8, C8, 0), T2, t8.w, n * T2, t8.N, t8.K, e); }
+        { Epi e; e.rps = T3; e.bias = r9a.b; e.act = ACT_ELU; e.out2 = buf9b + slot0 * s9b; e.out2_map = smap(s9b, 32, 0); e.out2_type = OUT2_F16;
+          gemm<__half>(buf9a + slot0 * s9a, smap(s9a, 64, 0), T3, r9a.w, n * T3, r9a.N, r9a.K, e); }
+        { Epi e; e.rps = T3; e.bias = r9b.b; e.resid = y9 + slot0 * 1920LL * 64; e.resid_map = smap(1920LL * 64, 64, 0);
+          e.act = ACT_ELU; e.out2 = buf11 + slot0 * s11; e.out2_map = smap(s11, 64, 2 * 64); e.out2_type = OUT2_F16;
+          gemm<__half>(buf9b + slot0 * s9b, smap(s9b, 32, 0), T3, r9b.w, n * T3, r9b.N, r9b.K, e); }
+        {
+            const int Rr = n * T3;
+            conv_n1_kernel<<<(Rr + 7) / 8, 256, 0, stream>>>(buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm + (long long)slot0 * FRAME);
+        }
+        shift_states_kernel<<<dim3(n, shifts.n), 128, 0, stream>>>(shifts, slot0, mimi_off);
+        launches += 4;
+        seg_end(s_sea);
+    }
+
+    void prepare_step(int slot0, int n) {
+        prepare_step_kernel<<<(n * M_T + 255) / 256, 256, 0, stream>>>(slot0, n, cur_len, mimi_off, row_slot, row_pos, mrow_slot, mrow_pos);
+        rope_table_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(row_pos, freq_flow, cs, n);
+        rope_table_kernel<<<(n * M_T * 32 + 255) / 256, 256, 0, stream>>>(mrow_pos, freq_mimi, mcs, n * M_T);
+        launches += 3;
+    }
+
+    // One generation step for slots [slot0, slot0+n) (reference _stream_sentence_step, src/pocket_tts.cpp:446-492).
+    void step_enqueue(int slot0, int n, bool injected) {
+        const int s_all = seg_begin(5);
+        prepare_step(slot0, n);
+        const int s_flow = seg_begin(1);
+        Epi e; e.out = h; e.out_map = rows(D_MODEL);
+        lin(lat_in_bf16 + (long long)slot0 * LDIM, input_linear, n, e);
+        flow_forward(n);
+        seg_end(s_flow);
+        const int s_head = seg_begin(2);
+        noise_kernel<<<(n * LDIM + 127) / 128, 128, 0, stream>>>(slot0, n, injected ? noise_inj : nullptr, seed, temp, gen_step, noise_f32, noise_bf);
+        flow_head(n);
+        step_logic_kernel<<<n, 32, 0, stream>>>(slot0, n, eos, latent, cur_len, gen_step, eos_step, max_gen, fae, active, lat_in_bf16, lat_f32, produced, eos_out);
+        launches += 2;
+        seg_end(s_head);
+        mimi(slot0, n);
+        seg_end(s_all);
+    }
+
+    void ensure_pinned(size_t nf, size_t ni) {
+        if (nf > pin_f_n) { if (pin_f) cudaFreeHost(pin_f); PTTS_CUDA_CHECK(cudaMallocHost(&pin_f, nf * sizeof(float))); pin_f_n = nf; }
+        if (ni > pin_i_n) { if (pin_i) cudaFreeHost(pin_i); PTTS_CUDA_CHECK(cudaMallocHost(&pin_i, ni * sizeof(int))); pin_i_n = ni; }
+    }
+};
+
+namespace {
+
+__global__ void set_meta_kernel(int slot, int cur, int mg, int f, float t, const float* bos, int* cur_len, int* gen_step, int* eos_step,
+                                int* max_gen, int* fae, int* active, float* temp, __nv_bfloat16* lat_in_bf16, float* lat_f32) {
+    const int i = threadIdx.x;
+    if (i == 0) { cur_len[slot] = cur; gen_step[slot] = 0; eos_step[slot] = -1; max_gen[slot] = mg; fae[slot] = f; active[slot] = mg > 0 ? 1 : 0; temp[slot] = t; }
+    if (i < LDIM) { lat_f32[slot * LDIM + i] = bos[i]; lat_in_bf16[slot * LDIM + i] = __float2bfloat16_rn(bos[i]); }
+}
+
+// copy_states (reference models/flow_lm.h:70-78): restore the voice-conditioned prefix rows [0, len) of every layer.
+__global__ void copy_prefix_kernel(char* kc, char* vc, long long slot_bytes, long long layer_bytes, int dst_slot, int src_slot, long long bytes) {
+    char* base = (blockIdx.y & 1) ? vc : kc;
+    const int layer = blockIdx.y >> 1;
+    const uint4* src = reinterpret_cast<const uint4*>(base + layer * layer_bytes + src_slot * slot_bytes);
+    uint4* dst = reinterpret_cast<uint4*>(base + layer * layer_bytes + dst_slot * slot_bytes);
+    const long long n = bytes / 16;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+__global__ void copy_rows_f32_kernel(const float* src, float* dst, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+void b200_default_config(b200_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->device = 0; c->max_slots = 1; c->max_voices = 8; c->kv_capacity = 2048; c->kv_f32 = 0; c->mimi_mask_mode = 0;
+    c->convt_split = 1; c->gemm_path = 0; c->max_prefill_rows = 512;
+}
+
+int b200_engine_create(const b200_config* cfg, b200_engine** out) {
+    if (!cfg || !out || cfg->max_slots < 1 || cfg->kv_capacity < 16 || cfg->kv_capacity > 12288) return B200_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "ptts_b200: error: no CUDA device (this engine has no CPU fallback)\n");
+        return B200_ESTATE;
+    }
+    auto* e = new b200_engine; e->cfg = *cfg;
+    if (e->cfg.max_prefill_rows <= 0) e->cfg.max_prefill_rows = 512;
+    if (e->cfg.max_voices < 1) e->cfg.max_voices = 1;
+    PTTS_CUDA_CHECK(cudaSetDevice(cfg->device));
+    PTTS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->total_slots = cfg->max_slots + e->cfg.max_voices;
+    e->max_rows = std::max(cfg->max_slots, e->cfg.max_prefill_rows);
+    e->voice_len.assign(e->cfg.max_voices, 0);
+    e->h_cur_len.assign(cfg->max_slots, 0);
+    e->tc = tc_plan_cache_create();
+    *out = e;
+    return B200_OK;
+}
+
+void b200_engine_destroy(b200_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaStreamSynchronize(e->stream);
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->pin_f) cudaFreeHost(e->pin_f);
+    if (e->pin_i) cudaFreeHost(e->pin_i);
+    tc_plan_cache_destroy(e->tc);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int b200_upload_tensor(b200_engine* e, const char* key, const void* data, int dtype, const int64_t* shape, int ndim) {
+    if (!e || !key || !data || e->finalized) return B200_EINVAL;
+    HostTensor t; t.dtype = dtype; size_t n = 1;
+    for (int i = 0; i < ndim; i++) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+    t.f.resize(n);
+    if (dtype == B200_DT_F32) memcpy(t.f.data(), data, n * 4);
+    else if (dtype == B200_DT_BF16) { const uint16_t* s = (const uint16_t*)data; for (size_t i = 0; i < n; i++) { uint32_t u = (uint32_t)s[i] << 16; memcpy(&t.f[i], &u, 4); } }
+    else if (dtype == B200_DT_F16) { const __half* s = (const __half*)data; for (size_t i = 0; i < n; i++) t.f[i] = __half2float(s[i]); }
+    else return B200_EINVAL;
+    e->host[key] = std::move(t);
+    return B200_OK;
+}
+
+int b200_finalize_weights(b200_engine* e) {
+    if (!e || e->finalized) return B200_ESTATE;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const auto& cfg = e->cfg;
+    // ---------------- weights ----------------
+    auto* emb = e->find("flow_lm.conditioner.embed.weight");
+    e->n_embed = (int)emb->shape[0];
+    e->embed = e->upload(b200_engine::to_bf16(emb->f));
+    e->emb_std = e->up_f32("flow_lm.emb_std"); e->emb_mean = e->up_f32("flow_lm.emb_mean");
+    e->h_bos = e->find("flow_lm.bos_emb")->f; e->d_bos = e->upload(e->h_bos);
+    e->input_linear = e->up_lin("flow_lm.input_linear", D_MODEL, LDIM);
+    e->onw = e->up_f32("flow_lm.out_norm.weight"); e->onb = e->up_f32("flow_lm.out_norm.bias", false);
+    e->w_eos = e->upload(b200_engine::to_bf16(e->find("flow_lm.out_eos.weight")->f));
+    e->b_eos = e->up_f32("flow_lm.out_eos.bias", false);
+    for (int l = 0; l < N_LAYERS; l++) {
+        const std::string p = "flow_lm.transformer.layers." + std::to_string(l) + ".";
+        auto& L = e->fl[l];
+        L.in_proj = e->up_lin(p + "self_attn.in_proj", 3 * D_MODEL, D_MODEL); L.out_proj = e->up_lin(p + "self_attn.out_proj", D_MODEL, D_MODEL);
+        L.lin1 = e->up_lin(p + "linear1", D_FF, D_MODEL); L.lin2 = e->up_lin(p + "linear2", D_MODEL, D_FF);
+        L.n1w = e->up_f32(p + "norm1.weight"); L.n1b = e->up_f32(p + "norm1.bias", false);
+        L.n2w = e->up_f32(p + "norm2.weight"); L.n2b = e->up_f32(p + "norm2.bias", false);
+    }
+    const std::string f = "flow_lm.flow_net.";
+    e->input_proj = e->up_lin(f + "input_proj", D_FLOW, LDIM);
+    e->cond_embed = e->up_lin(f + "cond_embed", D_FLOW, D_MODEL);
+    {   // seven adaLN projections of the same silu(y) fused into one [10240][512] weight
+        std::vector<float> w, b; bool has_b = true;
+        for (int r = 0; r <= N_RES; r++) {
+            const std::string p = r < N_RES ? f + "res_blocks." + std::to_string(r) + ".adaLN_modulation.1" : f + "final_layer.adaLN_modulation.1";
+            auto* tw = e->find(p + ".weight"); w.insert(w.end(), tw->f.begin(), tw->f.end());
+            auto* tb = e->find(p + ".bias", false);
+            if (tb) b.insert(b.end(), tb->f.begin(), tb->f.end()); else { has_b = false; b.resize(w.size() / D_FLOW, 0.f); }
+        }
+        (void)has_b;
+        e->ada_all.out = (int)(w.size() / D_FLOW); e->ada_all.in = D_FLOW;
+        e->ada_all.w = e->upload(b200_engine::to_bf16(w)); e->ada_all.b = e->upload(b);
+    }
+    for (int r = 0; r < N_RES; r++) {
+        const std::string p = f + "res_blocks." + std::to_string(r) + ".";
+        e->rb[r].lnw = e->up_f32(p + "in_ln.weight", false); e->rb[r].lnb = e->up_f32(p + "in_ln.bias", false);
+        e->rb[r].mlp0 = e->up_lin(p + "mlp.0", D_FLOW, D_FLOW); e->rb[r].mlp2 = e->up_lin(p + "mlp.2", D_FLOW, D_FLOW);
+    }
+    e->final_lin = e->up_lin(f + "final_layer.linear", LDIM, D_FLOW);
+    e->fnw = e->up_f32(f + "final_layer.norm_final.weight", false); e->fnb = e->up_f32(f + "final_layer.norm_final.bias", false);
+    {   // constant timestep embedding t_combined = (TE1(t=1) + TE0(s=0)) / 2 (reference modules/mlp.h:92-106,18-37,241-245)
+        std::vector<float> tc(D_FLOW, 0.f);
+        const float tval[2] = {0.0f, 1.0f};
+        for (int idx = 0; idx < 2; idx++) {
+            const std::string p = f + "time_embed." + std::to_string(idx) + ".";
+            auto *w0 = e->find(p + "mlp.0.weight"), *b0 = e->find(p + "mlp.0.bias", false), *w2 = e->find(p + "mlp.2.weight"), *b2 = e->find(p + "mlp.2.bias", false);
+            auto *alpha = e->find(p + "mlp.3.alpha"), *freqs = e->find(p + "freqs");
+            float emb2[256], h1[D_FLOW], u[D_FLOW];
+            for (int i = 0; i < 128; i++) { const float a = freqs->f[i] * tval[idx]; emb2[i] = h_bf16r(cosf(a)); emb2[128 + i] = h_bf16r(sinf(a)); }
+            for (int o = 0; o < D_FLOW; o++) { float acc = 0.f; for (int i = 0; i < 256; i++) acc += h_bf16r(w0->f[(size_t)o * 256 + i]) * emb2[i]; h1[o] = h_bf16r(h_silu(acc + (b0 ? b0->f[o] : 0.f))); }
+            for (int o = 0; o < D_FLOW; o++) { float acc = 0.f; for (int i = 0; i < D_FLOW; i++) acc += h_bf16r(w2->f[(size_t)o * D_FLOW + i]) * h1[i]; u[o] = acc + (b2 ? b2->f[o] : 0.f); }
+            double s = 0; for (int i = 0; i < D_FLOW; i++) s += u[i];
+            const float mean = (float)(s / D_FLOW);
+            double ss = 0; for (int i = 0; i < D_FLOW; i++) { const float d = u[i] - mean; ss += (double)(d * d); }
+            const float sd = sqrtf((float)ss * (1.f / (D_FLOW - 1)) + 1e-5f);
+            for (int i = 0; i < D_FLOW; i++) tc[i] += alpha->f[i] * (u[i] / sd);
+        }
+        for (auto& v : tc) v *= 0.5f;
+        e->t_combined = e->upload(tc);
+    }
+    // Mimi
+    {
+        auto* q = e->find("mimi.quantizer.output_proj.weight");
+        std::vector<__half> qh(q->f.size()); for (size_t i = 0; i < qh.size(); i++) qh[i] = __float2half_rn(q->f[i]);
+        e->wq = e->upload(qh);
+        e->wup = e->up_f32("mimi.upsample.convtr.convtr.weight"); e->bup = e->up_f32("mimi.upsample.convtr.convtr.bias", false);
+    }
+    for (int l = 0; l < M_LAYERS; l++) {
+        const std::string p = "mimi.decoder_transformer.transformer.layers." + std::to_string(l) + ".";
+        auto& L = e->ml[l];
+        L.in_proj = e->up_lin(p + "self_attn.in_proj", 3 * M_DIM, M_DIM); L.out_proj = e->up_lin(p + "self_attn.out_proj", M_DIM, M_DIM);
+        L.lin1 = e->up_lin(p + "linear1", M_FF, M_DIM); L.lin2 = e->up_lin(p + "linear2", M_DIM, M_FF);
+        L.n1w = e->up_f32(p + "norm1.weight"); L.n1b = e->up_f32(p + "norm1.bias", false);
+        L.n2w = e->up_f32(p + "norm2.weight"); L.n2b = e->up_f32(p + "norm2.bias", false);
+        L.ls1 = e->up_f32(p + "layer_scale_1.scale"); L.ls2 = e->up_f32(p + "layer_scale_2.scale");
+    }
+    e->C2 = cfg.convt_split ? 1024 : 512; e->C5 = cfg.convt_split ? 512 : 256; e->C8 = cfg.convt_split ? 256 : 128;
+    const std::string d = "mimi.decoder.model.";
+    e->c0 = e->up_conv(d + "0", 512, 512, 7);
+    e->t2 = e->up_convt(d + "2", 512, 256, 12, 6, e->C2);
+    e->r3a = e->up_conv(d + "3.block.1", 128, 256, 3); e->r3b = e->up_conv(d + "3.block.3", 256, 128, 1);
+    e->t5 = e->up_convt(d + "5", 256, 128, 10, 5, e->C5);
+    e->r6a = e->up_conv(d + "6.block.1", 64, 128, 3); e->r6b = e->up_conv(d + "6.block.3", 128, 64, 1);
+    e->t8 = e->up_convt(d + "8", 128, 64, 8, 4, e->C8);
+    e->r9a = e->up_conv(d + "9.block.1", 32, 64, 3); e->r9b = e->up_conv(d + "9.block.3", 64, 32, 1);
+    e->c11 = e->up_conv(d + "11", 1, 64, 3);
+    {
+        std::vector<float> ff(32), fm(32);
+        for (int i = 0; i < 32; i++) {
+            ff[i] = expf((float)i * (-logf(10000.0f) / 32));        // FlowLM: ggml_scale then ggml_exp (rope.h:36-38)
+            fm[i] = (float)expf(-logf(10000.0f) * i / 32);          // Mimi: ggml_timestep_embedding (rope.h:8-20)
+        }
+        e->freq_flow = e->upload(ff); e->freq_mimi = e->upload(fm);
+    }
+    e->host.clear();
+
+    // ---------------- state + scratch ----------------
+    const int S = cfg.max_slots, TS = e->total_slots, cap = cfg.kv_capacity, MR = e->max_rows;
+    e->kv_slot_stride = (long long)cap * D_MODEL; e->kv_layer_stride = e->kv_slot_stride * TS;
+    const size_t kv_elems = (size_t)e->kv_layer_stride * N_LAYERS;
+    if (cfg.kv_f32) { e->kc = e->dalloc<float>(kv_elems); e->vc = e->dalloc<float>(kv_elems); }
+    else { e->kc = e->dalloc<__nv_bfloat16>(kv_elems); e->vc = e->dalloc<__nv_bfloat16>(kv_elems); }
+    e->mkv_slot_stride = (long long)M_CTX * M_DIM; e->mkv_layer_stride = e->mkv_slot_stride * S;
+    e->mkc = e->dalloc<__nv_bfloat16>((size_t)e->mkv_layer_stride * M_LAYERS); e->mvc = e->dalloc<__nv_bfloat16>((size_t)e->mkv_layer_stride * M_LAYERS);
+    e->cur_len = e->dalloc<int>(TS); e->mimi_off = e->dalloc<int>(S); e->gen_step = e->dalloc<int>(S); e->eos_step = e->dalloc<int>(S);
+    e->max_gen = e->dalloc<int>(S); e->fae = e->dalloc<int>(S); e->active = e->dalloc<int>(S); e->temp = e->dalloc<float>(S);
+    e->lat_in_bf16 = e->dalloc<__nv_bfloat16>((size_t)S * LDIM); e->lat_f32 = e->dalloc<float>((size_t)S * LDIM);
+    e->e_prev = e->dalloc<float>((size_t)S * M_DIM);
+    e->h = e->dalloc<float>((size_t)MR * D_MODEL); e->q = e->dalloc<float>((size_t)MR * D_MODEL);
+    e->n_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_MODEL); e->att_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_MODEL);
+    e->ff_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_FF);
+    e->row_slot = e->dalloc<int>(MR); e->row_pos = e->dalloc<int>(MR); e->tok = e->dalloc<int>(MR); e->cs = e->dalloc<float2>((size_t)MR * 32);
+    e->c_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_MODEL); e->sy_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW);
+    e->hn_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW); e->h1_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW);
+    e->noise_bf = e->dalloc<__nv_bfloat16>((size_t)S * LDIM);
+    e->eos = e->dalloc<float>(S); e->eos_out = e->dalloc<float>(S); e->mod = e->dalloc<float>((size_t)S * e->ada_all.out); e->xh = e->dalloc<float>((size_t)S * D_FLOW);
+    e->noise_f32 = e->dalloc<float>((size_t)S * LDIM); e->noise_inj = e->dalloc<float>((size_t)S * LDIM); e->latent = e->dalloc<float>((size_t)S * LDIM);
+    e->produced = e->dalloc<int>(S);
+    const size_t MRm = (size_t)S * M_T;
+    e->mx = e->dalloc<float>(MRm * M_DIM); e->mn_bf = e->dalloc<__nv_bfloat16>(MRm * M_DIM); e->mq_bf = e->dalloc<__nv_bfloat16>(MRm * M_DIM);
+    e->matt_bf = e->dalloc<__nv_bfloat16>(MRm * M_DIM); e->mff_bf = e->dalloc<__nv_bfloat16>(MRm * M_FF);
+    e->mrow_slot = e->dalloc<int>(MRm); e->mrow_pos = e->dalloc<int>(MRm); e->mcs = e->dalloc<float2>(MRm * 32);
+    e->buf0 = e->dalloc<__half>((size_t)S * 22 * 512); e->buf2 = e->dalloc<__half>((size_t)S * 17 * e->C2);
+    e->buf3a = e->dalloc<__half>((size_t)S * 98 * 256); e->buf3b = e->dalloc<__half>((size_t)S * 96 * 128);
+    e->buf5 = e->dalloc<__half>((size_t)S * 97 * e->C5); e->buf6a = e->dalloc<__half>((size_t)S * 482 * 128);
+    e->buf6b = e->dalloc<__half>((size_t)S * 480 * 64); e->buf8 = e->dalloc<__half>((size_t)S * 481 * e->C8);
+    e->buf9a = e->dalloc<__half>((size_t)S * 1922 * 64); e->buf9b = e->dalloc<__half>((size_t)S * 1920 * 32);
+    e->buf11 = e->dalloc<__half>((size_t)S * 1922 * 64);
+    e->y3 = e->dalloc<float>((size_t)S * 96 * 256); e->y6 = e->dalloc<float>((size_t)S * 480 * 128); e->y9 = e->dalloc<float>((size_t)S * 1920 * 64);
+    e->pcm = e->dalloc<float>((size_t)S * FRAME);
+    e->shifts.n = 8;
+    e->shifts.d[0] = {e->buf0, 22LL * 512, 6, 16, 512};
+    e->shifts.d[1] = {e->buf2, 17LL * e->C2, 1, 16, e->C2};
+    e->shifts.d[2] = {e->buf3a, 98LL * 256, 2, 96, 256};
+    e->shifts.d[3] = {e->buf5, 97LL * e->C5, 1, 96, e->C5};
+    e->shifts.d[4] = {e->buf6a, 482LL * 128, 2, 480, 128};
+    e->shifts.d[5] = {e->buf8, 481LL * e->C8, 1, 480, e->C8};
+    e->shifts.d[6] = {e->buf9a, 1922LL * 64, 2, 1920, 64};
+    e->shifts.d[7] = {e->buf11, 1922LL * 64, 2, 1920, 64};
+    if (cfg.kv_capacity * sizeof(float) > 48 * 1024) {
+        PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cfg.kv_capacity * sizeof(float))));
+        PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cfg.kv_capacity * sizeof(float))));
+    }
+    PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->finalized = true;
+    return B200_OK;
+}
+
+// ---- ragged FlowLM prefill of `R` rows already staged in pin_i = [slot | pos | token] and (for voice rows) h ----
+static void prefill_rows(b200_engine* e, const std::vector<int>& slots, const std::vector<int>& pos, const std::vector<int>* tokens, const float* x_host) {
+    const int total = (int)slots.size();
+    for (int r0 = 0; r0 < total; r0 += e->cfg.max_prefill_rows) {
+        const int R = std::min(e->cfg.max_prefill_rows, total - r0);
+        e->ensure_pinned(x_host ? (size_t)R * D_MODEL : 1, (size_t)3 * R);
+        for (int i = 0; i < R; i++) { e->pin_i[i] = slots[r0 + i]; e->pin_i[R + i] = pos[r0 + i]; e->pin_i[2 * R + i] = tokens ? (*tokens)[r0 + i] : 0; }
+        PTTS_CUDA_CHECK(cudaMemcpyAsync(e->row_slot, e->pin_i, R * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        PTTS_CUDA_CHECK(cudaMemcpyAsync(e->row_pos, e->pin_i + R, R * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        if (tokens) {
+            PTTS_CUDA_CHECK(cudaMemcpyAsync(e->tok, e->pin_i + 2 * R, R * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+            embed_gather_kernel<<<R, 256, 0, e->stream>>>(e->embed, e->tok, e->h, R);
+            e->launches++;
+        } else {
+            memcpy(e->pin_f, x_host + (size_t)r0 * D_MODEL, (size_t)R * D_MODEL * sizeof(float));
+            PTTS_CUDA_CHECK(cudaMemcpyAsync(e->h, e->pin_f, (size_t)R * D_MODEL * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        }
+        rope_table_kernel<<<(R * 32 + 255) / 256, 256, 0, e->stream>>>(e->row_pos, e->freq_flow, e->cs, R);
+        e->launches++;
+        e->flow_forward(R);
+        PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));   // pinned staging is reused by the next chunk
+    }
+}
+
+int b200_voice_create(b200_engine* e, const float* audio_prompt, int T) {
+    if (!e || !e->finalized || T < 0 || (T > 0 && !audio_prompt)) return B200_EINVAL;
+    if (e->n_voices >= e->cfg.max_voices) return B200_ECAPACITY;
+    if (T > e->cfg.kv_capacity) return B200_ECAPACITY;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const int v = e->n_voices++;
+    const int slot = e->cfg.max_slots + v;
+    std::vector<int> slots(T, slot), pos(T);
+    for (int i = 0; i < T; i++) pos[i] = i;
+    if (T > 0) prefill_rows(e, slots, pos, nullptr, audio_prompt);
+    e->voice_len[v] = T;
+    return v;
+}
+
+int b200_begin_sentences(b200_engine* e, int n, const int32_t* slots, const int32_t* voices, const int32_t* tokens,
+                         const int32_t* tok_off, const int32_t* max_gen_len, const int32_t* frames_after_eos, const float* temp) {
+    if (!e || !e->finalized || n < 0) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const size_t elt = e->cfg.kv_f32 ? 4 : 2;
+    std::vector<int> rs, rp, rt;
+    for (int i = 0; i < n; i++) {
+        const int slot = slots[i], v = voices[i];
+        if (slot < 0 || slot >= e->cfg.max_slots || v < 0 || v >= e->n_voices) return B200_EINVAL;
+        const int nt = tok_off[i + 1] - tok_off[i];
+        const int start = e->voice_len[v];
+        if (start + nt >= e->cfg.kv_capacity) return B200_ECAPACITY;
+        for (int t = 0; t < nt; t++) {
+            const int id = tokens[tok_off[i] + t];
+            if (id < 0 || id >= e->n_embed) return B200_EINVAL;
+            rs.push_back(slot); rp.push_back(start + t); rt.push_back(id);
+        }
+    }
+    const float* bos = e->d_bos;
+    for (int i = 0; i < n; i++) {
+        const int slot = slots[i], v = voices[i];
+        const int nt = tok_off[i + 1] - tok_off[i];
+        const int start = e->voice_len[v];
+        if (start > 0) {
+            const long long bytes = (long long)start * D_MODEL * elt;
+            copy_prefix_kernel<<<dim3(16, 2 * N_LAYERS), 256, 0, e->stream>>>((char*)e->kc, (char*)e->vc, e->kv_slot_stride * elt, e->kv_layer_stride * elt,
+                                                                               slot, e->cfg.max_slots + v, bytes);
+        }
+        reset_slot_kernel<<<dim3(1, e->shifts.n), 256, 0, e->stream>>>(e->shifts, slot, e->e_prev, e->mimi_off);
+        // KV capacity guard (the reference has none: 1000 rows, no bounds check, src/pocket_tts.cpp:367): clamp the cap.
+        int mg = max_gen_len[i];
+        const int room = e->cfg.kv_capacity - (start + nt);
+        if (mg > room) mg = room;
+        set_meta_kernel<<<1, 32, 0, e->stream>>>(slot, start + nt, mg, frames_after_eos[i], temp[i], bos, e->cur_len, e->gen_step, e->eos_step,
+                                                 e->max_gen, e->fae, e->active, e->temp, e->lat_in_bf16, e->lat_f32);
+        e->h_cur_len[slot] = start + nt;
+        e->launches += 3;
+    }
+    if (!rs.empty()) prefill_rows(e, rs, rp, &rt, nullptr);
+    return B200_OK;
+}
+
+int b200_begin_sentence(b200_engine* e, int slot, int voice, const int32_t* tokens, int n_tokens, int max_gen_len, int frames_after_eos, float temp) {
+    const int32_t off[2] = {0, n_tokens};
+    return b200_begin_sentences(e, 1, &slot, &voice, tokens, off, &max_gen_len, &frames_after_eos, &temp);
+}
+
+int b200_step_enqueue(b200_engine* e, int slot0, int n, int use_injected_noise) {
+    if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->step_enqueue(slot0, n, use_injected_noise != 0);
+    return B200_OK;
+}
+
+int b200_sync(b200_engine* e) {
+    if (!e) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    PTTS_CUDA_CHECK(cudaGetLastError());
+    return B200_OK;
+}
+
+int b200_step(b200_engine* e, int slot0, int n, const float* noise, float* pcm, int32_t* produced, float* latents, float* eos_logit) {
+    if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots || !pcm || !produced) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->ensure_pinned((size_t)n * (FRAME + 2 * LDIM + 1), (size_t)std::max(n, 16) * 3);
+    float* p_noise = e->pin_f; float* p_pcm = e->pin_f + (size_t)n * LDIM; float* p_lat = p_pcm + (size_t)n * FRAME; float* p_eos = p_lat + (size_t)n * LDIM;
+    if (noise) {
+        memcpy(p_noise, noise, (size_t)n * LDIM * sizeof(float));
+        PTTS_CUDA_CHECK(cudaMemcpyAsync(e->noise_inj, p_noise, (size_t)n * LDIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    }
+    e->step_enqueue(slot0, n, noise != nullptr);
+    PTTS_CUDA_CHECK(cudaMemcpyAsync(p_pcm, e->pcm + (size_t)slot0 * FRAME, (size_t)n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    PTTS_CUDA_CHECK(cudaMemcpyAsync(e->pin_i, e->produced, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (latents) PTTS_CUDA_CHECK(cudaMemcpyAsync(p_lat, e->latent, (size_t)n * LDIM * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (eos_logit) PTTS_CUDA_CHECK(cudaMemcpyAsync(p_eos, e->eos_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    memcpy(pcm, p_pcm, (size_t)n * FRAME * sizeof(float));
+    for (int i = 0; i < n; i++) { produced[i] = e->pin_i[i]; }
+    if (latents) memcpy(latents, p_lat, (size_t)n * LDIM * sizeof(float));
+    if (eos_logit) memcpy(eos_logit, p_eos, (size_t)n * sizeof(float));
+    return B200_OK;
+}
+
+int b200_mimi_reset(b200_engine* e, int slot0, int n) {
+    if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    for (int s = slot0; s < slot0 + n; s++) reset_slot_kernel<<<dim3(1, e->shifts.n), 256, 0, e->stream>>>(e->shifts, s, e->e_prev, e->mimi_off);
+    e->launches += n;
+    return B200_OK;
+}
+
+int b200_mimi_decode_enqueue(b200_engine* e, int slot0, int n) {
+    if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->prepare_step(slot0, n);
+    e->mimi(slot0, n);
+    return B200_OK;
+}
+
+int b200_mimi_decode(b200_engine* e, int slot0, int n, const float* latents, float* pcm) {
+    if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots || !latents || !pcm) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->ensure_pinned((size_t)n * (FRAME + LDIM), 16);
+    memcpy(e->pin_f, latents, (size_t)n * LDIM * sizeof(float));
+    PTTS_CUDA_CHECK(cudaMemcpyAsync(e->lat_f32 + (size_t)slot0 * LDIM, e->pin_f, (size_t)n * LDIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    e->prepare_step(slot0, n);
+    e->mimi(slot0, n);
+    float* p_pcm = e->pin_f + (size_t)n * LDIM;
+    PTTS_CUDA_CHECK(cudaMemcpyAsync(p_pcm, e->pcm + (size_t)slot0 * FRAME, (size_t)n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    memcpy(pcm, p_pcm, (size_t)n * FRAME * sizeof(float));
+    return B200_OK;
+}
+
+void b200_set_seed(b200_engine* e, uint64_t seed) { if (e) e->seed = seed; }
+
+int b200_slot_position(b200_engine* e, int slot) {
+    if (!e || slot < 0 || slot >= e->cfg.max_slots) return B200_EINVAL;
+    int v = 0;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    PTTS_CUDA_CHECK(cudaMemcpy(&v, e->cur_len + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    return v;
+}
+
+int b200_debug_set_position(b200_engine* e, int slot0, int n, int pos, int max_gen_len) {
+    if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots || pos < 0 || pos + max_gen_len > e->cfg.kv_capacity) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const float* bos = e->d_bos;
+    for (int s = slot0; s < slot0 + n; s++) {
+        reset_slot_kernel<<<dim3(1, e->shifts.n), 256, 0, e->stream>>>(e->shifts, s, e->e_prev, e->mimi_off);
+        set_meta_kernel<<<1, 32, 0, e->stream>>>(s, pos, max_gen_len, 1 << 28, 0.f, bos, e->cur_len, e->gen_step, e->eos_step, e->max_gen, e->fae, e->active,
+                                                 e->temp, e->lat_in_bf16, e->lat_f32);
+    }
+    e->launches += 2 * n;
+    return B200_OK;
+}
+
+// Parity helper: overwrite the backbone input (previous latent) of slots [slot0, slot0+n) — teacher forcing.
+int b200_debug_set_latent(b200_engine* e, int slot0, int n, const float* latents) {
+    if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots || !latents) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    std::vector<__nv_bfloat16> b((size_t)n * LDIM);
+    for (size_t i = 0; i < b.size(); i++) b[i] = __float2bfloat16_rn(latents[i]);
+    PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    PTTS_CUDA_CHECK(cudaMemcpy(e->lat_f32 + (size_t)slot0 * LDIM, latents, (size_t)n * LDIM * sizeof(float), cudaMemcpyHostToDevice));
+    PTTS_CUDA_CHECK(cudaMemcpy(e->lat_in_bf16 + (size_t)slot0 * LDIM, b.data(), b.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    return B200_OK;
+}
+
+// Per-segment device timing. b200_profile(e,1) arms it; after b200_sync, b200_profile_read sums the recorded event
+// pairs per category: 0 FlowLM attention kernel, 1 FlowLM backbone, 2 head, 3 Mimi transformer, 4 SEANet, 5 whole step.
+// out_ms[6], out_count[6]. Reading disarms and clears.
+int b200_profile(b200_engine* e, int on) {
+    if (!e) return B200_EINVAL;
+    e->profiling = on != 0; e->segs.clear(); e->ev_used = 0;
+    return B200_OK;
+}
+int b200_profile_read(b200_engine* e, float* out_ms, int* out_count) {
+    if (!e || !out_ms || !out_count) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < 6; i++) { out_ms[i] = 0.f; out_count[i] = 0; }
+    for (auto& sg : e->segs) {
+        float ms = 0.f;
+        PTTS_CUDA_CHECK(cudaEventElapsedTime(&ms, sg.a, sg.b));
+        if (sg.cat >= 0 && sg.cat < 6) { out_ms[sg.cat] += ms; out_count[sg.cat]++; }
+    }
+    e->profiling = false; e->segs.clear(); e->ev_used = 0;
+    return B200_OK;
+}
+
+void* b200_stream(b200_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+void* b200_device_ptr(b200_engine* e, const char* name) {
+    if (!e || !name) return nullptr;
+    const std::string s = name;
+    if (s == "pcm") return e->pcm;
+    if (s == "latent") return e->latent;
+    if (s == "noise") return e->noise_inj;
+    if (s == "produced") return e->produced;
+    if (s == "eos") return e->eos_out;
+    if (s == "lat_f32") return e->lat_f32;
+    return nullptr;
+}
+
+long long b200_launch_count(b200_engine* e) { return e ? e->launches : 0; }
+
+int b200_read_kv(b200_engine* e, int slot, int layer, int which, int n_pos, float* out) {
+    if (!e || !e->finalized || slot < 0 || slot >= e->total_slots || layer < 0 || layer >= N_LAYERS || n_pos < 0 || n_pos > e->cfg.kv_capacity) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    const size_t n = (size_t)n_pos * D_MODEL;
+    const long long off = layer * e->kv_layer_stride + slot * e->kv_slot_stride;
+    if (e->cfg.kv_f32) {
+        PTTS_CUDA_CHECK(cudaMemcpy(out, (const float*)(which ? e->vc : e->kc) + off, n * 4, cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<uint16_t> tmp(n);
+        PTTS_CUDA_CHECK(cudaMemcpy(tmp.data(), (const __nv_bfloat16*)(which ? e->vc : e->kc) + off, n * 2, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) { uint32_t u = (uint32_t)tmp[i] << 16; memcpy(&out[i], &u, 4); }
+    }
+    return B200_OK;
+}
+
+const char* b200_build_info(void) { return "ptts_b200 sm_100a " __DATE__ " " __TIME__; }
+
+}  // extern "C"

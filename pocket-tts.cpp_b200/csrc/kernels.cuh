@@ -1,0 +1,382 @@
+// Non-GEMM kernels of the per-frame path: row preparation (RoPE tables), LayerNorm(+AdaLN modulate),
+// FlowLM decode/prefill attention, Mimi ring attention, flow-head glue, Mimi front end, state upkeep.
+#pragma once
+#include "common.cuh"
+
+namespace ptts {
+
+// ------------------------------------------------------------------------------------------------
+// Row preparation
+// ------------------------------------------------------------------------------------------------
+// (cos, sin)(pos * freq_i) per row. freq tables are computed on the host exactly like the reference's
+// two RoPE flavours (rope.h:36-38 for FlowLM, ggml_timestep_embedding for Mimi rope.h:8-20).
+__global__ void rope_table_kernel(const int* __restrict__ row_pos, const float* __restrict__ freq, float2* __restrict__ cs, int R) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * 32) return;
+    const float rad = (float)row_pos[idx >> 5] * freq[idx & 31];
+    cs[idx] = make_float2(cosf(rad), sinf(rad));
+}
+
+// Decode step: one FlowLM row and 16 Mimi rows per slot in [slot0, slot0+n).
+__global__ void prepare_step_kernel(int slot0, int n, const int* __restrict__ cur_len, const int* __restrict__ mimi_off,
+                                    int* __restrict__ row_slot, int* __restrict__ row_pos,
+                                    int* __restrict__ mrow_slot, int* __restrict__ mrow_pos) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) { row_slot[idx] = slot0 + idx; row_pos[idx] = cur_len[slot0 + idx]; }
+    if (idx < n * M_T) { const int s = slot0 + idx / M_T; mrow_slot[idx] = s; mrow_pos[idx] = mimi_off[s] + idx % M_T; }
+}
+
+// Text prefill: x[r] = float(embed[token[r]])   (ggml_get_rows, reference conditioners/text.h:29-37)
+__global__ void embed_gather_kernel(const __nv_bfloat16* __restrict__ table, const int* __restrict__ tokens, float* __restrict__ x, int R) {
+    const int r = blockIdx.x;
+    if (r >= R) return;
+    const __nv_bfloat16* src = table + (long long)tokens[r] * D_MODEL;
+    for (int i = threadIdx.x; i < D_MODEL; i += blockDim.x) x[(long long)r * D_MODEL + i] = __bfloat162float(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (ggml_norm: mean, biased variance of deviations, 1/sqrtf(var+eps); reference src/torch.h:49-60,
+// modules/mlp.h:52-64) with optional affine and optional AdaLN modulate y*(1+scale)+shift (mlp.h:3-9).
+// One warp per row; writes a low-precision copy (the A operand of the following GEMM) and/or f32.
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, RowMap xmap, int rps, int R, float eps,
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        const float* __restrict__ shift, const float* __restrict__ scale, int mod_ld,
+                                                        __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= R) return;
+    constexpr int PER = C / 32;
+    const float* xr = x + xmap.off(row, rps);
+    float v[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { v[i] = xr[lane + 32 * i]; s += v[i]; }
+    const float mean = warp_sum(s) / C;
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { v[i] -= mean; s2 += v[i] * v[i]; }
+    const float var = warp_sum(s2) / C;
+    const float rs = 1.0f / sqrtf(var + eps);
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int c = lane + 32 * i;
+        float y = v[i] * rs;
+        if (w) y = y * w[c];
+        if (b) y = y + b[c];
+        if (scale) y = y * (scale[(long long)row * mod_ld + c] + 1.f) + shift[(long long)row * mod_ld + c];
+        if (out_bf16) out_bf16[(long long)row * C + c] = __float2bfloat16_rn(y);
+        if (out_f32) out_f32[(long long)row * C + c] = y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FlowLM attention, one query row against its slot's cache rows [0, pos] (reference
+// modules/transformer.h:157-199, src/torch.h:128-150: scale 1/8, causal by construction, softmax with f32
+// probabilities, f32 PV). One CTA per (row, head). Baseline implementation; see attn_flow_split_kernel.
+// ------------------------------------------------------------------------------------------------
+template <typename KV>
+__global__ void __launch_bounds__(128) attn_flow_kernel(const float* __restrict__ q, const KV* __restrict__ kc, const KV* __restrict__ vc,
+                                                        long long kv_slot_stride, const int* __restrict__ row_slot,
+                                                        const int* __restrict__ row_pos, __nv_bfloat16* __restrict__ out) {
+    extern __shared__ float sc[];                 // [len] scores
+    __shared__ float qs[D_HEAD];
+    __shared__ float red[4];
+    __shared__ float pv[4][D_HEAD];
+    const int row = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int len = row_pos[row] + 1;
+    const KV* K = kc + (long long)row_slot[row] * kv_slot_stride + h * D_HEAD;
+    const KV* V = vc + (long long)row_slot[row] * kv_slot_stride + h * D_HEAD;
+    if (tid < D_HEAD) qs[tid] = q[(long long)row * D_MODEL + h * D_HEAD + tid];
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int j = tid; j < len; j += 128) {
+        const KV* kr = K + (long long)j * D_MODEL;
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < D_HEAD; d += 8) {
+            if constexpr (sizeof(KV) == 2) {
+                const uint4 kv = *reinterpret_cast<const uint4*>(kr + d);
+                const __nv_bfloat16* ke = reinterpret_cast<const __nv_bfloat16*>(&kv);
+#pragma unroll
+                for (int t = 0; t < 8; t++) acc = fmaf(__bfloat162float(ke[t]), qs[d + t], acc);
+            } else {
+                const float4 k0 = *reinterpret_cast<const float4*>(kr + d), k1 = *reinterpret_cast<const float4*>(kr + d + 4);
+                acc = fmaf(k0.x, qs[d], acc); acc = fmaf(k0.y, qs[d + 1], acc); acc = fmaf(k0.z, qs[d + 2], acc); acc = fmaf(k0.w, qs[d + 3], acc);
+                acc = fmaf(k1.x, qs[d + 4], acc); acc = fmaf(k1.y, qs[d + 5], acc); acc = fmaf(k1.z, qs[d + 6], acc); acc = fmaf(k1.w, qs[d + 7], acc);
+            }
+        }
+        acc *= 0.125f;
+        sc[j] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[wid] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = tid; j < len; j += 128) { const float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    if (lane == 0) red[wid] = sum;
+    __syncthreads();
+    const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = wid; j < len; j += 4) {
+        const float p = sc[j] * inv;
+        const KV* vr = V + (long long)j * D_MODEL + 2 * lane;
+        a0 = fmaf(p, to_f32<KV>(vr[0]), a0);
+        a1 = fmaf(p, to_f32<KV>(vr[1]), a1);
+    }
+    pv[wid][2 * lane] = a0; pv[wid][2 * lane + 1] = a1;
+    __syncthreads();
+    if (tid < D_HEAD) {
+        const float o = pv[0][tid] + pv[1][tid] + pv[2][tid] + pv[3][tid];
+        out[(long long)row * D_MODEL + h * D_HEAD + tid] = __float2bfloat16_rn(o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mimi ring attention: 16 queries of one slot x all 250 ring slots, additive 0/-inf bias taken from the
+// reference's pattern (src/torch.h:168-221, called with the chunk's START offset, mimi_transformer.h:1198).
+// mask_mode 0 = reference (non-causal quirk once offset > 250), 1 = ideal causal ring.
+// q (bf16), K/V ring (bf16), probabilities rounded to bf16 (ggml bf16 mul_mat), f32 accumulation.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool mimi_masked(int offset, int j, int c, int mask_mode) {
+    if (mask_mode == 1) {
+        const int last = offset + M_T - 1;
+        const int p = last - (((last - c) % M_CTX + M_CTX) % M_CTX);   // newest position living in ring slot c
+        return p < 0 || p > offset + j;
+    }
+    const int start = M_CTX * 2 - M_T;                                   // 484
+    const int idx = (offset <= M_CTX ? start - offset : M_CTX - (offset % M_CTX)) + c;
+    return idx >= start + 1 + j || (idx <= M_CTX - 1 && idx > M_CTX - 1 - (M_T - j - 1));
+}
+
+__global__ void __launch_bounds__(128) attn_mimi_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
+                                                        const __nv_bfloat16* __restrict__ vc, long long kv_slot_stride, int slot0,
+                                                        const int* __restrict__ mimi_off, int mask_mode, __nv_bfloat16* __restrict__ out) {
+    __shared__ float sc[4][M_CTX + 6];
+    __shared__ float qs[4][D_HEAD];
+    const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int slot = slot0 + b;
+    const int offset = mimi_off[slot];
+    const __nv_bfloat16* K = kc + (long long)slot * kv_slot_stride + h * D_HEAD;
+    const __nv_bfloat16* V = vc + (long long)slot * kv_slot_stride + h * D_HEAD;
+    for (int t = wid; t < M_T; t += 4) {
+        const long long row = (long long)b * M_T + t;
+        qs[wid][lane] = __bfloat162float(q[row * M_DIM + h * D_HEAD + lane]);
+        qs[wid][lane + 32] = __bfloat162float(q[row * M_DIM + h * D_HEAD + lane + 32]);
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int c = lane; c < M_CTX; c += 32) {
+            float s = -INFINITY;
+            if (!mimi_masked(offset, t, c, mask_mode)) {
+                const __nv_bfloat16* kr = K + (long long)c * M_DIM;
+                float acc = 0.f;
+#pragma unroll
+                for (int d = 0; d < D_HEAD; d += 8) {
+                    const uint4 kv = *reinterpret_cast<const uint4*>(kr + d);
+                    const __nv_bfloat16* ke = reinterpret_cast<const __nv_bfloat16*>(&kv);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) acc = fmaf(__bfloat162float(ke[u]), qs[wid][d + u], acc);
+                }
+                s = acc * 0.125f;
+            }
+            sc[wid][c] = s;
+            mx = fmaxf(mx, s);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int c = lane; c < M_CTX; c += 32) { const float e = expf(sc[wid][c] - mx); sc[wid][c] = e; sum += e; }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        __syncwarp();
+        float a0 = 0.f, a1 = 0.f;
+        for (int c = 0; c < M_CTX; c++) {
+            const float e = sc[wid][c];
+            if (e != 0.f) {
+                const float p = __bfloat162float(__float2bfloat16_rn(e * inv));
+                const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(V + (long long)c * M_DIM + 2 * lane);
+                a0 = fmaf(p, __bfloat162float(vv.x), a0);
+                a1 = fmaf(p, __bfloat162float(vv.y), a1);
+            }
+        }
+        *reinterpret_cast<__nv_bfloat162*>(out + row * M_DIM + h * D_HEAD + 2 * lane) = __floats2bfloat162_rn(a0, a1);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flow head glue
+// ------------------------------------------------------------------------------------------------
+// c = LN(h; out_norm) (bf16 copy for cond_embed) and EOS logit = out_eos(bf16(c)) + bias + 4
+// (reference models/flow_lm.h:114-129). One warp per row.
+__global__ void __launch_bounds__(256) head_pre_kernel(const float* __restrict__ h, int R, const float* __restrict__ w, const float* __restrict__ b,
+                                                       const __nv_bfloat16* __restrict__ w_eos, const float* __restrict__ b_eos,
+                                                       __nv_bfloat16* __restrict__ c_bf16, float* __restrict__ eos) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= R) return;
+    constexpr int PER = D_MODEL / 32;
+    const float* xr = h + (long long)row * D_MODEL;
+    float v[PER]; float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { v[i] = xr[lane + 32 * i]; s += v[i]; }
+    const float mean = warp_sum(s) / D_MODEL;
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { v[i] -= mean; s2 += v[i] * v[i]; }
+    const float rs = 1.0f / sqrtf(warp_sum(s2) / D_MODEL + 1e-5f);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int c = lane + 32 * i;
+        float y = v[i] * rs * w[c];
+        if (b) y += b[c];
+        const __nv_bfloat16 yb = __float2bfloat16_rn(y);
+        c_bf16[(long long)row * D_MODEL + c] = yb;
+        dot = fmaf(__bfloat162float(yb), __bfloat162float(w_eos[c]), dot);
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) eos[row] = dot + (b_eos ? b_eos[0] : 0.f) + 4.0f;
+}
+
+// noise -> (f32, bf16) per row. Noise is either injected by the caller (identical-noise parity runs, the
+// reference's injection point is GraphContext::normal_, src/context.h:465-509) or drawn on the device from a
+// counter-based generator keyed by (seed, slot, generation step): Philox-4x32-10 + Box-Muller, std = sqrt(temp).
+__device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void noise_kernel(int slot0, int n, const float* __restrict__ injected, unsigned long long seed, const float* __restrict__ temp,
+                             const int* __restrict__ gen_step, float* __restrict__ noise_f32, __nv_bfloat16* __restrict__ noise_bf16) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * LDIM) return;
+    const int r = idx / LDIM, i = idx % LDIM, slot = slot0 + r;
+    float z;
+    if (injected) {
+        z = injected[idx];
+    } else {
+        const float std = sqrtf(temp[slot]);
+        if (std == 0.f) z = 0.f;
+        else {
+            uint32_t o[4];
+            philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)slot, (uint32_t)gen_step[slot], (uint32_t)(i >> 1), 0x5054545Au, o);
+            const float u1 = ((float)(o[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            const float u2 = ((float)(o[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            const float rad = sqrtf(-2.0f * logf(u1));
+            float sn, cn; sincosf(6.28318530717958647692f * u2, &sn, &cn);
+            z = ((i & 1) ? rad * sn : rad * cn) * std;
+        }
+    }
+    noise_f32[idx] = z;
+    noise_bf16[idx] = __float2bfloat16_rn(z);
+}
+
+// Stop rule + bookkeeping after the head (reference src/pocket_tts.cpp:457-467,487-489). Per slot:
+//   eos_step = first step with logit+4 > 0; stop when gen_step >= eos_step + frames_after_eos; hard cap max_gen_len.
+// produced[r] = 1 when this step emits a frame. Also hands the new latent to the next step (bf16 copy = the
+// A operand of input_linear) and advances the FlowLM position.
+__global__ void step_logic_kernel(int slot0, int n, const float* __restrict__ eos, const float* __restrict__ latent,
+                                  int* __restrict__ cur_len, int* __restrict__ gen_step, int* __restrict__ eos_step,
+                                  const int* __restrict__ max_gen, const int* __restrict__ fae, int* __restrict__ active,
+                                  __nv_bfloat16* __restrict__ lat_in_bf16, float* __restrict__ lat_f32, int* __restrict__ produced,
+                                  float* __restrict__ eos_out) {
+    const int r = blockIdx.x, slot = slot0 + r, i = threadIdx.x;
+    if (r >= n) return;
+    __shared__ int emit;
+    if (i == 0) {
+        int e = 0;
+        if (active[slot]) {
+            const int g = gen_step[slot];
+            int es = eos_step[slot];
+            if (eos[r] > 0.f && es == -1) es = g;
+            eos_step[slot] = es;
+            cur_len[slot] += 1;                                   // increment_states (pocket_tts.cpp:96)
+            if (es != -1 && g >= es + fae[slot]) { gen_step[slot] = max_gen[slot]; active[slot] = 0; }
+            else {
+                e = 1; gen_step[slot] = g + 1;
+                if (g + 1 >= max_gen[slot]) active[slot] = 0;     // next receive would hit the cap (pocket_tts.cpp:450-453,495)
+            }
+        }
+        emit = e; produced[r] = e; if (eos_out) eos_out[r] = eos[r];
+    }
+    __syncthreads();
+    if (emit && i < LDIM) {
+        const float v = latent[r * LDIM + i];
+        lat_f32[slot * LDIM + i] = v;
+        lat_in_bf16[slot * LDIM + i] = __float2bfloat16_rn(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mimi front end: z = latent*emb_std + emb_mean; e = Wq . f16(z) (1x1 conv, f16 operands; reference
+// src/pocket_tts.cpp:472-478, models/mimi.h:77-83); depthwise x16 upsampler on one step with carried state
+// (modules/conv.h:283-331): x[k][c] = e[c]*w[c][k] + e_prev[c]*w[c][16+k] (+bias). State kept = e_prev.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) mimi_front_kernel(int slot0, const float* __restrict__ lat_f32, const float* __restrict__ emb_std,
+                                                         const float* __restrict__ emb_mean, const __half* __restrict__ wq,
+                                                         const float* __restrict__ wup, const float* __restrict__ bup,
+                                                         float* __restrict__ e_prev, float* __restrict__ x) {
+    __shared__ float z[LDIM];
+    const int slot = slot0 + blockIdx.x, c = threadIdx.x;
+    if (c < LDIM) z[c] = __half2float(__float2half_rn(__fadd_rn(__fmul_rn(emb_std[c], lat_f32[slot * LDIM + c]), emb_mean[c])));
+    __syncthreads();
+    float e = 0.f;
+#pragma unroll
+    for (int i = 0; i < LDIM; i++) e = fmaf(__half2float(wq[c * LDIM + i]), z[i], e);
+    const float ep = e_prev[(long long)slot * M_DIM + c];
+    e_prev[(long long)slot * M_DIM + c] = e;
+    const float bias = bup ? bup[c] : 0.f;
+    float* xo = x + (long long)slot * M_T * M_DIM + c;
+#pragma unroll
+    for (int k = 0; k < M_T; k++) {
+        const float y = __fadd_rn(__fmul_rn(e, wup[c * 32 + k]), __fmul_rn(ep, wup[c * 32 + 16 + k]));
+        xo[(long long)k * M_DIM] = y + bias;
+    }
+}
+
+// f32 [rows][C] -> f16 copy into a conv input buffer (rows placed after the state rows).
+__global__ void cast_f16_kernel(const float* __restrict__ x, RowMap xmap, __half* __restrict__ out, RowMap omap, int rps, int R, int C) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)R * C) return;
+    const int row = (int)(idx / C), col = (int)(idx % C);
+    out[omap.off(row, rps) + col] = __float2half_rn(x[xmap.off(row, rps) + col]);
+}
+
+// End-of-step upkeep for the streaming convs: every conv input buffer is [slot][S + T][C] with the S carried
+// rows first (reference modules/conv.h:60-76 keeps the last K-stride inputs; the transposed convs keep the last
+// input row instead of the reference's partial output). Copies the last S rows to the front.
+struct ShiftDesc { __half* buf; long long slot_stride; int S, T, C; };
+struct ShiftAll { ShiftDesc d[8]; int n; };
+__global__ void shift_states_kernel(ShiftAll sa, int slot0, int* __restrict__ mimi_off) {
+    const ShiftDesc d = sa.d[blockIdx.y];
+    const int slot = slot0 + blockIdx.x;
+    __half* base = d.buf + (long long)slot * d.slot_stride;
+    const int n = d.S * d.C;
+    // source rows [T, T+S) and destination rows [0, S) never overlap because T >= S for every conv here.
+    for (int i = threadIdx.x; i < n; i += blockDim.x) base[i] = base[(long long)d.T * d.C + i];
+    if (blockIdx.y == 0 && threadIdx.x == 0) mimi_off[slot] += M_T;
+}
+
+// Sentence start (reference src/pocket_tts.cpp:416-444, models/mimi.h:71-75): zero the carried conv state rows
+// and the upsampler state, reset the Mimi offset. The KV prefix restore is done with device copies by the host.
+__global__ void reset_slot_kernel(ShiftAll sa, int slot, float* __restrict__ e_prev, int* __restrict__ mimi_off) {
+    const ShiftDesc d = sa.d[blockIdx.y];
+    __half* base = d.buf + (long long)slot * d.slot_stride;
+    for (int i = threadIdx.x; i < d.S * d.C; i += blockDim.x) base[i] = __float2half_rn(0.f);
+    if (blockIdx.y == 0) {
+        for (int i = threadIdx.x; i < M_DIM; i += blockDim.x) e_prev[(long long)slot * M_DIM + i] = 0.f;
+        if (threadIdx.x == 0) mimi_off[slot] = 0;
+    }
+}
+
+}  // namespace ptts

@@ -1,0 +1,47 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/ptts_b200.h declares, plus the
+reference's ten C++ API functions under their original mangled names (drop-in for demos/pocket-tts.cpp)."""
+import ctypes
+import os
+import re
+import subprocess
+
+from conftest import REPO
+
+REFERENCE_MANGLED = [
+    "_Z13ptts_set_seedj", "_Z13ptts_get_seedv", "_Z9ptts_initP12ggml_backendS0_PKc", "_Z20ptts_get_sample_rateP14ptts_context_t",
+    "_Z19ptts_get_frame_sizeP14ptts_context_t", "_Z28ptts_stream_from_safetensorsP14ptts_context_tPKcf",
+    "_Z17ptts_stream_resetP13ptts_stream_t", "_Z17ptts_stream_flushP13ptts_stream_t",
+    "_Z16ptts_stream_sendP13ptts_stream_tPKc", "_Z19ptts_stream_receiveP13ptts_stream_tPf",
+]
+
+
+def test_exports(P):
+    hdr = open(os.path.join(REPO, "include", "ptts_b200.h")).read()
+    names = re.findall(r"B200_API\s+[\w\s\*]+?\b(\w+)\s*\(", hdr)
+    assert len(names) > 40
+    L = ctypes.CDLL(P.LIB_PATH)
+    for n in names + REFERENCE_MANGLED:
+        assert hasattr(L, n), n
+
+
+def test_loads_without_gpu_and_fails_loudly(P):
+    import torch
+    if torch.cuda.is_available():
+        return
+    cfg = P.default_config(max_slots=1)
+    h = ctypes.c_void_p()
+    rc = P.lib().b200_engine_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc != 0 and not h.value          # no CUDA device -> error, never a CPU fallback
+
+
+def test_constants(P):
+    assert P.FRAME == 1920 and P.SAMPLE_RATE == 24000
+
+
+def test_product_never_touches_oracle():
+    pkg = os.path.join(REPO, "pocket-tts.cpp_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                src = open(os.path.join(root, f), errors="ignore").read()
+                assert "oracle" not in src.replace("no CPU fallback", ""), os.path.join(root, f)

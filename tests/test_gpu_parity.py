@@ -1,0 +1,190 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Everything goes through the C ABI of libptts_b200.so.
+
+Tolerances (north_star: bit-exact ids / frame counts; latents max-abs + relative error; waveform SNR >= 40 dB):
+  * latents: max-abs <= 6e-2 (latent scale ~4), relative L2 <= 2e-2 per frame  — two *correct* implementations of this
+    bf16/f16 pipeline already differ by ~1.5e-2 max-abs through rounding flips (see tests/test_oracle.py)
+  * waveform: SNR >= 40 dB per frame against the oracle under identical injected noise
+Free-running comparisons use injected noise (temp 0.7): with temp 0 and RANDOM weights the latent feedback loop is
+chaotic (any two implementations diverge after ~10 frames), so the temp-0 --bench configuration is compared
+teacher-forced (oracle latents fed to both) and on its first frames against the golden fixture.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import BENCH_SENTENCE, REPO, snr_db
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(REPO, "tests", "golden")
+LAT_MAXABS, LAT_REL, SNR_MIN = 6e-2, 2e-2, 40.0
+
+
+@pytest.fixture(scope="module")
+def ctx(P, model_dir):
+    return P.Context(model_dir, max_slots=8, kv_capacity=1024)
+
+
+@pytest.fixture(scope="module")
+def ctx_f32kv(P, model_dir):
+    return P.Context(model_dir, max_slots=2, kv_capacity=1024, kv_f32=1, gemm_path=1)
+
+
+def _begin(ctx, oracle_mod, st, text, temp):
+    toks = ctx.tokenize(text)
+    ctx.engine.begin_sentence(st.slot, st.voice, toks, oracle_mod.max_gen_len_for(text), oracle_mod.frames_after_eos_guess(text), temp)
+    return toks
+
+
+def test_token_ids_bit_exact(ctx, orc):
+    g = json.load(open(os.path.join(GOLD, "text_golden.json")))
+    for text, ids in g["token_ids"].items():
+        assert ctx.tokenize(text) == ids == orc.tokenizer.encode(text)
+
+
+@pytest.mark.parametrize("which", ["bf16kv", "f32kv"])
+def test_prefill_kv_and_free_running_noise(which, ctx, ctx_f32kv, orc, oracle_mod):
+    c = ctx if which == "bf16kv" else ctx_f32kv
+    st = c.stream("cosette", temp=0.7)
+    toks = _begin(c, oracle_mod, st, BENCH_SENTENCE, 0.7)
+    os_ = orc.stream("cosette", kv_capacity=1024)
+    assert os_.sentence_init(BENCH_SENTENCE) == toks
+    n_pos = os_.current_end
+    assert c.engine.slot_position(st.slot) == n_pos                     # voice-embedding indexing / positions bit-exact
+    tol = 3e-2 if which == "f32kv" else 6e-2                            # bf16 cache adds 2^-9 relative rounding
+    for layer in (0, 3, 5):
+        for kv in (0, 1):
+            assert np.abs(c.engine.read_kv(st.slot, layer, kv, n_pos) - os_.kv(layer, kv)).max() < tol
+    rng = np.random.default_rng(0)
+    for i in range(24):
+        noise = (rng.standard_normal(32) * np.sqrt(0.7)).astype(np.float32)
+        ok, lat, pcm, e = os_.step(noise)
+        gp, prod, glat, geos = c.engine.step(st.slot, 1, noise[None])
+        assert ok and prod[0] == 1
+        assert np.abs(glat[0] - lat).max() < LAT_MAXABS, i
+        assert np.linalg.norm(glat[0] - lat) / np.linalg.norm(lat) < LAT_REL, i
+        assert abs(geos[0] - e) < 5e-2
+        assert snr_db(pcm, gp[0]) > SNR_MIN, i
+
+
+def test_bench_config_temp0_teacher_forced_and_golden(ctx, orc, oracle_mod):
+    g = np.load(os.path.join(GOLD, "bench_temp0.npz"))
+    st = ctx.stream("cosette", temp=0.0)
+    _begin(ctx, oracle_mod, st, BENCH_SENTENCE, 0.0)
+    os_ = orc.stream("cosette", kv_capacity=1024)
+    os_.sentence_init(BENCH_SENTENCE)
+    for i in range(40):
+        ok, lat, pcm, e = os_.step(None)
+        gp, prod, glat, geos = ctx.engine.step(st.slot, 1, None)
+        assert ok and prod[0] == 1
+        assert np.abs(glat[0] - lat).max() < LAT_MAXABS, i
+        assert np.linalg.norm(glat[0] - lat) / np.linalg.norm(lat) < LAT_REL, i
+        if i == 0:
+            assert np.abs(glat[0] - g["latents"][0]).max() < LAT_MAXABS
+            assert snr_db(g["pcm_full_frame0"], gp[0]) > SNR_MIN
+        # Mimi is compared on the SAME latent stream: decode the oracle latent on the engine as well
+        ctx.engine.debug_set_latent(st.slot, 1, lat[None])               # teacher forcing for the next FlowLM step
+
+
+def test_mimi_only_40_frames(ctx, orc):
+    """BASELINE config 3 shape: synthetic latents -> PCM; 40 frames crosses the ring wrap and the offset>250 mask regime."""
+    rng = np.random.default_rng(1)
+    lats = rng.standard_normal((40, 32)).astype(np.float32)
+    s = orc.stream("cosette", kv_capacity=256)
+    s.mimi_reset()
+    ctx.engine.mimi_reset(4, 3)
+    for f in range(40):
+        ref = s.mimi_frame(lats[f])
+        got = ctx.engine.mimi_decode(4, 3, np.stack([lats[f]] * 3))
+        assert snr_db(ref, got[0]) > 55.0, f
+        assert np.array_equal(got[0], got[1]) and np.array_equal(got[0], got[2])      # batch rows are independent + deterministic
+
+
+def test_frame_counts_bit_exact(P, model_dir_eos, orc_eos, oracle_mod):
+    counts = json.load(open(os.path.join(GOLD, "frame_counts_eos_mid.json")))
+    c = P.Context(model_dir_eos, max_slots=2, kv_capacity=1024)
+    st = c.stream("cosette", temp=0.7)
+    for text, info in counts.items():
+        _begin(c, oracle_mod, st, text, 0.7)
+        rng = np.random.default_rng(info["seed"])
+        n = 0
+        while True:
+            noise = (rng.standard_normal(32) * np.sqrt(0.7)).astype(np.float32)
+            gp, prod, glat, geos = c.engine.step(st.slot, 1, noise[None])
+            if not prod[0]:
+                break
+            n += 1
+            assert n <= info["max_gen_len"]
+        assert n == info["frames"], text
+
+
+def test_batched_equals_single(ctx, oracle_mod):
+    """Utterances are independent: a ragged batch of 4 sentences gives the same frames as each sentence alone."""
+    texts = ["Hello world.", BENCH_SENTENCE, "One two three four five six seven eight nine ten eleven twelve.", "Short one."]
+    eng = ctx.engine
+    st = ctx.stream("cosette", temp=0.7)
+    voice = st.voice
+    toks = [ctx.tokenize(t) for t in texts]
+    mg = [oracle_mod.max_gen_len_for(t) for t in texts]
+    fae = [oracle_mod.frames_after_eos_guess(t) for t in texts]
+    rng = np.random.default_rng(7)
+    noise = (rng.standard_normal((6, 4, 32)) * np.sqrt(0.7)).astype(np.float32)
+    eng.begin_sentences([0, 1, 2, 3], [voice] * 4, toks, mg, fae, [0.7] * 4)
+    batch = [eng.step(0, 4, noise[i]) for i in range(6)]
+    for k in range(4):
+        eng.begin_sentence(5, voice, toks[k], mg[k], fae[k], 0.7)
+        for i in range(6):
+            pcm, prod, lat, eos = eng.step(5, 1, noise[i, k][None])
+            assert prod[0] == batch[i][1][k] == 1
+            assert np.abs(lat[0] - batch[i][2][k]).max() < 2e-2           # different GEMM kernels (GEMV vs tile) at different batch sizes
+            assert snr_db(batch[i][0][k], pcm[0]) > 45.0
+
+
+def test_stream_api_matches_reference_driver_loop(P, model_dir, orc, oracle_mod):
+    """The reference's own call sequence (demos/pocket-tts.cpp:456-520): feed 15 chars at a time, poll receive."""
+    c = P.Context(model_dir, max_slots=1, kv_capacity=1024)
+    P.set_seed(0)
+    st = c.stream("cosette", temp=0.0)
+    text = "Hello there. How are you?"
+    frames = []
+    rest = text
+    active = True
+    while active:
+        active = False
+        if rest:
+            st.send(rest[:15]); rest = rest[15:]
+            if not rest:
+                st.flush()
+            active = True
+        f = st.receive()
+        if f is not None:
+            frames.append(f); active = True
+    # never-EOS checkpoint: each sentence runs to its cap int((words+2)*12.5)  (src/pocket_tts.cpp:429-430)
+    sp = oracle_mod.StrProcessor(); sp.ingest(text); sp.flush()
+    want = sum(oracle_mod.max_gen_len_for(s) for s in sp.sentences)
+    assert len(frames) == want
+    # first frame of the first sentence == oracle
+    os_ = orc.stream("cosette", kv_capacity=1024)
+    os_.sentence_init(sp.sentences[0])
+    ok, lat, pcm, e = os_.step(None)
+    assert snr_db(pcm, frames[0]) > SNR_MIN
+    assert P.get_seed() == 0 and c.sample_rate == 24000 and c.frame_size == 1920
+
+
+def test_device_rng_statistics(ctx, oracle_mod):
+    """temp > 0 without injected noise: counter-based device RNG, seeded, reproducible, N(0, temp)."""
+    st = ctx.stream("cosette", temp=0.7)
+    eng = ctx.engine
+    import ctypes
+    outs = []
+    for rep in range(2):
+        eng.set_seed(1234)
+        _begin(ctx, oracle_mod, st, BENCH_SENTENCE, 0.7)
+        pcm, prod, lat, eos = eng.step(st.slot, 1, None)
+        outs.append(lat.copy())
+    assert np.array_equal(outs[0], outs[1])
+    eng.set_seed(99)
+    _begin(ctx, oracle_mod, st, BENCH_SENTENCE, 0.7)
+    pcm, prod, lat2, eos = eng.step(st.slot, 1, None)
+    assert not np.array_equal(outs[0], lat2)

@@ -308,10 +308,10 @@ def make_model_dir(out_dir: str, seed: int = 1234, dtype: str = "BF16", eos_mode
     return out_dir + "/"
 
 
-def default_model_dir(eos_mode: str = "never", dtype: str = "BF16", t_voice: int = 125, seed: int = 1234) -> str:
+def default_model_dir(eos_mode: str = "never", dtype: str = "BF16", t_voice: int = 125, seed: int = 1234, voices=None) -> str:
     root = os.environ.get("PTTS_B200_ASSETS", "/tmp/ptts_b200_assets")
-    name = f"model_s{seed}_{dtype.lower()}_{eos_mode}_v{t_voice}"
-    return make_model_dir(os.path.join(root, name), seed=seed, dtype=dtype, eos_mode=eos_mode, t_voice=t_voice)
+    name = f"model_s{seed}_{dtype.lower()}_{eos_mode}_v{t_voice}" + ("" if voices is None else "_" + "-".join(voices))
+    return make_model_dir(os.path.join(root, name), seed=seed, dtype=dtype, eos_mode=eos_mode, t_voice=t_voice, voices=voices)
 
 
 if __name__ == "__main__":
