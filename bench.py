@@ -210,6 +210,8 @@ def main():
     sampler = ClockSampler(local); sampler.start()
     barrier()
     l0 = eng.launch_count()
+    if rank == 0:
+        print(f"[bench] launches_before_timed_region={l0}", file=sys.stderr, flush=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
     for _ in range(args.steps):
