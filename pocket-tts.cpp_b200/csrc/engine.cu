@@ -137,12 +137,14 @@ struct b200_engine {
         return L;
     }
     // causal conv (torch [co][ci][k]) -> f16 [co][k*ci]  (loader policy: ggml_conv_1d weights F16, src/loader.h:209)
-    ConvW up_conv(const std::string& p, int co, int ci, int k) {
+    // ci_pad > ci zero-pads the input-channel axis (the activation buffer is padded likewise) so that K % 64 == 0.
+    ConvW up_conv(const std::string& p, int co, int ci, int k, int ci_pad = 0) {
         auto* w = find(p + ".conv.weight");
-        std::vector<__half> o((size_t)co * k * ci);
+        const int cp = ci_pad > ci ? ci_pad : ci;
+        std::vector<__half> o((size_t)co * k * cp, __float2half_rn(0.f));
         for (int a = 0; a < co; a++) for (int b = 0; b < ci; b++) for (int c = 0; c < k; c++)
-            o[((size_t)a * k + c) * ci + b] = __float2half_rn(w->f[((size_t)a * ci + b) * k + c]);
-        ConvW C; C.N = co; C.K = k * ci; C.w = upload(o); C.b = up_f32(p + ".conv.bias", false);
+            o[((size_t)a * k + c) * cp + b] = __float2half_rn(w->f[((size_t)a * ci + b) * k + c]);
+        ConvW C; C.N = co; C.K = k * cp; C.w = upload(o); C.b = up_f32(p + ".conv.bias", false);
         return C;
     }
     // transposed conv K = 2s (torch [ci][co][k]) as a 2-tap GEMM over [prev row | current row]:
@@ -267,7 +269,7 @@ struct b200_engine {
         // SEANet (reference modules/seanet.h:187-211); every conv is a GEMM over overlapping channel-last rows.
         const int T0 = 16, T1 = 96, T2 = 480, T3 = 1920;
         const long long s0 = 22LL * 512, s2 = 17LL * C2, s3a = 98LL * 256, s3b = 96LL * 128, s5 = 97LL * C5, s6a = 482LL * 128, s6b = 480LL * 64,
-                        s8 = 481LL * C8, s9a = 1922LL * 64, s9b = 1920LL * 32, s11 = 1922LL * 64;
+                        s8 = 481LL * C8, s9a = 1922LL * 64, s9b = 1920LL * 64, s11 = 1922LL * 64;
         const int o2t = cfg.convt_split ? OUT2_F16_SPLIT : OUT2_F16;
         {
             const long long tot = (long long)R * M_DIM;
@@ -294,11 +296,11 @@ struct b200_engine {
         { Epi e; e.rps = T2; e.bias = t8.b; e.out = y9 + slot0 * 1920LL * 64; e.out_map = smap(1920LL * 64, 256, 0);
           e.act = ACT_ELU; e.out2 = buf9a + slot0 * s9a; e.out2_map = smap(s9a, 256, 2 * 64); e.out2_type = OUT2_F16;
           gemm<__half>(buf8 + slot0 * s8, smap(s8, C8, 0), T2, t8.w, n * T2, t8.N, t8.K, e); }
-        { Epi e; e.rps = T3; e.bias = r9a.b; e.act = ACT_ELU; e.out2 = buf9b + slot0 * s9b; e.out2_map = smap(s9b, 32, 0); e.out2_type = OUT2_F16;
+        { Epi e; e.rps = T3; e.bias = r9a.b; e.act = ACT_ELU; e.out2 = buf9b + slot0 * s9b; e.out2_map = smap(s9b, 64, 0); e.out2_type = OUT2_F16;
           gemm<__half>(buf9a + slot0 * s9a, smap(s9a, 64, 0), T3, r9a.w, n * T3, r9a.N, r9a.K, e); }
         { Epi e; e.rps = T3; e.bias = r9b.b; e.resid = y9 + slot0 * 1920LL * 64; e.resid_map = smap(1920LL * 64, 64, 0);
           e.act = ACT_ELU; e.out2 = buf11 + slot0 * s11; e.out2_map = smap(s11, 64, 2 * 64); e.out2_type = OUT2_F16;
-          gemm<__half>(buf9b + slot0 * s9b, smap(s9b, 32, 0), T3, r9b.w, n * T3, r9b.N, r9b.K, e); }
+          gemm<__half>(buf9b + slot0 * s9b, smap(s9b, 64, 0), T3, r9b.w, n * T3, r9b.N, r9b.K, e); }
         {
             const int Rr = n * T3;
             conv_n1_kernel<<<(Rr + 7) / 8, 256, 0, stream>>>(buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm + (long long)slot0 * FRAME);
@@ -511,7 +513,7 @@ int b200_finalize_weights(b200_engine* e) {
     e->t5 = e->up_convt(d + "5", 256, 128, 10, 5, e->C5);
     e->r6a = e->up_conv(d + "6.block.1", 64, 128, 3); e->r6b = e->up_conv(d + "6.block.3", 128, 64, 1);
     e->t8 = e->up_convt(d + "8", 128, 64, 8, 4, e->C8);
-    e->r9a = e->up_conv(d + "9.block.1", 32, 64, 3); e->r9b = e->up_conv(d + "9.block.3", 64, 32, 1);
+    e->r9a = e->up_conv(d + "9.block.1", 32, 64, 3); e->r9b = e->up_conv(d + "9.block.3", 64, 32, 1, 64);
     e->c11 = e->up_conv(d + "11", 1, 64, 3);
     {
         std::vector<float> ff(32), fm(32);
@@ -553,7 +555,7 @@ int b200_finalize_weights(b200_engine* e) {
     e->buf3a = e->dalloc<__half>((size_t)S * 98 * 256); e->buf3b = e->dalloc<__half>((size_t)S * 96 * 128);
     e->buf5 = e->dalloc<__half>((size_t)S * 97 * e->C5); e->buf6a = e->dalloc<__half>((size_t)S * 482 * 128);
     e->buf6b = e->dalloc<__half>((size_t)S * 480 * 64); e->buf8 = e->dalloc<__half>((size_t)S * 481 * e->C8);
-    e->buf9a = e->dalloc<__half>((size_t)S * 1922 * 64); e->buf9b = e->dalloc<__half>((size_t)S * 1920 * 32);
+    e->buf9a = e->dalloc<__half>((size_t)S * 1922 * 64); e->buf9b = e->dalloc<__half>((size_t)S * 1920 * 64);   // 32 channels zero-padded to 64 (K % 64 == 0 for the tensor-core path)
     e->buf11 = e->dalloc<__half>((size_t)S * 1922 * 64);
     e->y3 = e->dalloc<float>((size_t)S * 96 * 256); e->y6 = e->dalloc<float>((size_t)S * 480 * 128); e->y9 = e->dalloc<float>((size_t)S * 1920 * 64);
     e->pcm = e->dalloc<float>((size_t)S * FRAME);
