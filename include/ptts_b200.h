@@ -89,6 +89,11 @@ B200_API void b200_set_seed(b200_engine* e, uint64_t seed);
 B200_API int  b200_slot_position(b200_engine* e, int slot);        /* FlowLM current_end of a slot (host mirror) */
 /* Force every slot in the range to position `pos` with an active, never-ending sentence (bench: KV length control). */
 B200_API int  b200_debug_set_position(b200_engine* e, int slot0, int n, int pos, int max_gen_len);
+/* Unit-test hook for the GEMM family (tests/test_gpu_gemm.py): out[n_slots*T][N] = windows(A) . W^T (+bias); A is
+ * [n_slots][rows_buf][C] f32 (rounded to bf16, or f16 when f16 != 0), window of output row (slot,t) = rows t..t+taps-1.
+ * path 0 = dispatcher, 1 = CUDA-core. Returns 1 when the tcgen05 kernel ran, 0 for a CUDA-core kernel, <0 on error. */
+B200_API int  b200_debug_gemm(b200_engine* e, int f16, const float* A, int n_slots, int rows_buf, int C, int T, int taps, const float* W, int N,
+                              const float* bias, int path, float* out, float* out2_as_f32);
 /* Parity helper (teacher forcing): overwrite the backbone input latent [n][32] of slots [slot0, slot0+n). */
 B200_API int  b200_debug_set_latent(b200_engine* e, int slot0, int n, const float* latents);
 /* Per-segment device timing with CUDA events on the engine stream (bench.py roofline leg). Categories: 0 FlowLM attention

@@ -65,6 +65,7 @@ def lib():
         "b200_slot_position": (ci, [vp, ci]),
         "b200_debug_set_position": (ci, [vp, ci, ci, ci, ci]),
         "b200_debug_set_latent": (ci, [vp, ci, ci, fp]),
+        "b200_debug_gemm": (ci, [vp, ci, fp, ci, ci, ci, ci, ci, fp, ci, fp, ci, fp, fp]),
         "b200_profile": (ci, [vp, ci]),
         "b200_profile_read": (ci, [vp, fp, ip]),
         "b200_stream": (vp, [vp]),
@@ -207,6 +208,21 @@ class Engine:
         rc = self.L.b200_debug_set_position(self.h, slot0, n, pos, max_gen_len)
         if rc != 0:
             raise RuntimeError(f"b200_debug_set_position failed: {rc}")
+
+    def debug_gemm(self, A, W, T, taps, f16=False, bias=None, path=0, want_out2=False):
+        """A [n_slots][rows_buf][C], W [N][taps*C] -> (out [n_slots*T][N] f32, out2 or None, used_tensor_cores)."""
+        A = np.ascontiguousarray(A, np.float32); W = np.ascontiguousarray(W, np.float32)
+        n_slots, rows_buf, C = A.shape
+        N = W.shape[0]
+        assert W.shape[1] == taps * C
+        out = np.zeros((n_slots * T, N), np.float32)
+        out2 = np.zeros((n_slots * T, N), np.float32) if want_out2 else None
+        b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+        rc = self.L.b200_debug_gemm(self.h, 1 if f16 else 0, _fp(A), n_slots, rows_buf, C, T, taps, _fp(W), N, _fp(b) if b is not None else None,
+                                    path, _fp(out), _fp(out2) if out2 is not None else None)
+        if rc < 0:
+            raise RuntimeError(f"b200_debug_gemm failed: {rc}")
+        return out, out2, bool(rc)
 
     def debug_set_latent(self, slot0, n, latents):
         lat = np.ascontiguousarray(latents, np.float32).reshape(n, LDIM)

@@ -753,6 +753,46 @@ int b200_debug_set_position(b200_engine* e, int slot0, int n, int pos, int max_g
     return B200_OK;
 }
 
+// Unit-test hook for the GEMM family: C[n_slots*T][N] = windows(A)[.][taps*C] . W[N][taps*C]^T (+bias, optional ELU->f16 copy)
+// A is [n_slots][rows_buf][C] (f32 on the host, rounded to bf16/f16 here). path: 0 = dispatcher (tcgen05 when supported),
+// 1 = CUDA-core. Returns 1 if the tensor-core kernel was used, 0 if a CUDA-core kernel was, negative on error.
+int b200_debug_gemm(b200_engine* e, int f16, const float* A, int n_slots, int rows_buf, int C, int T, int taps, const float* W, int N,
+                    const float* bias, int path, float* out, float* out2_as_f32) {
+    if (!e || !A || !W || !out || n_slots < 1 || T < 1 || rows_buf < T + taps - 1) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const int R = n_slots * T, K = taps * C;
+    const size_t na = (size_t)n_slots * rows_buf * C, nw = (size_t)N * K;
+    void *dA, *dW; float *dO, *dB = nullptr; void* dO2;
+    PTTS_CUDA_CHECK(cudaMalloc(&dA, na * 2)); PTTS_CUDA_CHECK(cudaMalloc(&dW, nw * 2));
+    PTTS_CUDA_CHECK(cudaMalloc(&dO, (size_t)R * N * 4)); PTTS_CUDA_CHECK(cudaMalloc(&dO2, (size_t)R * N * 2));
+    std::vector<uint16_t> ha(na), hw(nw);
+    auto cvt = [&](float v) -> uint16_t { if (f16) { __half h = __float2half_rn(v); return *(uint16_t*)&h; } __nv_bfloat16 b = __float2bfloat16_rn(v); return *(uint16_t*)&b; };
+    for (size_t i = 0; i < na; i++) ha[i] = cvt(A[i]);
+    for (size_t i = 0; i < nw; i++) hw[i] = cvt(W[i]);
+    PTTS_CUDA_CHECK(cudaMemcpy(dA, ha.data(), na * 2, cudaMemcpyHostToDevice));
+    PTTS_CUDA_CHECK(cudaMemcpy(dW, hw.data(), nw * 2, cudaMemcpyHostToDevice));
+    if (bias) { PTTS_CUDA_CHECK(cudaMalloc(&dB, N * 4)); PTTS_CUDA_CHECK(cudaMemcpy(dB, bias, N * 4, cudaMemcpyHostToDevice)); }
+    Epi ep; ep.rps = T; ep.bias = dB; ep.out = dO; ep.out_map = b200_engine::smap((long long)T * N, N, 0);
+    if (out2_as_f32) { ep.out2 = dO2; ep.out2_map = ep.out_map; ep.out2_type = f16 ? OUT2_F16 : OUT2_BF16; ep.act = ACT_ELU; }
+    const RowMap am = (n_slots == 1 && taps == 1) ? b200_engine::rows(C) : b200_engine::smap((long long)rows_buf * C, C, 0);
+    const int rps = (n_slots == 1 && taps == 1) ? (1 << 30) : T;
+    const int saved = e->cfg.gemm_path; e->cfg.gemm_path = path;
+    int used_tc = 0;
+    if (f16) { used_tc = (path == 0 && tc_gemm_supported<__half>(R, N, K, am, rps)); e->gemm<__half>((const __half*)dA, am, rps, (const __half*)dW, R, N, K, ep); }
+    else { used_tc = (path == 0 && tc_gemm_supported<__nv_bfloat16>(R, N, K, am, rps)); e->gemm<__nv_bfloat16>((const __nv_bfloat16*)dA, am, rps, (const __nv_bfloat16*)dW, R, N, K, ep); }
+    e->cfg.gemm_path = saved;
+    PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    PTTS_CUDA_CHECK(cudaGetLastError());
+    PTTS_CUDA_CHECK(cudaMemcpy(out, dO, (size_t)R * N * 4, cudaMemcpyDeviceToHost));
+    if (out2_as_f32) {
+        std::vector<uint16_t> h2((size_t)R * N);
+        PTTS_CUDA_CHECK(cudaMemcpy(h2.data(), dO2, h2.size() * 2, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < h2.size(); i++) out2_as_f32[i] = f16 ? __half2float(*(__half*)&h2[i]) : __bfloat162float(*(__nv_bfloat16*)&h2[i]);
+    }
+    cudaFree(dA); cudaFree(dW); cudaFree(dO); cudaFree(dO2); if (dB) cudaFree(dB);
+    return used_tc;
+}
+
 // Parity helper: overwrite the backbone input (previous latent) of slots [slot0, slot0+n) — teacher forcing.
 int b200_debug_set_latent(b200_engine* e, int slot0, int n, const float* latents) {
     if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots || !latents) return B200_EINVAL;

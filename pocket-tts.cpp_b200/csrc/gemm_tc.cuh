@@ -275,7 +275,7 @@ inline TcGeom tc_geometry(int R, int K, const RowMap& amap, int a_rps) {
     const long long C = amap.row_stride;
     if (C <= 0 || C % 64 != 0 || K % C != 0 || amap.base != 0) return g;
     g.C = (int)C; g.taps = (int)(K / C);
-    if (a_rps >= R) {                                  // plain matrix (one "slot")
+    if (amap.slot_stride == 0) {                       // plain matrix (one "slot")
         if (g.taps != 1) return g;
         g.T = R; g.CH = 128; g.cps = (R + 127) / 128; g.n_slots = 1; g.rows_per_slot_buf = R; g.slot_stride = (long long)R * C;
         g.ok = true; return g;
@@ -335,7 +335,7 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     cuuint32_t wbox[2] = {64, (cuuint32_t)bn};
     const CUtensorMap* tw = tc_get_map(c, W, f16, 2, wdims, wstr, wbox);
     TcParams p; p.R = R; p.N = N; p.K = K; p.kb_per_tap = g.C / 64; p.CH = g.CH; p.cps = g.cps;
-    p.total_chunks = (a_rps >= R) ? (R + 127) / 128 : g.n_slots * g.cps;
+    p.total_chunks = (amap.slot_stride == 0) ? (R + 127) / 128 : g.n_slots * g.cps;
     // instruction descriptor (kind::f16): D=f32, A/B = bf16|f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     p.idesc = (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     dim3 grid(N / bn, (R + 127) / 128);

@@ -137,8 +137,9 @@ def test_batched_equals_single(ctx, oracle_mod):
         for i in range(6):
             pcm, prod, lat, eos = eng.step(5, 1, noise[i, k][None])
             assert prod[0] == batch[i][1][k] == 1
-            assert np.abs(lat[0] - batch[i][2][k]).max() < 2e-2           # different GEMM kernels (GEMV vs tile) at different batch sizes
-            assert snr_db(batch[i][0][k], pcm[0]) > 45.0
+            # different GEMM kernels at different batch sizes (GEMV / CUDA-core tile / tcgen05): same bound as engine-vs-oracle
+            assert np.abs(lat[0] - batch[i][2][k]).max() < LAT_MAXABS
+            assert snr_db(batch[i][0][k], pcm[0]) > SNR_MIN
 
 
 def test_stream_api_matches_reference_driver_loop(P, model_dir, orc, oracle_mod):
