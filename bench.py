@@ -59,7 +59,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.device)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
@@ -188,7 +188,7 @@ def main():
     # this rank's utterance slice: global utterance id = rank * B + i
     texts = [synth_paragraph(rank * B + i) for i in range(B)]
     toks = [ctx.tokenize(t) for t in texts]
-    total_steps = args.warmup + args.steps * 3 + 8  # warm-up + timed + e2e + profiled passes
+    total_steps = args.warmup + args.steps * 3 + 8 + 400  # warm-up + timed + clock-sampling filler + e2e + profiled passes
     eng.set_seed(1234 + rank)
     eng.begin_sentences(list(range(B)), [st.voice] * B, toks, [total_steps + 64] * B, [1 << 20] * B, [0.7] * B)
     eng.sync()
@@ -202,12 +202,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from the warm-up through the timed region (the timed region alone can be shorter than one sample period)
+    sampler = ClockSampler(local); sampler.start()
+    time.sleep(0.3)
     steps_done = 0
     for _ in range(args.warmup):
         eng.step_enqueue(0, B); steps_done += 1
     eng.sync()
-
-    sampler = ClockSampler(local); sampler.start()
     barrier()
     l0 = eng.launch_count()
     if rank == 0:
@@ -221,6 +222,11 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
+    if ms < 400.0:                                     # keep the GPU under the same load until a few clock samples exist
+        t_end = time.time() + 0.4
+        while time.time() < t_end:
+            eng.step_enqueue(0, B); steps_done += 1
+            eng.sync()
     clocks = sampler.stop()
     mid_step = steps_done + args.steps / 2.0
     steps_done += args.steps

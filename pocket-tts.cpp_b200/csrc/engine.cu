@@ -69,6 +69,7 @@ struct b200_engine {
     // ---- scratch ----
     float *h = nullptr, *q = nullptr; __nv_bfloat16 *n_bf = nullptr, *att_bf = nullptr, *ff_bf = nullptr;
     int *row_slot = nullptr, *row_pos = nullptr, *tok = nullptr; float2* cs = nullptr;
+    float *af_ml = nullptr, *af_acc = nullptr;   // split-KV attention workspace [rows][splits][32] / [rows][splits][1024]
     __nv_bfloat16 *c_bf = nullptr, *sy_bf = nullptr, *hn_bf = nullptr, *h1_bf = nullptr, *noise_bf = nullptr;
     float *eos = nullptr, *ycond = nullptr, *mod = nullptr, *xh = nullptr, *noise_f32 = nullptr, *noise_inj = nullptr, *latent = nullptr;
     int* produced = nullptr; float* eos_out = nullptr;
@@ -199,10 +200,17 @@ struct b200_engine {
             if (cfg.kv_f32) { e.kcache = (float*)kc + l * kv_layer_stride; e.vcache = (float*)vc + l * kv_layer_stride; }
             else { e.kcache = (__nv_bfloat16*)kc + l * kv_layer_stride; e.vcache = (__nv_bfloat16*)vc + l * kv_layer_stride; }
             lin(n_bf, L.in_proj, R, e);
-            const size_t smem = (size_t)cfg.kv_capacity * sizeof(float);
             const int sg = seg_begin(0);
-            if (cfg.kv_f32) attn_flow_kernel<float><<<dim3(R, N_HEADS), 128, smem, stream>>>(q, (const float*)e.kcache, (const float*)e.vcache, kv_slot_stride, row_slot, row_pos, att_bf);
-            else attn_flow_kernel<__nv_bfloat16><<<dim3(R, N_HEADS), 128, smem, stream>>>(q, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, kv_slot_stride, row_slot, row_pos, att_bf);
+            if (cfg.kv_f32) {
+                const size_t smem = (size_t)cfg.kv_capacity * sizeof(float);
+                attn_flow_kernel<float><<<dim3(R, N_HEADS), 128, smem, stream>>>(q, (const float*)e.kcache, (const float*)e.vcache, kv_slot_stride, row_slot, row_pos, att_bf);
+            } else {
+                // enough CTAs for ~4 waves of one 128 KB-smem CTA per SM; each split streams >= a few dozen cache rows
+                int splits = (148 * 4 + R - 1) / R; splits = std::max(1, std::min(splits, AF_MAX_SPLITS));
+                attn_flow_split_kernel<<<dim3(splits, R), 288, AF_SMEM, stream>>>(q, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, kv_slot_stride,
+                                                                                  row_slot, row_pos, splits, af_ml, af_acc, att_bf);
+                if (splits > 1) { attn_flow_merge_kernel<<<R, 256, 0, stream>>>(af_ml, af_acc, splits, att_bf); launches++; }
+            }
             seg_end(sg);
             Epi eo; eo.resid = h; eo.resid_map = rows(D_MODEL); eo.out = h; eo.out_map = rows(D_MODEL);
             lin(att_bf, L.out_proj, R, eo);
@@ -540,6 +548,7 @@ int b200_finalize_weights(b200_engine* e) {
     e->h = e->dalloc<float>((size_t)MR * D_MODEL); e->q = e->dalloc<float>((size_t)MR * D_MODEL);
     e->n_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_MODEL); e->att_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_MODEL);
     e->ff_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_FF);
+    e->af_ml = e->dalloc<float>((size_t)MR * AF_MAX_SPLITS * 32); e->af_acc = e->dalloc<float>((size_t)MR * AF_MAX_SPLITS * D_MODEL);
     e->row_slot = e->dalloc<int>(MR); e->row_pos = e->dalloc<int>(MR); e->tok = e->dalloc<int>(MR); e->cs = e->dalloc<float2>((size_t)MR * 32);
     e->c_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_MODEL); e->sy_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW);
     e->hn_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW); e->h1_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW);
@@ -568,6 +577,7 @@ int b200_finalize_weights(b200_engine* e) {
     e->shifts.d[5] = {e->buf8, 481LL * e->C8, 1, 480, e->C8};
     e->shifts.d[6] = {e->buf9a, 1922LL * 64, 2, 1920, 64};
     e->shifts.d[7] = {e->buf11, 1922LL * 64, 2, 1920, 64};
+    PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
     if (cfg.kv_capacity * sizeof(float) > 48 * 1024) {
         PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cfg.kv_capacity * sizeof(float))));
         PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cfg.kv_capacity * sizeof(float))));

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include <cuda.h>
+#include <algorithm>
 #include <map>
 #include <tuple>
 
@@ -82,54 +83,135 @@ struct TcParams {
     uint32_t idesc;
 };
 
-// Vectorised GENERIC epilogue: 8 consecutive columns of one row.
-__device__ __forceinline__ void epi_vec8(const Epi& e, int row, int col, float (&v)[8], long long ro, long long r2, long long rr) {
-    if (e.bias) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    }
-    if (e.colscale) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.colscale + col)), b1 = __ldg(reinterpret_cast<const float4*>(e.colscale + col + 4));
-        v[0] *= b0.x; v[1] *= b0.y; v[2] *= b0.z; v[3] *= b0.w; v[4] *= b1.x; v[5] *= b1.y; v[6] *= b1.z; v[7] *= b1.w;
-    }
-    if (e.rowmul) {
-        const float* g = e.rowmul + (long long)row * e.rowmul_ld + col;
-        const float4 b0 = *reinterpret_cast<const float4*>(g), b1 = *reinterpret_cast<const float4*>(g + 4);
-        v[0] *= b0.x; v[1] *= b0.y; v[2] *= b0.z; v[3] *= b0.w; v[4] *= b1.x; v[5] *= b1.y; v[6] *= b1.z; v[7] *= b1.w;
-    }
+// ---- GENERIC epilogue for 32 consecutive columns of one row; loads are issued before any arithmetic/stores ----
+__device__ __forceinline__ void epi_generic32(const Epi& e, int row, int col0, float (&v)[32], long long ro, long long r2, long long rr) {
     if (e.resid) {
-        const float* g = e.resid + rr + col;
-        const float4 b0 = *reinterpret_cast<const float4*>(g), b1 = *reinterpret_cast<const float4*>(g + 4);
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        float4 rs[8];
+        const float4* g = reinterpret_cast<const float4*>(e.resid + rr + col0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) rs[j] = g[j];
+        if (e.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j); v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w; }
+        }
+        if (e.colscale) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.colscale + col0) + j); v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w; }
+        }
+        if (e.rowmul) {
+            const float4* gm = reinterpret_cast<const float4*>(e.rowmul + (long long)row * e.rowmul_ld + col0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float4 b = gm[j]; v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) { v[4 * j] += rs[j].x; v[4 * j + 1] += rs[j].y; v[4 * j + 2] += rs[j].z; v[4 * j + 3] += rs[j].w; }
+    } else {
+        if (e.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j); v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w; }
+        }
+        if (e.colscale) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.colscale + col0) + j); v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w; }
+        }
+        if (e.rowmul) {
+            const float4* gm = reinterpret_cast<const float4*>(e.rowmul + (long long)row * e.rowmul_ld + col0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float4 b = gm[j]; v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w; }
+        }
     }
     if (e.out) {
-        float* g = e.out + ro + col;
-        *reinterpret_cast<float4*>(g) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(g + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        float4* g = reinterpret_cast<float4*>(e.out + ro + col0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) g[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
     if (e.out2_type != OUT2_NONE) {
-        float a[8];
+        if (e.act != ACT_NONE) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) a[i] = apply_act(v[i], e.act);
+            for (int i = 0; i < 32; i++) v[i] = apply_act(v[i], e.act);
+        }
         if (e.out2_type == OUT2_BF16) {
-            __nv_bfloat162 p[4];
+            uint4* g = reinterpret_cast<uint4*>((__nv_bfloat16*)e.out2 + r2 + col0);
 #pragma unroll
-            for (int i = 0; i < 4; i++) p[i] = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
-            *reinterpret_cast<uint4*>((__nv_bfloat16*)e.out2 + r2 + col) = *reinterpret_cast<uint4*>(p);
-        } else {
-            __half2 hi[4];
+            for (int j = 0; j < 4; j++) {
+                __nv_bfloat162 p[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) hi[i] = __floats2half2_rn(a[2 * i], a[2 * i + 1]);
-            *reinterpret_cast<uint4*>((__half*)e.out2 + r2 + col) = *reinterpret_cast<uint4*>(hi);
-            if (e.out2_type == OUT2_F16_SPLIT) {
-                __half2 lo[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float2 h = __half22float2(hi[i]);
-                    lo[i] = __floats2half2_rn(a[2 * i] - h.x, a[2 * i + 1] - h.y);
-                }
-                *reinterpret_cast<uint4*>((__half*)e.out2 + r2 + col + e.split_off) = *reinterpret_cast<uint4*>(lo);
+                for (int i = 0; i < 4; i++) p[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                g[j] = *reinterpret_cast<uint4*>(p);
             }
+        } else {
+            uint4* g = reinterpret_cast<uint4*>((__half*)e.out2 + r2 + col0);
+            uint4* gl = reinterpret_cast<uint4*>((__half*)e.out2 + r2 + col0 + e.split_off);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                __half2 hi[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) hi[i] = __floats2half2_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                g[j] = *reinterpret_cast<uint4*>(hi);
+                if (e.out2_type == OUT2_F16_SPLIT) {
+                    __half2 lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { const float2 h = __half22float2(hi[i]); lo[i] = __floats2half2_rn(v[8 * j + 2 * i] - h.x, v[8 * j + 2 * i + 1] - h.y); }
+                    gl[j] = *reinterpret_cast<uint4*>(lo);
+                }
+            }
+        }
+    }
+}
+
+// ---- QKV epilogue for 32 consecutive columns (= half a head): RoPE with vector loads/stores (see epi_apply for the math) ----
+__device__ __forceinline__ void epi_qkv32(const Epi& e, int row, int col0, float (&v)[32]) {
+    const bool mimi = (e.mode == EPI_MIMI_QKV);
+    const int D = mimi ? M_DIM : D_MODEL;
+    if (e.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] += e.bias[col0 + i];
+    }
+    const int part = col0 / D, c = col0 - part * D;
+    const int slot = e.row_slot[row], pos = e.row_pos[row];
+    const long long cbase = (long long)slot * e.kv_slot_stride + (long long)(mimi ? pos % M_CTX : pos) * D;
+    if (part == 2) {
+        if (!mimi && e.kv_f32) {
+            float4* g = reinterpret_cast<float4*>((float*)e.vcache + cbase + c);
+#pragma unroll
+            for (int j = 0; j < 8; j++) g[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+            uint4* g = reinterpret_cast<uint4*>((__nv_bfloat16*)e.vcache + cbase + c);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                __nv_bfloat162 p[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) p[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                g[j] = *reinterpret_cast<uint4*>(p);
+            }
+        }
+        return;
+    }
+    const int h = c >> 6, i0 = ((c & 63) >> 5) * 16;          // 16 rotation pairs i0..i0+15 of head h
+    float re[16], im[16];
+    const float4* cs4 = reinterpret_cast<const float4*>(e.cs + row * 32 + i0);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float4 t = cs4[j];                                // (cos, sin) of pairs 2j, 2j+1
+        re[2 * j] = v[4 * j] * t.x - v[4 * j + 1] * t.y;          im[2 * j] = v[4 * j] * t.y + v[4 * j + 1] * t.x;
+        re[2 * j + 1] = v[4 * j + 2] * t.z - v[4 * j + 3] * t.w;  im[2 * j + 1] = v[4 * j + 2] * t.w + v[4 * j + 3] * t.z;
+    }
+    const int i_re = (h << 6) + i0, i_im = i_re + 32;          // de-interleaved [re(0..31) | im(0..31)]
+    const bool f32dst = !mimi && (part == 0 || e.kv_f32);
+    if (f32dst) {
+        float* dst = (part == 0) ? e.q_out_f32 + (long long)row * D : (float*)e.kcache + cbase;
+        float4* gr = reinterpret_cast<float4*>(dst + i_re); float4* gi = reinterpret_cast<float4*>(dst + i_im);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { gr[j] = make_float4(re[4 * j], re[4 * j + 1], re[4 * j + 2], re[4 * j + 3]); gi[j] = make_float4(im[4 * j], im[4 * j + 1], im[4 * j + 2], im[4 * j + 3]); }
+    } else {
+        __nv_bfloat16* dst = (part == 0) ? e.q_out_bf16 + (long long)row * D : (__nv_bfloat16*)e.kcache + cbase;
+        uint4* gr = reinterpret_cast<uint4*>(dst + i_re); uint4* gi = reinterpret_cast<uint4*>(dst + i_im);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            __nv_bfloat162 pr[4], pi[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { pr[i] = __floats2bfloat162_rn(re[8 * j + 2 * i], re[8 * j + 2 * i + 1]); pi[i] = __floats2bfloat162_rn(im[8 * j + 2 * i], im[8 * j + 2 * i + 1]); }
+            gr[j] = *reinterpret_cast<uint4*>(pr); gi[j] = *reinterpret_cast<uint4*>(pi);
         }
     }
 }
@@ -140,21 +222,25 @@ struct TcCfg {
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int W_BYTES = BN * 128;
     static constexpr int SMEM = STAGES * (A_BYTES + W_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN;                   // double-buffered accumulator
 };
 
+// Persistent: CTA b processes tiles b, b + gridDim.x, ... (tile = tile_m * tiles_n + tile_n). The accumulator is double
+// buffered in TMEM so the epilogue of tile i overlaps the TMA/MMA of tile i+1.
 template <int BN>
-__global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+__global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                                          const TcParams p, const Epi epi) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = base, sW = base + STAGES * Cfg::A_BYTES;
-    const uint32_t bars = sW + STAGES * Cfg::W_BYTES;          // full[STAGES] | empty[STAGES] | tmem_full | tmem_ptr
-    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tptr = tfull + 8;
+    const uint32_t bars = sW + STAGES * Cfg::W_BYTES;          // full[S] | empty[S] | tfull[2] | tempty[2] | tmem_ptr
+    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16, tptr = tempty0 + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
     const int num_kb = p.K / 64;
+    const int tiles_n = p.N / BN;
+    const int total_tiles = tiles_n * ((p.R + 127) / 128);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
@@ -162,12 +248,12 @@ __global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        mbar_init(tfull, 1);
+        for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -180,72 +266,82 @@ __global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__
         if (lane == 0) {
             // ===== TMA producer =====
             const int cpt = 128 / p.CH;                         // chunks per tile
-            const int g0 = tile_m * cpt;
-            int valid = p.total_chunks - g0; if (valid > cpt) valid = cpt;
-            const uint32_t bytes = (uint32_t)(valid * p.CH * 128 + Cfg::W_BYTES);
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(empty0 + 8 * s, ph ^ 1);
-                const int tap = kb / p.kb_per_tap, c0 = (kb % p.kb_per_tap) * 64;
-                mbar_expect_tx(full0 + 8 * s, bytes);
-                for (int c = 0; c < valid; c++) {
-                    const int g = g0 + c;
-                    const int slot = g / p.cps, t0 = (g % p.cps) * p.CH;
-                    tma_load_3d(sA + s * Cfg::A_BYTES + c * p.CH * 128, &tmA, full0 + 8 * s, c0, t0 + tap, slot);
+            uint32_t cnt = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int tile_n = tile % tiles_n, tile_m = tile / tiles_n;
+                const int g0 = tile_m * cpt;
+                int valid = p.total_chunks - g0; if (valid > cpt) valid = cpt;
+                const uint32_t bytes = (uint32_t)(valid * p.CH * 128 + Cfg::W_BYTES);
+                for (int kb = 0; kb < num_kb; kb++, cnt++) {
+                    const int s = cnt % STAGES; const uint32_t ph = (cnt / STAGES) & 1;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    const int tap = kb / p.kb_per_tap, c0 = (kb % p.kb_per_tap) * 64;
+                    mbar_expect_tx(full0 + 8 * s, bytes);
+                    for (int c = 0; c < valid; c++) {
+                        const int g = g0 + c;
+                        const int slot = g / p.cps, t0 = (g % p.cps) * p.CH;
+                        tma_load_3d(sA + s * Cfg::A_BYTES + c * p.CH * 128, &tmA, full0 + 8 * s, c0, t0 + tap, slot);
+                    }
+                    tma_load_2d(sW + s * Cfg::W_BYTES, &tmW, full0 + 8 * s, kb * 64, tile_n * BN);
                 }
-                tma_load_2d(sW + s * Cfg::W_BYTES, &tmW, full0 + 8 * s, kb * 64, tile_n * BN);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(full0 + 8 * s, ph);
+            uint32_t cnt = 0; int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+                const int buf = it & 1;
+                mbar_wait(tempty0 + 8 * buf, ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator buffer
                 tc_fence_after();
-                const uint64_t ad = make_smem_desc_sw128(sA + s * Cfg::A_BYTES), bd = make_smem_desc_sw128(sW + s * Cfg::W_BYTES);
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < num_kb; kb++, cnt++) {
+                    const int s = cnt % STAGES; const uint32_t ph = (cnt / STAGES) & 1;
+                    mbar_wait(full0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint64_t ad = make_smem_desc_sw128(sA + s * Cfg::A_BYTES), bd = make_smem_desc_sw128(sW + s * Cfg::W_BYTES);
 #pragma unroll
-                for (int k = 0; k < 4; k++) tc_mma_f16(tmem_base, ad + 2 * k, bd + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
-                tc_commit(empty0 + 8 * s);                       // frees the smem stage when these MMAs retire
+                    for (int k = 0; k < 4; k++) tc_mma_f16(tacc, ad + 2 * k, bd + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(empty0 + 8 * s);                   // frees the smem stage when these MMAs retire
+                }
+                tc_commit(tfull0 + 8 * buf);                     // accumulator complete
             }
-            tc_commit(tfull);                                    // accumulator complete
         }
     } else {
-        // ===== epilogue warps =====
-        const int ew = warp & 3;
-        const int row = tile_m * 128 + ew * 32 + lane;
-        mbar_wait(tfull, 0);
-        tc_fence_after();
-        const bool live = row < p.R;
-        long long ro = 0, r2 = 0, rr = 0;
-        if (live && epi.mode == EPI_GENERIC) {
-            ro = epi.out ? epi.out_map.off(row, epi.rps) : 0;
-            r2 = epi.out2 ? epi.out2_map.off(row, epi.rps) : 0;
-            rr = epi.resid ? epi.resid_map.off(row, epi.rps) : 0;
-        }
+        // ===== epilogue warps: lane group (warp & 3), 32-column chunks alternate between the two warps of a lane group =====
+        const int ew = warp & 3, half = (warp - 2) >> 2;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+            const int tile_n = tile % tiles_n, tile_m = tile / tiles_n;
+            const int buf = it & 1;
+            const int row = tile_m * 128 + ew * 32 + lane;
+            mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
+            tc_fence_after();
+            const bool live = row < p.R;
+            long long ro = 0, r2 = 0, rr = 0;
+            if (live && epi.mode == EPI_GENERIC) {
+                ro = epi.out ? epi.out_map.off(row, epi.rps) : 0;
+                r2 = epi.out2 ? epi.out2_map.off(row, epi.rps) : 0;
+                rr = epi.resid ? epi.resid_map.off(row, epi.rps) : 0;
+            }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            float v[32];
-            tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
-            if (live) {
-                const int col0 = tile_n * BN + c0;
-                if (epi.mode == EPI_GENERIC) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float w[8];
-#pragma unroll
-                        for (int i = 0; i < 8; i++) w[i] = v[j + i];
-                        epi_vec8(epi, row, col0 + j, w, ro, r2, rr);
-                    }
-                } else {
-                    epi_apply<32>(epi, row, col0, v, p.N);
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
+                float v[32];
+                tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+                if (live) {
+                    const int col0 = tile_n * BN + c0;
+                    if (epi.mode == EPI_GENERIC) epi_generic32(epi, row, col0, v, ro, r2, rr);
+                    else epi_qkv32(epi, row, col0, v);
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * buf) : "memory");
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -258,12 +354,15 @@ struct TcPlanCache {
     PFN_tmapEncodeTiled encode = nullptr;
     std::map<std::tuple<const void*, long long, long long, long long, long long, int, int>, CUtensorMap> maps;
     bool attr_set[3] = {false, false, false};
+    int num_sms = 148;
 };
 
 inline TcPlanCache* tc_plan_cache_create() {
     auto* c = new TcPlanCache;
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) c->encode = (PFN_tmapEncodeTiled)fn;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) c->num_sms = sms;
     return c;
 }
 inline void tc_plan_cache_destroy(TcPlanCache* c) { delete c; }
@@ -338,11 +437,12 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     p.total_chunks = (amap.slot_stride == 0) ? (R + 127) / 128 : g.n_slots * g.cps;
     // instruction descriptor (kind::f16): D=f32, A/B = bf16|f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     p.idesc = (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    dim3 grid(N / bn, (R + 127) / 128);
+    const int total_tiles = (N / bn) * ((R + 127) / 128);
+    dim3 grid(std::min(total_tiles, 2 * c->num_sms));
     const int bi = bn == 128 ? 0 : (bn == 64 ? 1 : 2);
     auto launch = [&](auto kern, int smem) {
         if (!c->attr_set[bi]) { PTTS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); c->attr_set[bi] = true; }
-        kern<<<grid, 192, smem, stream>>>(*ta, *tw, p, epi);
+        kern<<<grid, 320, smem, stream>>>(*ta, *tw, p, epi);
     };
     if (bn == 128) launch(gemm_tc_kernel<128>, TcCfg<128>::SMEM);
     else if (bn == 64) launch(gemm_tc_kernel<64>, TcCfg<64>::SMEM);

@@ -137,6 +137,188 @@ __global__ void __launch_bounds__(128) attn_flow_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// FlowLM attention, split-KV streaming version for the bf16 cache (the dominant kernel at large batch: pure KV stream).
+// One CTA per (KV split, query row), all 16 heads at once so that every cache row is read as one contiguous 2 KB line.
+// Warp 8 lane 0 is the producer: it streams groups of 8 consecutive K rows and V rows (16 KB each, contiguous in the
+// cache) into a 4-stage shared-memory ring with cp.async.bulk + mbarrier complete_tx. Consumer warp w owns key w of each
+// stage: lane l, chunk i reads the 16 bytes at i*512 + l*16 of the row = 8 dims of head 4i + l/8, so a row is four
+// conflict-free LDS.128 per lane; the dot products are finished with three shuffles inside each 8-lane group; softmax is
+// the online (running max / sum) form in fp32. Partial (m, l, acc) per split go to a workspace and attn_flow_merge_kernel
+// combines them (for one split the normalised bf16 output is written directly).
+// Same math as attn_flow_kernel (reference modules/transformer.h:157-199, src/torch.h:128-150).
+// ------------------------------------------------------------------------------------------------
+constexpr int AF_STAGES = 4, AF_KEYS = 8, AF_ROW_BYTES = D_MODEL * 2, AF_STAGE_BYTES = 2 * AF_KEYS * AF_ROW_BYTES;   // 32 KB
+constexpr int AF_SMEM = AF_STAGES * AF_STAGE_BYTES + 128;
+constexpr int AF_MAX_SPLITS = 16;
+
+__device__ __forceinline__ uint32_t af_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void af_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+__global__ void __launch_bounds__(288, 1) attn_flow_split_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
+                                                                 const __nv_bfloat16* __restrict__ vc, long long kv_slot_stride,
+                                                                 const int* __restrict__ row_slot, const int* __restrict__ row_pos, int splits,
+                                                                 float* __restrict__ ws_ml, float* __restrict__ ws_acc,
+                                                                 __nv_bfloat16* __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t af_smem[];
+    const int row = blockIdx.y, split = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int len = row_pos[row] + 1;
+    int chunk = (len + splits - 1) / splits; chunk = (chunk + AF_KEYS - 1) / AF_KEYS * AF_KEYS;
+    const int j_begin = split * chunk, j_end = min(len, j_begin + chunk);
+    const int n_keys = max(0, j_end - j_begin);
+    const int n_stages_total = (n_keys + AF_KEYS - 1) / AF_KEYS;
+    const uint32_t sbase = af_smem_u32(af_smem);
+    const uint32_t bars = sbase + AF_STAGES * AF_STAGE_BYTES;      // full[4] | empty[4]
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < AF_STAGES; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8 * s), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8 * (AF_STAGES + s)), "r"(8));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const long long slot_off = (long long)row_slot[row] * kv_slot_stride;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            const char* kg = reinterpret_cast<const char*>(kc + slot_off + (long long)j_begin * D_MODEL);
+            const char* vg = reinterpret_cast<const char*>(vc + slot_off + (long long)j_begin * D_MODEL);
+            for (int it = 0; it < n_stages_total; it++) {
+                const int s = it % AF_STAGES; const uint32_t ph = (it / AF_STAGES) & 1;
+                af_mbar_wait(bars + 8 * (AF_STAGES + s), ph ^ 1);
+                const int nk = min(AF_KEYS, n_keys - it * AF_KEYS);
+                const uint32_t bytes = (uint32_t)nk * AF_ROW_BYTES;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8 * s), "r"(2 * bytes) : "memory");
+                const uint32_t dst = sbase + s * AF_STAGE_BYTES;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(kg + (long long)it * AF_KEYS * AF_ROW_BYTES), "r"(bytes), "r"(bars + 8 * s) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + AF_KEYS * AF_ROW_BYTES), "l"(vg + (long long)it * AF_KEYS * AF_ROW_BYTES), "r"(bytes), "r"(bars + 8 * s) : "memory");
+            }
+        }
+    } else {
+        // ---- consumers: lane owns dims d(i,e) = i*256 + lane*8 + e of head 4i + lane/8 ----
+        float qr[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float* qp = q + (long long)row * D_MODEL + i * 256 + lane * 8;
+            const float4 a = *reinterpret_cast<const float4*>(qp), b = *reinterpret_cast<const float4*>(qp + 4);
+            qr[i][0] = a.x * 0.125f; qr[i][1] = a.y * 0.125f; qr[i][2] = a.z * 0.125f; qr[i][3] = a.w * 0.125f;
+            qr[i][4] = b.x * 0.125f; qr[i][5] = b.y * 0.125f; qr[i][6] = b.z * 0.125f; qr[i][7] = b.w * 0.125f;
+        }
+        float m[4], l[4], acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { m[i] = -INFINITY; l[i] = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc[i][e] = 0.f; }
+        for (int it = 0; it < n_stages_total; it++) {
+            const int s = it % AF_STAGES; const uint32_t ph = (it / AF_STAGES) & 1;
+            af_mbar_wait(bars + 8 * s, ph);
+            const int nk = min(AF_KEYS, n_keys - it * AF_KEYS);
+            if (warp < nk) {
+                const uint8_t* kr = af_smem + s * AF_STAGE_BYTES + warp * AF_ROW_BYTES + lane * 16;
+                const uint8_t* vr = kr + AF_KEYS * AF_ROW_BYTES;
+                float sc[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint4 kv = *reinterpret_cast<const uint4*>(kr + i * 512);
+                    const uint32_t w[4] = {kv.x, kv.y, kv.z, kv.w};
+                    float a = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        a = fmaf(__uint_as_float(w[t] << 16), qr[i][2 * t], a);
+                        a = fmaf(__uint_as_float(w[t] & 0xffff0000u), qr[i][2 * t + 1], a);
+                    }
+                    a += __shfl_xor_sync(0xffffffffu, a, 4);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    sc[i] = a;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float mn = fmaxf(m[i], sc[i]);
+                    const float corr = expf(m[i] - mn), p = expf(sc[i] - mn);
+                    m[i] = mn; l[i] = l[i] * corr + p;
+                    const uint4 vv = *reinterpret_cast<const uint4*>(vr + i * 512);
+                    const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        acc[i][2 * t] = fmaf(acc[i][2 * t], corr, p * __uint_as_float(w[t] << 16));
+                        acc[i][2 * t + 1] = fmaf(acc[i][2 * t + 1], corr, p * __uint_as_float(w[t] & 0xffff0000u));
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * (AF_STAGES + s)) : "memory");
+        }
+        // ---- cross-warp merge through shared memory (ring is drained: every stage was consumed by all 8 warps) ----
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float* sm_m = reinterpret_cast<float*>(af_smem);               // [8][16]
+        float* sm_l = sm_m + 8 * 16;                                   // [8][16]
+        float* sm_a = sm_l + 8 * 16;                                   // [8][1024]
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if ((lane & 7) == 0) { sm_m[warp * 16 + 4 * i + (lane >> 3)] = m[i]; sm_l[warp * 16 + 4 * i + (lane >> 3)] = l[i]; }
+            float* ap = sm_a + warp * D_MODEL + i * 256 + lane * 8;
+            *reinterpret_cast<float4*>(ap) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            *reinterpret_cast<float4*>(ap + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int t = threadIdx.x;                                     // 0..255: dims 4t..4t+3, head t/16
+        const int h = t >> 4;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 8; w++) M = fmaxf(M, sm_m[w * 16 + h]);
+        float L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const float mw = sm_m[w * 16 + h];
+            const float sc = (mw == -INFINITY) ? 0.f : expf(mw - M);
+            L = fmaf(sm_l[w * 16 + h], sc, L);
+            const float4 a = *reinterpret_cast<const float4*>(sm_a + w * D_MODEL + 4 * t);
+            o[0] = fmaf(a.x, sc, o[0]); o[1] = fmaf(a.y, sc, o[1]); o[2] = fmaf(a.z, sc, o[2]); o[3] = fmaf(a.w, sc, o[3]);
+        }
+        if (splits == 1) {
+            const float inv = 1.0f / L;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0] * inv, o[1] * inv), p1 = __floats2bfloat162_rn(o[2] * inv, o[3] * inv);
+            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(out + (long long)row * D_MODEL + 4 * t) = pk;
+        } else {
+            const long long wo = (long long)row * splits + split;
+            if ((t & 15) == 0) { ws_ml[wo * 32 + h] = M; ws_ml[wo * 32 + 16 + h] = L; }
+            *reinterpret_cast<float4*>(ws_acc + wo * D_MODEL + 4 * t) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) attn_flow_merge_kernel(const float* __restrict__ ws_ml, const float* __restrict__ ws_acc, int splits,
+                                                              __nv_bfloat16* __restrict__ out) {
+    const int row = blockIdx.x, t = threadIdx.x, h = t >> 4;
+    float M = -INFINITY;
+    for (int s = 0; s < splits; s++) M = fmaxf(M, ws_ml[((long long)row * splits + s) * 32 + h]);
+    float L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < splits; s++) {
+        const long long wo = (long long)row * splits + s;
+        const float ms = ws_ml[wo * 32 + h];
+        const float sc = (ms == -INFINITY) ? 0.f : expf(ms - M);
+        L = fmaf(ws_ml[wo * 32 + 16 + h], sc, L);
+        const float4 a = *reinterpret_cast<const float4*>(ws_acc + wo * D_MODEL + 4 * t);
+        o[0] = fmaf(a.x, sc, o[0]); o[1] = fmaf(a.y, sc, o[1]); o[2] = fmaf(a.z, sc, o[2]); o[3] = fmaf(a.w, sc, o[3]);
+    }
+    const float inv = 1.0f / L;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0] * inv, o[1] * inv), p1 = __floats2bfloat162_rn(o[2] * inv, o[3] * inv);
+    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(out + (long long)row * D_MODEL + 4 * t) = pk;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Mimi ring attention: 16 queries of one slot x all 250 ring slots, additive 0/-inf bias taken from the
 // reference's pattern (src/torch.h:168-221, called with the chunk's START offset, mimi_transformer.h:1198).
 // mask_mode 0 = reference (non-causal quirk once offset > 250), 1 = ideal causal ring.
