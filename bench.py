@@ -214,11 +214,16 @@ def main():
     if rank == 0:
         print(f"[bench] launches_before_timed_region={l0}", file=sys.stderr, flush=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ncu_range = os.environ.get("PTTS_NCU_RANGE") == "1"    # `ncu --profile-from-start off`: capture only the timed steps
+    if ncu_range:
+        P.lib().b200_profiler_range(1)
     e0.record(ext)
     for _ in range(args.steps):
         eng.step_enqueue(0, B)
     e1.record(ext)
     eng.sync()
+    if ncu_range:
+        P.lib().b200_profiler_range(0)
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0

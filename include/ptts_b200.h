@@ -36,6 +36,7 @@ typedef struct b200_config {
     int convt_split;      /* 1 = transposed convs see hi+lo f16 activations (~fp32, reference conv.h:282 is f32)   */
     int gemm_path;        /* 0 = auto (tcgen05 for large row counts), 1 = CUDA-core only (validation path)          */
     int max_prefill_rows; /* rows per prefill chunk (0 = default 512)                                               */
+    int cuda_graphs;      /* 1 = replay the per-frame step as a CUDA graph (captured on second use of a shape)       */
 } b200_config;
 
 B200_API void b200_default_config(b200_config* cfg);
@@ -100,6 +101,8 @@ B200_API int  b200_debug_set_latent(b200_engine* e, int slot0, int n, const floa
  * kernel, 1 FlowLM backbone, 2 flow head, 3 Mimi transformer, 4 SEANet, 5 whole step. out_ms[6], out_count[6]. */
 B200_API int  b200_profile(b200_engine* e, int on);
 B200_API int  b200_profile_read(b200_engine* e, float* out_ms, int* out_count);
+/* cudaProfilerStart (1) / cudaProfilerStop (0): lets `ncu --profile-from-start off` capture only a bracketed region. */
+B200_API void b200_profiler_range(int start);
 B200_API void* b200_stream(b200_engine* e);                        /* cudaStream_t the engine launches on */
 B200_API void* b200_device_ptr(b200_engine* e, const char* name);  /* "pcm", "latent", "noise", "produced", "eos" */
 B200_API long long b200_launch_count(b200_engine* e);              /* kernels launched so far by this engine */

@@ -22,7 +22,7 @@ LDIM = 32
 class B200Config(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("max_slots", ctypes.c_int), ("max_voices", ctypes.c_int), ("kv_capacity", ctypes.c_int),
                 ("kv_f32", ctypes.c_int), ("mimi_mask_mode", ctypes.c_int), ("convt_split", ctypes.c_int), ("gemm_path", ctypes.c_int),
-                ("max_prefill_rows", ctypes.c_int)]
+                ("max_prefill_rows", ctypes.c_int), ("cuda_graphs", ctypes.c_int)]
 
 
 _lib = None
@@ -68,6 +68,7 @@ def lib():
         "b200_debug_gemm": (ci, [vp, ci, fp, ci, ci, ci, ci, ci, fp, ci, fp, ci, fp, fp]),
         "b200_profile": (ci, [vp, ci]),
         "b200_profile_read": (ci, [vp, fp, ip]),
+        "b200_profiler_range": (None, [ci]),
         "b200_stream": (vp, [vp]),
         "b200_device_ptr": (vp, [vp, cp]),
         "b200_launch_count": (ctypes.c_longlong, [vp]),

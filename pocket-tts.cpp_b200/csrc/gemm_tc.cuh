@@ -81,6 +81,9 @@ struct TcParams {
     int cps;              // chunks per slot (T / CH)
     int total_chunks;     // ceil(R / CH) (plain) or n_slots * cps
     uint32_t idesc;
+    int splits;           // deterministic split-K: work item = (tile, split); partial sums go to a workspace
+    int kb_per_split;
+    long long ws_split_stride;   // elements between the partial-sum planes of consecutive splits
 };
 
 // ---- GENERIC epilogue for 32 consecutive columns of one row; loads are issued before any arithmetic/stores ----
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.K / 64;
     const int tiles_n = p.N / BN;
-    const int total_tiles = tiles_n * ((p.R + 127) / 128);
+    const int total_tiles = tiles_n * ((p.R + 127) / 128) * p.splits;      // work items (tile, split), split fastest
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
@@ -267,12 +270,14 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
             // ===== TMA producer =====
             const int cpt = 128 / p.CH;                         // chunks per tile
             uint32_t cnt = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+                const int split = work % p.splits, tile = work / p.splits;
                 const int tile_n = tile % tiles_n, tile_m = tile / tiles_n;
                 const int g0 = tile_m * cpt;
                 int valid = p.total_chunks - g0; if (valid > cpt) valid = cpt;
                 const uint32_t bytes = (uint32_t)(valid * p.CH * 128 + Cfg::W_BYTES);
-                for (int kb = 0; kb < num_kb; kb++, cnt++) {
+                const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; kb++, cnt++) {
                     const int s = cnt % STAGES; const uint32_t ph = (cnt / STAGES) & 1;
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
                     const int tap = kb / p.kb_per_tap, c0 = (kb % p.kb_per_tap) * 64;
@@ -290,18 +295,20 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
         if (lane == 0) {
             // ===== MMA issuer =====
             uint32_t cnt = 0; int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+            for (int work = blockIdx.x; work < total_tiles; work += gridDim.x, it++) {
                 const int buf = it & 1;
                 mbar_wait(tempty0 + 8 * buf, ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator buffer
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-                for (int kb = 0; kb < num_kb; kb++, cnt++) {
+                const int split = work % p.splits;
+                const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; kb++, cnt++) {
                     const int s = cnt % STAGES; const uint32_t ph = (cnt / STAGES) & 1;
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
                     const uint64_t ad = make_smem_desc_sw128(sA + s * Cfg::A_BYTES), bd = make_smem_desc_sw128(sW + s * Cfg::W_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) tc_mma_f16(tacc, ad + 2 * k, bd + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; k++) tc_mma_f16(tacc, ad + 2 * k, bd + 2 * k, p.idesc, (kb > kb0 || k != 0) ? 1u : 0u);
                     tc_commit(empty0 + 8 * s);                   // frees the smem stage when these MMAs retire
                 }
                 tc_commit(tfull0 + 8 * buf);                     // accumulator complete
@@ -311,7 +318,8 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
         // ===== epilogue warps: lane group (warp & 3), 32-column chunks alternate between the two warps of a lane group =====
         const int ew = warp & 3, half = (warp - 2) >> 2;
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+        for (int work = blockIdx.x; work < total_tiles; work += gridDim.x, it++) {
+            const int split = work % p.splits, tile = work / p.splits;
             const int tile_n = tile % tiles_n, tile_m = tile / tiles_n;
             const int buf = it & 1;
             const int row = tile_m * 128 + ew * 32 + lane;
@@ -320,7 +328,7 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
             const bool live = row < p.R;
             long long ro = 0, r2 = 0, rr = 0;
             if (live && epi.mode == EPI_GENERIC) {
-                ro = epi.out ? epi.out_map.off(row, epi.rps) : 0;
+                ro = (epi.out ? epi.out_map.off(row, epi.rps) : 0) + (long long)split * p.ws_split_stride;
                 r2 = epi.out2 ? epi.out2_map.off(row, epi.rps) : 0;
                 rr = epi.resid ? epi.resid_map.off(row, epi.rps) : 0;
             }
@@ -344,6 +352,20 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
 }
 
+// Deterministic split-K reduction: sums the partial planes in a fixed order and applies the real epilogue.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long plane, int R, int N, const Epi epi) {
+    const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (idx >= (long long)R * N) return;
+    const int row = (int)(idx / N), col = (int)(idx % N);
+    float4 a = *reinterpret_cast<const float4*>(ws + idx);
+    for (int s = 1; s < splits; s++) {
+        const float4 b = *reinterpret_cast<const float4*>(ws + (long long)s * plane + idx);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const float v[4] = {a.x, a.y, a.z, a.w};
+    epi_apply<4>(epi, row, col, v, N);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side: tensor-map cache + dispatch
 // ------------------------------------------------------------------------------------------------
@@ -355,6 +377,7 @@ struct TcPlanCache {
     std::map<std::tuple<const void*, long long, long long, long long, long long, int, int>, CUtensorMap> maps;
     bool attr_set[3] = {false, false, false};
     int num_sms = 148;
+    float* ws = nullptr; size_t ws_elems = 0;   // split-K partial sums
 };
 
 inline TcPlanCache* tc_plan_cache_create() {
@@ -365,7 +388,7 @@ inline TcPlanCache* tc_plan_cache_create() {
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) c->num_sms = sms;
     return c;
 }
-inline void tc_plan_cache_destroy(TcPlanCache* c) { delete c; }
+inline void tc_plan_cache_destroy(TcPlanCache* c) { if (c && c->ws) cudaFree(c->ws); delete c; }
 
 struct TcGeom { int C, taps, T, CH, cps, n_slots, rows_per_slot_buf; long long slot_stride; bool ok; };
 
@@ -388,8 +411,12 @@ inline TcGeom tc_geometry(int R, int K, const RowMap& amap, int a_rps) {
     g.ok = true; return g;
 }
 
-inline int tc_pick_bn(int R, int N) {
+inline int tc_pick_bn(int R, int N, int K = 0) {
     const int tiles_m = (R + 127) / 128;
+    if (tiles_m <= 2 && K >= 512) {            // small-M, long-K: wide tiles + split-K (see tc_gemm_launch)
+        for (int bn : {128, 64, 32}) if (N % bn == 0) return bn;
+        return 0;
+    }
     for (int bn : {128, 64, 32}) {
         if (N % bn != 0) continue;
         if (tiles_m * (N / bn) >= 120 || bn == 32) return bn;
@@ -401,7 +428,7 @@ template <typename T>
 inline bool tc_gemm_supported(int R, int N, int K, const RowMap& amap, int a_rps) {
     if (R < 64 || K % 64 != 0 || N % 32 != 0) return false;
     if (!tc_geometry(R, K, amap, a_rps).ok) return false;
-    return tc_pick_bn(R, N) != 0;
+    return tc_pick_bn(R, N, K) != 0;
 }
 
 inline const CUtensorMap* tc_get_map(TcPlanCache* c, const void* ptr, bool f16, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -424,7 +451,7 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     if (!c || !c->encode) { fprintf(stderr, "ptts_b200: tensor-map encoder unavailable\n"); abort(); }
     constexpr bool f16 = std::is_same<T, __half>::value;
     const TcGeom g = tc_geometry(R, K, amap, a_rps);
-    const int bn = tc_pick_bn(R, N);
+    const int bn = tc_pick_bn(R, N, K);
     cuuint64_t adims[3] = {(cuuint64_t)g.C, (cuuint64_t)g.rows_per_slot_buf, (cuuint64_t)g.n_slots};
     cuuint64_t astr[2] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.slot_stride * 2};
     cuuint32_t abox[3] = {64, (cuuint32_t)g.CH, 1};
@@ -434,19 +461,45 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     cuuint32_t wbox[2] = {64, (cuuint32_t)bn};
     const CUtensorMap* tw = tc_get_map(c, W, f16, 2, wdims, wstr, wbox);
     TcParams p; p.R = R; p.N = N; p.K = K; p.kb_per_tap = g.C / 64; p.CH = g.CH; p.cps = g.cps;
+    // Small-M GEMMs (FlowLM decode: R = batch) cannot fill the SMs with output tiles alone: split K deterministically.
+    const int num_kb = K / 64, tiles = (N / bn) * ((R + 127) / 128);
+    int splits = 1;
+    if (tiles * 2 <= c->num_sms && num_kb >= 8) {
+        splits = std::min(std::min((2 * c->num_sms + tiles - 1) / tiles, num_kb / 4), 16);
+        if (splits < 2) splits = 1;
+    }
+    p.splits = splits; p.kb_per_split = (num_kb + splits - 1) / splits; p.ws_split_stride = 0;
+    Epi kepi = epi;
+    if (splits > 1) {
+        p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
+        splits = p.splits;
+        // one fixed workspace for the engine's lifetime (its address is baked into captured CUDA graphs)
+        if (!c->ws) { c->ws_elems = (size_t)32 << 20; PTTS_CUDA_CHECK(cudaMalloc(&c->ws, c->ws_elems * sizeof(float))); }
+        while (splits > 1 && (size_t)splits * R * N > c->ws_elems) {
+            p.kb_per_split *= 2; p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split; splits = p.splits;
+        }
+    }
+    if (splits > 1) {
+        kepi = Epi{}; kepi.out = c->ws; kepi.out_map.row_stride = N; p.ws_split_stride = (long long)R * N;
+    } else { p.splits = 1; p.kb_per_split = num_kb; }
     p.total_chunks = (amap.slot_stride == 0) ? (R + 127) / 128 : g.n_slots * g.cps;
     // instruction descriptor (kind::f16): D=f32, A/B = bf16|f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     p.idesc = (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int total_tiles = (N / bn) * ((R + 127) / 128);
+    const int total_tiles = tiles * splits;
     dim3 grid(std::min(total_tiles, 2 * c->num_sms));
     const int bi = bn == 128 ? 0 : (bn == 64 ? 1 : 2);
     auto launch = [&](auto kern, int smem) {
         if (!c->attr_set[bi]) { PTTS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); c->attr_set[bi] = true; }
-        kern<<<grid, 320, smem, stream>>>(*ta, *tw, p, epi);
+        kern<<<grid, 320, smem, stream>>>(*ta, *tw, p, kepi);
     };
     if (bn == 128) launch(gemm_tc_kernel<128>, TcCfg<128>::SMEM);
     else if (bn == 64) launch(gemm_tc_kernel<64>, TcCfg<64>::SMEM);
     else launch(gemm_tc_kernel<32>, TcCfg<32>::SMEM);
+    if (splits > 1) {
+        const long long quads = (long long)R * N / 4;
+        splitk_reduce_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(c->ws, splits, (long long)R * N, R, N, epi);
+        return 2;
+    }
     return 1;
 }
 

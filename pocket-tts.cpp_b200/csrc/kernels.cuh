@@ -335,58 +335,98 @@ __device__ __forceinline__ bool mimi_masked(int offset, int j, int c, int mask_m
     return idx >= start + 1 + j || (idx <= M_CTX - 1 && idx > M_CTX - 1 - (M_T - j - 1));
 }
 
-__global__ void __launch_bounds__(128) attn_mimi_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
+// One CTA (8 warps) per (slot, head). K and V of the head (250 x 64 bf16 each) are staged once in shared memory; warp w
+// owns queries w and w+8. Scores: lane = ring slot (K rows read as 16-byte chunks, XOR-swizzled by row so that the 32 rows
+// a warp touches spread over all banks), q broadcast from shared memory. Softmax per query row with warp shuffles, the
+// probabilities are rounded to bf16 (ggml's bf16 mul_mat does that to the f32 operand), then PV with lane = 2 output dims.
+constexpr int AM_SMEM = (2 * M_CTX * D_HEAD) * 2 + M_T * 256 * 4 + M_T * D_HEAD * 4;   // K,V bf16 + P f32 + Q f32 = 84,480 B
+
+__global__ void __launch_bounds__(256) attn_mimi_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
                                                         const __nv_bfloat16* __restrict__ vc, long long kv_slot_stride, int slot0,
                                                         const int* __restrict__ mimi_off, int mask_mode, __nv_bfloat16* __restrict__ out) {
-    __shared__ float sc[4][M_CTX + 6];
-    __shared__ float qs[4][D_HEAD];
+    extern __shared__ __align__(16) uint8_t am_smem[];
+    uint4* sK = reinterpret_cast<uint4*>(am_smem);                               // [250][8 chunks], chunk index XOR (row & 7)
+    uint4* sV = sK + M_CTX * 8;                                                  // [250][8 chunks]
+    float* sP = reinterpret_cast<float*>(sV + M_CTX * 8);                        // [16][256]
+    float* sQ = sP + M_T * 256;                                                  // [16][64]
     const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int slot = slot0 + b;
     const int offset = mimi_off[slot];
-    const __nv_bfloat16* K = kc + (long long)slot * kv_slot_stride + h * D_HEAD;
-    const __nv_bfloat16* V = vc + (long long)slot * kv_slot_stride + h * D_HEAD;
-    for (int t = wid; t < M_T; t += 4) {
-        const long long row = (long long)b * M_T + t;
-        qs[wid][lane] = __bfloat162float(q[row * M_DIM + h * D_HEAD + lane]);
-        qs[wid][lane + 32] = __bfloat162float(q[row * M_DIM + h * D_HEAD + lane + 32]);
-        __syncwarp();
-        float mx = -INFINITY;
-        for (int c = lane; c < M_CTX; c += 32) {
-            float s = -INFINITY;
-            if (!mimi_masked(offset, t, c, mask_mode)) {
-                const __nv_bfloat16* kr = K + (long long)c * M_DIM;
-                float acc = 0.f;
+    const uint4* Kg = reinterpret_cast<const uint4*>(kc + (long long)slot * kv_slot_stride + h * D_HEAD);   // row stride M_DIM*2 B = 64 uint4
+    const uint4* Vg = reinterpret_cast<const uint4*>(vc + (long long)slot * kv_slot_stride + h * D_HEAD);
+    for (int i = tid; i < M_CTX * 8; i += 256) {
+        const int r = i >> 3, ch = i & 7;
+        sK[r * 8 + (ch ^ (r & 7))] = Kg[(long long)r * (M_DIM / 8) + ch];
+        sV[i] = Vg[(long long)r * (M_DIM / 8) + ch];
+    }
+    for (int i = tid; i < M_T * D_HEAD; i += 256) {
+        const int t = i >> 6, d = i & 63;
+        sQ[i] = __bfloat162float(q[((long long)b * M_T + t) * M_DIM + h * D_HEAD + d]);
+    }
+    __syncthreads();
+    const int q0 = wid, q1 = wid + 8;
+    // ---- scores (scale 1/8, additive 0/-inf bias) ----
+    for (int c = lane; c < 256; c += 32) {
+        float s0 = -INFINITY, s1 = -INFINITY;
+        if (c < M_CTX) {
+            const bool m0 = mimi_masked(offset, q0, c, mask_mode), m1 = mimi_masked(offset, q1, c, mask_mode);
+            if (!(m0 && m1)) {
+                float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                for (int d = 0; d < D_HEAD; d += 8) {
-                    const uint4 kv = *reinterpret_cast<const uint4*>(kr + d);
-                    const __nv_bfloat16* ke = reinterpret_cast<const __nv_bfloat16*>(&kv);
-#pragma unroll
-                    for (int u = 0; u < 8; u++) acc = fmaf(__bfloat162float(ke[u]), qs[wid][d + u], acc);
+                for (int ch = 0; ch < 8; ch++) {
+                    const uint4 kv = sK[c * 8 + (ch ^ (c & 7))];
+                    const uint32_t w[4] = {kv.x, kv.y, kv.z, kv.w};
+                    const float4 qa0 = *reinterpret_cast<const float4*>(sQ + q0 * 64 + ch * 8), qb0 = *reinterpret_cast<const float4*>(sQ + q0 * 64 + ch * 8 + 4);
+                    const float4 qa1 = *reinterpret_cast<const float4*>(sQ + q1 * 64 + ch * 8), qb1 = *reinterpret_cast<const float4*>(sQ + q1 * 64 + ch * 8 + 4);
+                    const float k0 = __uint_as_float(w[0] << 16), k1 = __uint_as_float(w[0] & 0xffff0000u), k2 = __uint_as_float(w[1] << 16), k3 = __uint_as_float(w[1] & 0xffff0000u);
+                    const float k4 = __uint_as_float(w[2] << 16), k5 = __uint_as_float(w[2] & 0xffff0000u), k6 = __uint_as_float(w[3] << 16), k7 = __uint_as_float(w[3] & 0xffff0000u);
+                    a0 = fmaf(k0, qa0.x, a0); a0 = fmaf(k1, qa0.y, a0); a0 = fmaf(k2, qa0.z, a0); a0 = fmaf(k3, qa0.w, a0);
+                    a0 = fmaf(k4, qb0.x, a0); a0 = fmaf(k5, qb0.y, a0); a0 = fmaf(k6, qb0.z, a0); a0 = fmaf(k7, qb0.w, a0);
+                    a1 = fmaf(k0, qa1.x, a1); a1 = fmaf(k1, qa1.y, a1); a1 = fmaf(k2, qa1.z, a1); a1 = fmaf(k3, qa1.w, a1);
+                    a1 = fmaf(k4, qb1.x, a1); a1 = fmaf(k5, qb1.y, a1); a1 = fmaf(k6, qb1.z, a1); a1 = fmaf(k7, qb1.w, a1);
                 }
-                s = acc * 0.125f;
+                if (!m0) s0 = a0 * 0.125f;
+                if (!m1) s1 = a1 * 0.125f;
             }
-            sc[wid][c] = s;
-            mx = fmaxf(mx, s);
         }
+        sP[q0 * 256 + c] = s0; sP[q1 * 256 + c] = s1;
+    }
+    __syncwarp();
+    // ---- softmax rows q0, q1 (this warp wrote them) ----
+#pragma unroll
+    for (int rsel = 0; rsel < 2; rsel++) {
+        float* pr = sP + (rsel ? q1 : q0) * 256;
+        float mx = -INFINITY;
+        for (int c = lane; c < 256; c += 32) mx = fmaxf(mx, pr[c]);
         mx = warp_max(mx);
         float sum = 0.f;
-        for (int c = lane; c < M_CTX; c += 32) { const float e = expf(sc[wid][c] - mx); sc[wid][c] = e; sum += e; }
+        for (int c = lane; c < 256; c += 32) { const float e = expf(pr[c] - mx); pr[c] = e; sum += e; }
         sum = warp_sum(sum);
         const float inv = 1.0f / sum;
-        __syncwarp();
-        float a0 = 0.f, a1 = 0.f;
-        for (int c = 0; c < M_CTX; c++) {
-            const float e = sc[wid][c];
-            if (e != 0.f) {
-                const float p = __bfloat162float(__float2bfloat16_rn(e * inv));
-                const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(V + (long long)c * M_DIM + 2 * lane);
-                a0 = fmaf(p, __bfloat162float(vv.x), a0);
-                a1 = fmaf(p, __bfloat162float(vv.y), a1);
-            }
-        }
-        *reinterpret_cast<__nv_bfloat162*>(out + row * M_DIM + h * D_HEAD + 2 * lane) = __floats2bfloat162_rn(a0, a1);
-        __syncwarp();
+        for (int c = lane; c < 256; c += 32) pr[c] = __bfloat162float(__float2bfloat16_rn(pr[c] * inv));
     }
+    __syncwarp();
+    // ---- PV: lane owns output dims 2*lane, 2*lane+1 ----
+    float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
+    const uint32_t* sV32 = reinterpret_cast<const uint32_t*>(sV);
+    for (int c = 0; c < 248; c += 4) {
+        const float4 p0 = *reinterpret_cast<const float4*>(sP + q0 * 256 + c), p1 = *reinterpret_cast<const float4*>(sP + q1 * 256 + c);
+        const float pa[4] = {p0.x, p0.y, p0.z, p0.w}, pb[4] = {p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t vv = sV32[(c + u) * 32 + lane];
+            const float v0 = __uint_as_float(vv << 16), v1 = __uint_as_float(vv & 0xffff0000u);
+            o00 = fmaf(pa[u], v0, o00); o01 = fmaf(pa[u], v1, o01); o10 = fmaf(pb[u], v0, o10); o11 = fmaf(pb[u], v1, o11);
+        }
+    }
+    for (int c = 248; c < M_CTX; c++) {
+        const uint32_t vv = sV32[c * 32 + lane];
+        const float v0 = __uint_as_float(vv << 16), v1 = __uint_as_float(vv & 0xffff0000u);
+        const float pa = sP[q0 * 256 + c], pb = sP[q1 * 256 + c];
+        o00 = fmaf(pa, v0, o00); o01 = fmaf(pa, v1, o01); o10 = fmaf(pb, v0, o10); o11 = fmaf(pb, v1, o11);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(out + ((long long)b * M_T + q0) * M_DIM + h * D_HEAD + 2 * lane) = __floats2bfloat162_rn(o00, o01);
+    *reinterpret_cast<__nv_bfloat162*>(out + ((long long)b * M_T + q1) * M_DIM + h * D_HEAD + 2 * lane) = __floats2bfloat162_rn(o10, o11);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -438,7 +478,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__global__ void noise_kernel(int slot0, int n, const float* __restrict__ injected, unsigned long long seed, const float* __restrict__ temp,
+__global__ void noise_kernel(int slot0, int n, const float* __restrict__ injected, const unsigned long long* __restrict__ seed_ptr, const float* __restrict__ temp,
                              const int* __restrict__ gen_step, float* __restrict__ noise_f32, __nv_bfloat16* __restrict__ noise_bf16) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * LDIM) return;
@@ -451,6 +491,7 @@ __global__ void noise_kernel(int slot0, int n, const float* __restrict__ injecte
         if (std == 0.f) z = 0.f;
         else {
             uint32_t o[4];
+            const unsigned long long seed = *seed_ptr;
             philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)slot, (uint32_t)gen_step[slot], (uint32_t)(i >> 1), 0x5054545Au, o);
             const float u1 = ((float)(o[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
             const float u2 = ((float)(o[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
