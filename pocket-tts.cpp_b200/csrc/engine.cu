@@ -171,12 +171,14 @@ struct b200_engine {
     }
 
     // ---------------------------------------------------------------------------------------------
+    // Returns true when the LayerNorm described by `ln` was fused into the GEMM's split-K reduction.
     template <typename T>
-    void gemm(const T* A, RowMap amap, int a_rps, const T* W, int R, int N, int K, const Epi& epi) {
-        if (R <= 0) return;
+    bool gemm(const T* A, RowMap amap, int a_rps, const T* W, int R, int N, int K, const Epi& epi, const LnFuse* ln = nullptr) {
+        if (R <= 0) return false;
         if (cfg.gemm_path == 0 && tc_gemm_supported<T>(R, N, K, amap, a_rps)) {
-            launches += tc_gemm_launch<T>(tc, A, amap, a_rps, W, R, N, K, epi, stream);
-            return;
+            bool done = false;
+            launches += tc_gemm_launch<T>(tc, A, amap, a_rps, W, R, N, K, epi, stream, ln, &done);
+            return done;
         }
         if (R <= 8) {
             const int warps = (N + 1) / 2, blocks = (warps + 7) / 8;
@@ -186,20 +188,22 @@ struct b200_engine {
             gemm_ffma_kernel<T><<<grid, 256, 0, stream>>>(A, amap, a_rps, W, R, N, K, epi);
         }
         launches++;
+        return false;
     }
     static RowMap rows(long long ld) { RowMap m; m.row_stride = ld; return m; }
     static RowMap smap(long long slot_stride, long long row_stride, long long base) { RowMap m; m.slot_stride = slot_stride; m.row_stride = row_stride; m.base = base; return m; }
-    void lin(const __nv_bfloat16* A, const LinW& L, int R, Epi epi) {
+    bool lin(const __nv_bfloat16* A, const LinW& L, int R, Epi epi, const LnFuse* ln = nullptr) {
         if (!epi.bias) epi.bias = L.b;
-        gemm<__nv_bfloat16>(A, rows(L.in), 1 << 30, L.w, R, L.out, L.in, epi);
+        return gemm<__nv_bfloat16>(A, rows(L.in), 1 << 30, L.w, R, L.out, L.in, epi, ln);
     }
 
     // FlowLM transformer over R rows held in `h` (reference modules/transformer.h:253-278,363-374).
     void flow_forward(int R) {
         const int BIG = 1 << 30;
+        bool ln1_done = false;                                   // norm1 of layer l already produced by layer l-1's linear2 reduction
         for (int l = 0; l < N_LAYERS; l++) {
             auto& L = fl[l];
-            layernorm_kernel<D_MODEL><<<(R + 7) / 8, 256, 0, stream>>>(h, rows(D_MODEL), BIG, R, 1e-5f, L.n1w, L.n1b, nullptr, nullptr, 0, n_bf, nullptr);
+            if (!ln1_done) { layernorm_kernel<D_MODEL><<<(R + 7) / 8, 256, 0, stream>>>(h, rows(D_MODEL), BIG, R, 1e-5f, L.n1w, L.n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++; }
             Epi e; e.mode = EPI_FLOW_QKV; e.row_slot = row_slot; e.row_pos = row_pos; e.cs = cs; e.kv_f32 = cfg.kv_f32;
             e.kv_slot_stride = kv_slot_stride; e.q_out_f32 = q;
             if (cfg.kv_f32) { e.kcache = (float*)kc + l * kv_layer_stride; e.vcache = (float*)vc + l * kv_layer_stride; }
@@ -216,15 +220,22 @@ struct b200_engine {
                                                                                   row_slot, row_pos, splits, af_ml, af_acc, att_bf);
                 if (splits > 1) { attn_flow_merge_kernel<<<R, 256, 0, stream>>>(af_ml, af_acc, splits, att_bf); launches++; }
             }
+            launches++;
             seg_end(sg);
             Epi eo; eo.resid = h; eo.resid_map = rows(D_MODEL); eo.out = h; eo.out_map = rows(D_MODEL);
-            lin(att_bf, L.out_proj, R, eo);
-            layernorm_kernel<D_MODEL><<<(R + 7) / 8, 256, 0, stream>>>(h, rows(D_MODEL), BIG, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, n_bf, nullptr);
+            LnFuse f2; f2.w = L.n2w; f2.b = L.n2b; f2.eps = 1e-5f; f2.out = n_bf;
+            if (!lin(att_bf, L.out_proj, R, eo, &f2)) {
+                layernorm_kernel<D_MODEL><<<(R + 7) / 8, 256, 0, stream>>>(h, rows(D_MODEL), BIG, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
+            }
             Epi e1; e1.out2 = ff_bf; e1.out2_map = rows(D_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
             lin(n_bf, L.lin1, R, e1);
             Epi e2; e2.resid = h; e2.resid_map = rows(D_MODEL); e2.out = h; e2.out_map = rows(D_MODEL);
-            lin(ff_bf, L.lin2, R, e2);
-            launches += 3;
+            if (l + 1 < N_LAYERS) {
+                LnFuse f1; f1.w = fl[l + 1].n1w; f1.b = fl[l + 1].n1b; f1.eps = 1e-5f; f1.out = n_bf;
+                ln1_done = lin(ff_bf, L.lin2, R, e2, &f1);
+            } else {
+                lin(ff_bf, L.lin2, R, e2);
+            }
         }
     }
 
@@ -316,7 +327,7 @@ struct b200_engine {
           gemm<__half>(buf9b + slot0 * s9b, smap(s9b, 64, 0), T3, r9b.w, n * T3, r9b.N, r9b.K, e); }
         {
             const int Rr = n * T3;
-            conv_n1_kernel<<<(Rr + 7) / 8, 256, 0, stream>>>(buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm + (long long)slot0 * FRAME);
+            conv_n1_kernel<<<(Rr * 4 + 255) / 256, 256, 0, stream>>>(buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm + (long long)slot0 * FRAME);
         }
         shift_states_kernel<<<dim3(n, shifts.n), 128, 0, stream>>>(shifts, slot0, mimi_off);
         launches += 4;
@@ -603,6 +614,18 @@ int b200_finalize_weights(b200_engine* e) {
     e->shifts.d[5] = {e->buf8, 481LL * e->C8, 1, 480, e->C8};
     e->shifts.d[6] = {e->buf9a, 1922LL * 64, 2, 1920, 64};
     e->shifts.d[7] = {e->buf11, 1922LL * 64, 2, 1920, 64};
+    // Keep the shared-memory carve-out identical for every kernel of the step: mixed carve-outs force an SM reconfiguration
+    // between consecutive launches, which shows up as microseconds of idle time on the ~100 small kernels of a frame.
+    {
+        const void* ks[] = {(const void*)prepare_step_kernel, (const void*)rope_table_kernel, (const void*)gemm_ffma_kernel<__nv_bfloat16>, (const void*)gemm_ffma_kernel<__half>,
+                            (const void*)gemv_small_kernel<__nv_bfloat16, 8>, (const void*)gemv_small_kernel<__half, 8>, (const void*)layernorm_kernel<D_MODEL>,
+                            (const void*)layernorm_kernel<D_FLOW>, (const void*)gemm_tc_kernel<32>, (const void*)gemm_tc_kernel<64>, (const void*)gemm_tc_kernel<128>,
+                            (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
+                            (const void*)attn_flow_split_kernel, (const void*)attn_flow_merge_kernel, (const void*)noise_kernel, (const void*)head_pre_kernel,
+                            (const void*)step_logic_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)cast_f16_kernel,
+                            (const void*)conv_n1_kernel, (const void*)shift_states_kernel};
+        for (const void* k : ks) PTTS_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_mimi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM));
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
     if (cfg.kv_capacity * sizeof(float) > 48 * 1024) {

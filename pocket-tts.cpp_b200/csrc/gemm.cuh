@@ -175,24 +175,34 @@ __global__ void __launch_bounds__(256) gemv_small_kernel(const T* __restrict__ A
     }
 }
 
-// Final SEANet conv (64 -> 1 channel, k=3; reference seanet.h:208, defaults.h:113-118): one warp per output sample.
+// Final SEANet conv (64 -> 1 channel, k=3; reference seanet.h:208, defaults.h:113-118). Four lanes per output sample
+// (16 channels x 3 taps each, two shuffles to finish), eight consecutive samples per warp so every global load
+// instruction covers 1 KB of contiguous channel-last rows. f16 operands, fp32 accumulation like every other conv.
 __global__ void __launch_bounds__(256) conv_n1_kernel(const __half* __restrict__ A, RowMap amap, int rps,
                                                       const __half* __restrict__ W, const float* __restrict__ bias,
                                                       int R, int K, float* __restrict__ out) {
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (row >= R) return;
-    const __half* a = A + amap.off(row, rps);
+    const int gl = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = gl >> 2, g = gl & 3;                       // output sample, channel group (16 channels)
+    const bool live = row < R;
     float acc = 0.f;
-    for (int k = lane * 8; k < K; k += 256) {
-        const uint4 av = *reinterpret_cast<const uint4*>(a + k);
-        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(W + k));
-        const __half* ae = reinterpret_cast<const __half*>(&av);
-        const __half* we = reinterpret_cast<const __half*>(&wv);
+    if (live) {
+        const __half* a = A + amap.off(row, rps) + g * 16;     // window = 3 consecutive rows of 64 channels (K == 192)
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc = fmaf(__half2float(ae[j]), __half2float(we[j]), acc);
+        for (int k = 0; k < 3; k++) {
+            const uint4 a0 = *reinterpret_cast<const uint4*>(a + k * 64), a1 = *reinterpret_cast<const uint4*>(a + k * 64 + 8);
+            const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(W + k * 64 + g * 16)), w1 = __ldg(reinterpret_cast<const uint4*>(W + k * 64 + g * 16 + 8));
+            const __half2* ah0 = reinterpret_cast<const __half2*>(&a0); const __half2* ah1 = reinterpret_cast<const __half2*>(&a1);
+            const __half2* wh0 = reinterpret_cast<const __half2*>(&w0); const __half2* wh1 = reinterpret_cast<const __half2*>(&w1);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 x = __half22float2(ah0[j]), y = __half22float2(wh0[j]), x2 = __half22float2(ah1[j]), y2 = __half22float2(wh1[j]);
+                acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x2.x, y2.x, acc); acc = fmaf(x2.y, y2.y, acc);
+            }
+        }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) out[row] = acc + (bias ? bias[0] : 0.f);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (live && g == 0) out[row] = acc + (bias ? bias[0] : 0.f);
 }
 
 }  // namespace ptts

@@ -366,6 +366,53 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     epi_apply<4>(epi, row, col, v, N);
 }
 
+// Same, one warp per row of C columns, followed by the LayerNorm that consumes this GEMM's output (ggml_norm semantics, see
+// layernorm_kernel): the row is already in registers, so the separate LN launch and its read of the row disappear.
+struct LnFuse { const float* w = nullptr; const float* b = nullptr; float eps = 0.f; __nv_bfloat16* out = nullptr; };
+
+template <int C>
+__global__ void __launch_bounds__(256) splitk_reduce_ln_kernel(const float* __restrict__ ws, int splits, long long plane, int R, const Epi epi, const LnFuse ln) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= R) return;
+    constexpr int Q = C / 128;                                  // float4 groups per lane
+    float v[Q][4];
+    const long long rr = epi.resid ? epi.resid_map.off(row, epi.rps) : 0, ro = epi.out ? epi.out_map.off(row, epi.rps) : 0;
+#pragma unroll
+    for (int qd = 0; qd < Q; qd++) {
+        const int col = (qd * 32 + lane) * 4;
+        float4 a = *reinterpret_cast<const float4*>(ws + (long long)row * C + col);
+        for (int s = 1; s < splits; s++) {
+            const float4 b = *reinterpret_cast<const float4*>(ws + (long long)s * plane + (long long)row * C + col);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        v[qd][0] = a.x; v[qd][1] = a.y; v[qd][2] = a.z; v[qd][3] = a.w;
+        if (epi.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col)); v[qd][0] += b.x; v[qd][1] += b.y; v[qd][2] += b.z; v[qd][3] += b.w; }
+        if (epi.colscale) { const float4 b = __ldg(reinterpret_cast<const float4*>(epi.colscale + col)); v[qd][0] *= b.x; v[qd][1] *= b.y; v[qd][2] *= b.z; v[qd][3] *= b.w; }
+        if (epi.resid) { const float4 b = *reinterpret_cast<const float4*>(epi.resid + rr + col); v[qd][0] += b.x; v[qd][1] += b.y; v[qd][2] += b.z; v[qd][3] += b.w; }
+        if (epi.out) *reinterpret_cast<float4*>(epi.out + ro + col) = make_float4(v[qd][0], v[qd][1], v[qd][2], v[qd][3]);
+    }
+    float s1 = 0.f;
+#pragma unroll
+    for (int qd = 0; qd < Q; qd++) s1 += v[qd][0] + v[qd][1] + v[qd][2] + v[qd][3];
+    const float mean = warp_sum(s1) / C;
+    float s2 = 0.f;
+#pragma unroll
+    for (int qd = 0; qd < Q; qd++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) { v[qd][i] -= mean; s2 += v[qd][i] * v[qd][i]; }
+    const float rs = 1.0f / sqrtf(warp_sum(s2) / C + ln.eps);
+#pragma unroll
+    for (int qd = 0; qd < Q; qd++) {
+        const int col = (qd * 32 + lane) * 4;
+        float y[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { y[i] = v[qd][i] * rs; if (ln.w) y[i] *= ln.w[col + i]; if (ln.b) y[i] += ln.b[col + i]; }
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(ln.out + (long long)row * C + col) = pk;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side: tensor-map cache + dispatch
 // ------------------------------------------------------------------------------------------------
@@ -447,7 +494,8 @@ inline const CUtensorMap* tc_get_map(TcPlanCache* c, const void* ptr, bool f16, 
 }
 
 template <typename T>
-inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, const T* W, int R, int N, int K, const Epi& epi, cudaStream_t stream) {
+inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, const T* W, int R, int N, int K, const Epi& epi, cudaStream_t stream,
+                          const LnFuse* ln = nullptr, bool* ln_done = nullptr) {
     if (!c || !c->encode) { fprintf(stderr, "ptts_b200: tensor-map encoder unavailable\n"); abort(); }
     constexpr bool f16 = std::is_same<T, __half>::value;
     const TcGeom g = tc_geometry(R, K, amap, a_rps);
@@ -495,9 +543,17 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     if (bn == 128) launch(gemm_tc_kernel<128>, TcCfg<128>::SMEM);
     else if (bn == 64) launch(gemm_tc_kernel<64>, TcCfg<64>::SMEM);
     else launch(gemm_tc_kernel<32>, TcCfg<32>::SMEM);
+    if (ln_done) *ln_done = false;
     if (splits > 1) {
-        const long long quads = (long long)R * N / 4;
-        splitk_reduce_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(c->ws, splits, (long long)R * N, R, N, epi);
+        const bool fuse = ln && ln->out && epi.mode == EPI_GENERIC && !epi.rowmul && epi.out2_type == OUT2_NONE && (N == 1024 || N == 512);
+        if (fuse) {
+            if (N == 1024) splitk_reduce_ln_kernel<1024><<<(R + 7) / 8, 256, 0, stream>>>(c->ws, splits, (long long)R * N, R, epi, *ln);
+            else splitk_reduce_ln_kernel<512><<<(R + 7) / 8, 256, 0, stream>>>(c->ws, splits, (long long)R * N, R, epi, *ln);
+            if (ln_done) *ln_done = true;
+        } else {
+            const long long quads = (long long)R * N / 4;
+            splitk_reduce_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(c->ws, splits, (long long)R * N, R, N, epi);
+        }
         return 2;
     }
     return 1;
