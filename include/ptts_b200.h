@@ -37,6 +37,7 @@ typedef struct b200_config {
     int gemm_path;        /* 0 = auto (tcgen05 for large row counts), 1 = CUDA-core only (validation path)          */
     int max_prefill_rows; /* rows per prefill chunk (0 = default 512)                                               */
     int cuda_graphs;      /* 1 = replay the per-frame step as a CUDA graph (captured on second use of a shape)       */
+    int pdl;              /* 1 = programmatic dependent launch: each kernel's prologue overlaps its predecessor's tail  */
 } b200_config;
 
 B200_API void b200_default_config(b200_config* cfg);

@@ -22,7 +22,7 @@ LDIM = 32
 class B200Config(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("max_slots", ctypes.c_int), ("max_voices", ctypes.c_int), ("kv_capacity", ctypes.c_int),
                 ("kv_f32", ctypes.c_int), ("mimi_mask_mode", ctypes.c_int), ("convt_split", ctypes.c_int), ("gemm_path", ctypes.c_int),
-                ("max_prefill_rows", ctypes.c_int), ("cuda_graphs", ctypes.c_int)]
+                ("max_prefill_rows", ctypes.c_int), ("cuda_graphs", ctypes.c_int), ("pdl", ctypes.c_int)]
 
 
 _lib = None

@@ -20,6 +20,24 @@
 
 namespace ptts {
 
+// Programmatic dependent launch (PDL): every kernel of the per-frame step starts with pdl_prologue(): it lets the NEXT kernel's
+// CTAs be scheduled early (their prologue - barrier init, TMEM allocation, descriptor prefetch - overlaps this kernel's tail)
+// and then waits until the PREVIOUS kernel has completed and flushed its memory before touching any data.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = pdl ? 1 : 0;
+    PTTS_CUDA_CHECK(cudaLaunchKernelEx(&lc, kernel, KArgs(args)...));
+}
+
 // ---- model constants (reference src/config.h:53-87, models/defaults.h, modules/transformer.h:297-300) ----
 constexpr int D_MODEL = 1024, N_HEADS = 16, D_HEAD = 64, N_LAYERS = 6, D_FF = 4096, LDIM = 32;
 constexpr int D_FLOW = 512, N_RES = 6;
@@ -42,17 +60,23 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Activations. The epilogues evaluate ~150 M of these per frame batch, so they use the hardware exponential
+// (ex2.approx via __expf, relative error ~2^-22) instead of libdevice's expm1f/tanhf (40+ instructions each): with those the
+// SEANet GEMM epilogues were instruction-issue bound (ncu: 66 thread-instructions per output element, profiles/).
+// Every result is rounded to f16/bf16 right after, which swamps the difference (parity unchanged, tests/test_gpu_parity.py).
+//
 // ggml_gelu on CPU: tanh form through an f16 table (input and output rounded to f16); reference
 // modules/transformer.h:271, modules/mimi_transformer.h:959 + SURVEY.md Appendix C.
 __device__ __forceinline__ float gelu_ggml(float x) {
     if (x <= -10.0f) return 0.0f;
     if (x >= 10.0f) return x;
-    float xf = __half2float(__float2half_rn(x));
-    float g = 0.5f * xf * (1.0f + tanhf(0.79788456080286535587989211986876f * xf * (1.0f + 0.044715f * xf * xf)));
-    return __half2float(__float2half_rn(g));
+    const float xf = __half2float(__float2half_rn(x));
+    const float u = 0.79788456080286535587989211986876f * xf * (1.0f + 0.044715f * xf * xf);
+    const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));          // tanh(u)
+    return __half2float(__float2half_rn(0.5f * xf * (1.0f + t)));
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
-__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
 __device__ __forceinline__ float apply_act(float v, int act) {
     switch (act) {
         case ACT_GELU: return gelu_ggml(v);

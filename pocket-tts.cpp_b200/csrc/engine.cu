@@ -35,6 +35,7 @@ struct b200_engine {
     std::map<std::string, HostTensor> host;
     std::vector<void*> allocs;
     bool finalized = false;
+    bool pdl_active = false;   // programmatic dependent launch for the current enqueue (small batches only, see run_graphed)
     long long launches = 0;
     uint64_t seed = 0; unsigned long long* d_seed = nullptr;
     // CUDA graphs of the per-frame step, keyed by (kind, slot0, n, injected); first use runs eagerly (warm-up), second captures
@@ -182,10 +183,10 @@ struct b200_engine {
         }
         if (R <= 8) {
             const int warps = (N + 1) / 2, blocks = (warps + 7) / 8;
-            gemv_small_kernel<T, 8><<<blocks, 256, 0, stream>>>(A, amap, a_rps, W, R, N, K, epi);
+            launch_k(pdl_active, gemv_small_kernel<T, 8>, dim3(blocks), dim3(256), (size_t)(0), stream, A, amap, a_rps, W, R, N, K, epi);
         } else {
             dim3 grid((N + 63) / 64, (R + 63) / 64);
-            gemm_ffma_kernel<T><<<grid, 256, 0, stream>>>(A, amap, a_rps, W, R, N, K, epi);
+            launch_k(pdl_active, gemm_ffma_kernel<T>, dim3(grid), dim3(256), (size_t)(0), stream, A, amap, a_rps, W, R, N, K, epi);
         }
         launches++;
         return false;
@@ -203,7 +204,7 @@ struct b200_engine {
         bool ln1_done = false;                                   // norm1 of layer l already produced by layer l-1's linear2 reduction
         for (int l = 0; l < N_LAYERS; l++) {
             auto& L = fl[l];
-            if (!ln1_done) { layernorm_kernel<D_MODEL><<<(R + 7) / 8, 256, 0, stream>>>(h, rows(D_MODEL), BIG, R, 1e-5f, L.n1w, L.n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++; }
+            if (!ln1_done) { launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n1w, L.n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++; }
             Epi e; e.mode = EPI_FLOW_QKV; e.row_slot = row_slot; e.row_pos = row_pos; e.cs = cs; e.kv_f32 = cfg.kv_f32;
             e.kv_slot_stride = kv_slot_stride; e.q_out_f32 = q;
             if (cfg.kv_f32) { e.kcache = (float*)kc + l * kv_layer_stride; e.vcache = (float*)vc + l * kv_layer_stride; }
@@ -212,20 +213,20 @@ struct b200_engine {
             const int sg = seg_begin(0);
             if (cfg.kv_f32) {
                 const size_t smem = (size_t)cfg.kv_capacity * sizeof(float);
-                attn_flow_kernel<float><<<dim3(R, N_HEADS), 128, smem, stream>>>(q, (const float*)e.kcache, (const float*)e.vcache, kv_slot_stride, row_slot, row_pos, att_bf);
+                launch_k(pdl_active, attn_flow_kernel<float>, dim3(R, N_HEADS), dim3(128), (size_t)(smem), stream, q, (const float*)e.kcache, (const float*)e.vcache, kv_slot_stride, row_slot, row_pos, att_bf);
             } else {
                 // enough CTAs for ~4 waves of one 128 KB-smem CTA per SM; each split streams >= a few dozen cache rows
                 int splits = (148 * 4 + R - 1) / R; splits = std::max(1, std::min(splits, AF_MAX_SPLITS));
-                attn_flow_split_kernel<<<dim3(splits, R), 288, AF_SMEM, stream>>>(q, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, kv_slot_stride,
+                launch_k(pdl_active, attn_flow_split_kernel, dim3(splits, R), dim3(288), (size_t)(AF_SMEM), stream, q, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, kv_slot_stride,
                                                                                   row_slot, row_pos, splits, af_ml, af_acc, att_bf);
-                if (splits > 1) { attn_flow_merge_kernel<<<R, 256, 0, stream>>>(af_ml, af_acc, splits, att_bf); launches++; }
+                if (splits > 1) { launch_k(pdl_active, attn_flow_merge_kernel, dim3(R), dim3(256), (size_t)(0), stream, af_ml, af_acc, splits, att_bf); launches++; }
             }
             launches++;
             seg_end(sg);
             Epi eo; eo.resid = h; eo.resid_map = rows(D_MODEL); eo.out = h; eo.out_map = rows(D_MODEL);
             LnFuse f2; f2.w = L.n2w; f2.b = L.n2b; f2.eps = 1e-5f; f2.out = n_bf;
             if (!lin(att_bf, L.out_proj, R, eo, &f2)) {
-                layernorm_kernel<D_MODEL><<<(R + 7) / 8, 256, 0, stream>>>(h, rows(D_MODEL), BIG, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
+                launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
             }
             Epi e1; e1.out2 = ff_bf; e1.out2_map = rows(D_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
             lin(n_bf, L.lin1, R, e1);
@@ -242,7 +243,7 @@ struct b200_engine {
     // out_norm + EOS + 1-step LSD head over R rows of `h` (reference models/flow_lm.h:114-142, modules/mlp.h:233-251).
     void flow_head(int R) {
         const int BIG = 1 << 30;
-        head_pre_kernel<<<(R + 7) / 8, 256, 0, stream>>>(h, R, onw, onb, w_eos, b_eos, c_bf, eos);
+        launch_k(pdl_active, head_pre_kernel, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, h, R, onw, onb, w_eos, b_eos, c_bf, eos);
         // y = t_combined + cond_embed(c); sy = silu(y)
         Epi ec; ec.resid = t_combined; ec.resid_map = RowMap{}; ec.out2 = sy_bf; ec.out2_map = rows(D_FLOW); ec.out2_type = OUT2_BF16; ec.act = ACT_SILU;
         lin(c_bf, cond_embed, R, ec);
@@ -253,14 +254,14 @@ struct b200_engine {
         lin(noise_bf, input_proj, R, ei);
         for (int r = 0; r < N_RES; r++) {
             const float* m = mod + r * 3 * D_FLOW;
-            layernorm_kernel<D_FLOW><<<(R + 7) / 8, 256, 0, stream>>>(xh, rows(D_FLOW), BIG, R, 1e-6f, rb[r].lnw, rb[r].lnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
+            launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, rb[r].lnw, rb[r].lnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
             Epi e0; e0.out2 = h1_bf; e0.out2_map = rows(D_FLOW); e0.out2_type = OUT2_BF16; e0.act = ACT_SILU;
             lin(hn_bf, rb[r].mlp0, R, e0);
             Epi e2; e2.rowmul = m + 2 * D_FLOW; e2.rowmul_ld = ada_all.out; e2.resid = xh; e2.resid_map = rows(D_FLOW); e2.out = xh; e2.out_map = rows(D_FLOW);
             lin(h1_bf, rb[r].mlp2, R, e2);
         }
         const float* m = mod + N_RES * 3 * D_FLOW;
-        layernorm_kernel<D_FLOW><<<(R + 7) / 8, 256, 0, stream>>>(xh, rows(D_FLOW), BIG, R, 1e-6f, fnw, fnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
+        launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, fnw, fnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
         Epi ef; ef.resid = noise_f32; ef.resid_map = rows(LDIM); ef.out = latent; ef.out_map = rows(LDIM);
         lin(hn_bf, final_lin, R, ef);
         launches += 2 + N_RES;
@@ -269,19 +270,19 @@ struct b200_engine {
     // Mimi decoder for slots [slot0, slot0+n) from lat_f32 (reference models/mimi.h:85-104).
     void mimi(int slot0, int n) {
         const int BIG = 1 << 30, R = n * M_T;
-        mimi_front_kernel<<<n, M_DIM, 0, stream>>>(slot0, lat_f32, emb_std, emb_mean, wq, wup, bup, e_prev, mx);
+        launch_k(pdl_active, mimi_front_kernel, dim3(n), dim3(M_DIM), (size_t)(0), stream, slot0, lat_f32, emb_std, emb_mean, wq, wup, bup, e_prev, mx);
         float* x = mx + (long long)slot0 * M_T * M_DIM;
         const int s_mtf = seg_begin(3);
         for (int l = 0; l < M_LAYERS; l++) {
             auto& L = ml[l];
-            layernorm_kernel<M_DIM><<<(R + 7) / 8, 256, 0, stream>>>(x, rows(M_DIM), BIG, R, 0.0f, L.n1w, L.n1b, nullptr, nullptr, 0, mn_bf, nullptr);
+            launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n1w, L.n1b, nullptr, nullptr, 0, mn_bf, nullptr);
             Epi e; e.mode = EPI_MIMI_QKV; e.row_slot = mrow_slot; e.row_pos = mrow_pos; e.cs = mcs; e.kv_slot_stride = mkv_slot_stride;
             e.kcache = mkc + l * mkv_layer_stride; e.vcache = mvc + l * mkv_layer_stride; e.q_out_bf16 = mq_bf;
             lin(mn_bf, L.in_proj, R, e);
-            attn_mimi_kernel<<<dim3(n, M_HEADS), 256, AM_SMEM, stream>>>(mq_bf, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, mimi_off, cfg.mimi_mask_mode, matt_bf);
+            launch_k(pdl_active, attn_mimi_kernel, dim3(n, M_HEADS), dim3(256), (size_t)(AM_SMEM), stream, mq_bf, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, mimi_off, cfg.mimi_mask_mode, matt_bf);
             Epi eo; eo.colscale = L.ls1; eo.resid = x; eo.resid_map = rows(M_DIM); eo.out = x; eo.out_map = rows(M_DIM);
             lin(matt_bf, L.out_proj, R, eo);
-            layernorm_kernel<M_DIM><<<(R + 7) / 8, 256, 0, stream>>>(x, rows(M_DIM), BIG, R, 0.0f, L.n2w, L.n2b, nullptr, nullptr, 0, mn_bf, nullptr);
+            launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n2w, L.n2b, nullptr, nullptr, 0, mn_bf, nullptr);
             Epi e1; e1.out2 = mff_bf; e1.out2_map = rows(M_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
             lin(mn_bf, L.lin1, R, e1);
             Epi e2; e2.colscale = L.ls2; e2.resid = x; e2.resid_map = rows(M_DIM); e2.out = x; e2.out_map = rows(M_DIM);
@@ -297,7 +298,7 @@ struct b200_engine {
         const int o2t = cfg.convt_split ? OUT2_F16_SPLIT : OUT2_F16;
         {
             const long long tot = (long long)R * M_DIM;
-            cast_f16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(x, smap(16LL * 512, 512, 0), buf0 + slot0 * s0, smap(s0, 512, 6 * 512), T0, R, M_DIM);
+            launch_k(pdl_active, cast_f16_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), (size_t)(0), stream, x, smap(16LL * 512, 512, 0), buf0 + slot0 * s0, smap(s0, 512, 6 * 512), T0, R, M_DIM);
         }
         { Epi e; e.rps = T0; e.bias = c0.b; e.act = ACT_ELU; e.out2 = buf2 + slot0 * s2; e.out2_map = smap(s2, C2, C2); e.out2_type = o2t; e.split_off = 512;
           gemm<__half>(buf0 + slot0 * s0, smap(s0, 512, 0), T0, c0.w, n * T0, c0.N, c0.K, e); }
@@ -327,17 +328,17 @@ struct b200_engine {
           gemm<__half>(buf9b + slot0 * s9b, smap(s9b, 64, 0), T3, r9b.w, n * T3, r9b.N, r9b.K, e); }
         {
             const int Rr = n * T3;
-            conv_n1_kernel<<<(Rr * 4 + 255) / 256, 256, 0, stream>>>(buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm + (long long)slot0 * FRAME);
+            launch_k(pdl_active, conv_n1_kernel, dim3((Rr * 4 + 255) / 256), dim3(256), (size_t)(0), stream, buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm + (long long)slot0 * FRAME);
         }
-        shift_states_kernel<<<dim3(n, shifts.n), 128, 0, stream>>>(shifts, slot0, mimi_off);
+        launch_k(pdl_active, shift_states_kernel, dim3(n, shifts.n), dim3(128), (size_t)(0), stream, shifts, slot0, mimi_off);
         launches += 4;
         seg_end(s_sea);
     }
 
     void prepare_step(int slot0, int n) {
-        prepare_step_kernel<<<(n * M_T + 255) / 256, 256, 0, stream>>>(slot0, n, cur_len, mimi_off, row_slot, row_pos, mrow_slot, mrow_pos);
-        rope_table_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(row_pos, freq_flow, cs, n);
-        rope_table_kernel<<<(n * M_T * 32 + 255) / 256, 256, 0, stream>>>(mrow_pos, freq_mimi, mcs, n * M_T);
+        launch_k(pdl_active, prepare_step_kernel, dim3((n * M_T + 255) / 256), dim3(256), (size_t)(0), stream, slot0, n, cur_len, mimi_off, row_slot, row_pos, mrow_slot, mrow_pos);
+        launch_k(pdl_active, rope_table_kernel, dim3((n * 32 + 255) / 256), dim3(256), (size_t)(0), stream, row_pos, freq_flow, cs, n);
+        launch_k(pdl_active, rope_table_kernel, dim3((n * M_T * 32 + 255) / 256), dim3(256), (size_t)(0), stream, mrow_pos, freq_mimi, mcs, n * M_T);
         launches += 3;
     }
 
@@ -351,9 +352,9 @@ struct b200_engine {
         flow_forward(n);
         seg_end(s_flow);
         const int s_head = seg_begin(2);
-        noise_kernel<<<(n * LDIM + 127) / 128, 128, 0, stream>>>(slot0, n, injected ? noise_inj : nullptr, d_seed, temp, gen_step, noise_f32, noise_bf);
+        launch_k(pdl_active, noise_kernel, dim3((n * LDIM + 127) / 128), dim3(128), (size_t)(0), stream, slot0, n, injected ? noise_inj : nullptr, d_seed, temp, gen_step, noise_f32, noise_bf);
         flow_head(n);
-        step_logic_kernel<<<n, 32, 0, stream>>>(slot0, n, eos, latent, cur_len, gen_step, eos_step, max_gen, fae, active, lat_in_bf16, lat_f32, produced, eos_out);
+        launch_k(pdl_active, step_logic_kernel, dim3(n), dim3(32), (size_t)(0), stream, slot0, n, eos, latent, cur_len, gen_step, eos_step, max_gen, fae, active, lat_in_bf16, lat_f32, produced, eos_out);
         launches += 2;
         seg_end(s_head);
         mimi(slot0, n);
@@ -362,6 +363,10 @@ struct b200_engine {
 
     // kind 0 = full generation step, 1 = Mimi-only decode
     void run_graphed(int kind, int slot0, int n, bool injected) {
+        // PDL overlaps each kernel's prologue with its predecessor's tail: a large win when the step is launch/latency bound
+        // (batch 1: 0.76 -> 0.25 ms per Mimi step), a small loss once kernels fill the machine (measured at batch >= 16).
+        pdl_active = cfg.pdl != 0 && n <= 8;
+        tc->pdl = pdl_active;
         auto body = [&]() { if (kind == 0) step_enqueue(slot0, n, injected); else { prepare_step(slot0, n); mimi(slot0, n); } };
         if (!cfg.cuda_graphs || profiling) { body(); return; }
         GraphEntry& g = graphs[std::make_tuple(kind, slot0, n, injected ? 1 : 0)];
@@ -388,6 +393,7 @@ namespace {
 
 __global__ void set_meta_kernel(int slot, int cur, int mg, int f, float t, const float* bos, int* cur_len, int* gen_step, int* eos_step,
                                 int* max_gen, int* fae, int* active, float* temp, __nv_bfloat16* lat_in_bf16, float* lat_f32) {
+    pdl_prologue();
     const int i = threadIdx.x;
     if (i == 0) { cur_len[slot] = cur; gen_step[slot] = 0; eos_step[slot] = -1; max_gen[slot] = mg; fae[slot] = f; active[slot] = mg > 0 ? 1 : 0; temp[slot] = t; }
     if (i < LDIM) { lat_f32[slot * LDIM + i] = bos[i]; lat_in_bf16[slot * LDIM + i] = __float2bfloat16_rn(bos[i]); }
@@ -395,6 +401,7 @@ __global__ void set_meta_kernel(int slot, int cur, int mg, int f, float t, const
 
 // copy_states (reference models/flow_lm.h:70-78): restore the voice-conditioned prefix rows [0, len) of every layer.
 __global__ void copy_prefix_kernel(char* kc, char* vc, long long slot_bytes, long long layer_bytes, int dst_slot, int src_slot, long long bytes) {
+    pdl_prologue();
     char* base = (blockIdx.y & 1) ? vc : kc;
     const int layer = blockIdx.y >> 1;
     const uint4* src = reinterpret_cast<const uint4*>(base + layer * layer_bytes + src_slot * slot_bytes);
@@ -404,6 +411,7 @@ __global__ void copy_prefix_kernel(char* kc, char* vc, long long slot_bytes, lon
 }
 
 __global__ void copy_rows_f32_kernel(const float* src, float* dst, long long n) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
 }
@@ -418,7 +426,7 @@ extern "C" {
 void b200_default_config(b200_config* c) {
     memset(c, 0, sizeof(*c));
     c->device = 0; c->max_slots = 1; c->max_voices = 8; c->kv_capacity = 2048; c->kv_f32 = 0; c->mimi_mask_mode = 0;
-    c->convt_split = 1; c->gemm_path = 0; c->max_prefill_rows = 512; c->cuda_graphs = 1;
+    c->convt_split = 1; c->gemm_path = 0; c->max_prefill_rows = 512; c->cuda_graphs = 1; c->pdl = 1;
 }
 
 int b200_engine_create(const b200_config* cfg, b200_engine** out) {
@@ -640,6 +648,7 @@ int b200_finalize_weights(b200_engine* e) {
 // ---- ragged FlowLM prefill of `R` rows already staged in pin_i = [slot | pos | token] and (for voice rows) h ----
 static void prefill_rows(b200_engine* e, const std::vector<int>& slots, const std::vector<int>& pos, const std::vector<int>* tokens, const float* x_host) {
     const int total = (int)slots.size();
+    e->pdl_active = false; e->tc->pdl = false;
     for (int r0 = 0; r0 < total; r0 += e->cfg.max_prefill_rows) {
         const int R = std::min(e->cfg.max_prefill_rows, total - r0);
         e->ensure_pinned(x_host ? (size_t)R * D_MODEL : 1, (size_t)3 * R);
@@ -648,13 +657,13 @@ static void prefill_rows(b200_engine* e, const std::vector<int>& slots, const st
         PTTS_CUDA_CHECK(cudaMemcpyAsync(e->row_pos, e->pin_i + R, R * sizeof(int), cudaMemcpyHostToDevice, e->stream));
         if (tokens) {
             PTTS_CUDA_CHECK(cudaMemcpyAsync(e->tok, e->pin_i + 2 * R, R * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-            embed_gather_kernel<<<R, 256, 0, e->stream>>>(e->embed, e->tok, e->h, R);
+            launch_k(false, embed_gather_kernel, dim3(R), dim3(256), (size_t)(0), e->stream, e->embed, e->tok, e->h, R);
             e->launches++;
         } else {
             memcpy(e->pin_f, x_host + (size_t)r0 * D_MODEL, (size_t)R * D_MODEL * sizeof(float));
             PTTS_CUDA_CHECK(cudaMemcpyAsync(e->h, e->pin_f, (size_t)R * D_MODEL * sizeof(float), cudaMemcpyHostToDevice, e->stream));
         }
-        rope_table_kernel<<<(R * 32 + 255) / 256, 256, 0, e->stream>>>(e->row_pos, e->freq_flow, e->cs, R);
+        launch_k(false, rope_table_kernel, dim3((R * 32 + 255) / 256), dim3(256), (size_t)(0), e->stream, e->row_pos, e->freq_flow, e->cs, R);
         e->launches++;
         e->flow_forward(R);
         PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));   // pinned staging is reused by the next chunk
@@ -700,15 +709,15 @@ int b200_begin_sentences(b200_engine* e, int n, const int32_t* slots, const int3
         const int start = e->voice_len[v];
         if (start > 0) {
             const long long bytes = (long long)start * D_MODEL * elt;
-            copy_prefix_kernel<<<dim3(16, 2 * N_LAYERS), 256, 0, e->stream>>>((char*)e->kc, (char*)e->vc, e->kv_slot_stride * elt, e->kv_layer_stride * elt,
+            launch_k(false, copy_prefix_kernel, dim3(16, 2 * N_LAYERS), dim3(256), (size_t)(0), e->stream, (char*)e->kc, (char*)e->vc, e->kv_slot_stride * elt, e->kv_layer_stride * elt,
                                                                                slot, e->cfg.max_slots + v, bytes);
         }
-        reset_slot_kernel<<<dim3(1, e->shifts.n), 256, 0, e->stream>>>(e->shifts, slot, e->e_prev, e->mimi_off);
+        launch_k(false, reset_slot_kernel, dim3(1, e->shifts.n), dim3(256), (size_t)(0), e->stream, e->shifts, slot, e->e_prev, e->mimi_off);
         // KV capacity guard (the reference has none: 1000 rows, no bounds check, src/pocket_tts.cpp:367): clamp the cap.
         int mg = max_gen_len[i];
         const int room = e->cfg.kv_capacity - (start + nt);
         if (mg > room) mg = room;
-        set_meta_kernel<<<1, 32, 0, e->stream>>>(slot, start + nt, mg, frames_after_eos[i], temp[i], bos, e->cur_len, e->gen_step, e->eos_step,
+        launch_k(false, set_meta_kernel, dim3(1), dim3(32), (size_t)(0), e->stream, slot, start + nt, mg, frames_after_eos[i], temp[i], bos, e->cur_len, e->gen_step, e->eos_step,
                                                  e->max_gen, e->fae, e->active, e->temp, e->lat_in_bf16, e->lat_f32);
         e->h_cur_len[slot] = start + nt;
         e->launches += 3;
@@ -761,7 +770,7 @@ int b200_step(b200_engine* e, int slot0, int n, const float* noise, float* pcm, 
 int b200_mimi_reset(b200_engine* e, int slot0, int n) {
     if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
-    for (int s = slot0; s < slot0 + n; s++) reset_slot_kernel<<<dim3(1, e->shifts.n), 256, 0, e->stream>>>(e->shifts, s, e->e_prev, e->mimi_off);
+    for (int s = slot0; s < slot0 + n; s++) launch_k(false, reset_slot_kernel, dim3(1, e->shifts.n), dim3(256), (size_t)(0), e->stream, e->shifts, s, e->e_prev, e->mimi_off);
     e->launches += n;
     return B200_OK;
 }
@@ -811,8 +820,8 @@ int b200_debug_set_position(b200_engine* e, int slot0, int n, int pos, int max_g
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     const float* bos = e->d_bos;
     for (int s = slot0; s < slot0 + n; s++) {
-        reset_slot_kernel<<<dim3(1, e->shifts.n), 256, 0, e->stream>>>(e->shifts, s, e->e_prev, e->mimi_off);
-        set_meta_kernel<<<1, 32, 0, e->stream>>>(s, pos, max_gen_len, 1 << 28, 0.f, bos, e->cur_len, e->gen_step, e->eos_step, e->max_gen, e->fae, e->active,
+        launch_k(false, reset_slot_kernel, dim3(1, e->shifts.n), dim3(256), (size_t)(0), e->stream, e->shifts, s, e->e_prev, e->mimi_off);
+        launch_k(false, set_meta_kernel, dim3(1), dim3(32), (size_t)(0), e->stream, s, pos, max_gen_len, 1 << 28, 0.f, bos, e->cur_len, e->gen_step, e->eos_step, e->max_gen, e->fae, e->active,
                                                  e->temp, e->lat_in_bf16, e->lat_f32);
     }
     e->launches += 2 * n;
@@ -843,6 +852,7 @@ int b200_debug_gemm(b200_engine* e, int f16, const float* A, int n_slots, int ro
     const RowMap am = (n_slots == 1 && taps == 1) ? b200_engine::rows(C) : b200_engine::smap((long long)rows_buf * C, C, 0);
     const int rps = (n_slots == 1 && taps == 1) ? (1 << 30) : T;
     const int saved = e->cfg.gemm_path; e->cfg.gemm_path = path;
+    e->pdl_active = false; e->tc->pdl = false;
     int used_tc = 0;
     if (f16) { used_tc = (path == 0 && tc_gemm_supported<__half>(R, N, K, am, rps)); e->gemm<__half>((const __half*)dA, am, rps, (const __half*)dW, R, N, K, ep); }
     else { used_tc = (path == 0 && tc_gemm_supported<__nv_bfloat16>(R, N, K, am, rps)); e->gemm<__nv_bfloat16>((const __nv_bfloat16*)dA, am, rps, (const __nv_bfloat16*)dW, R, N, K, ep); }

@@ -89,6 +89,7 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int row, int col0, const
 template <typename T>
 __global__ void __launch_bounds__(256) gemm_ffma_kernel(const T* __restrict__ A, RowMap amap, int a_rps,
                                                         const T* __restrict__ W, int R, int N, int K, Epi epi) {
+    pdl_prologue();
     constexpr int BM = 64, BN = 64, BK = 32, LD = BM + 4;
     __shared__ __align__(16) float As[BK][LD];
     __shared__ __align__(16) float Ws[BK][LD];
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(const T* __restrict__ A,
 template <typename T, int RMAX>
 __global__ void __launch_bounds__(256) gemv_small_kernel(const T* __restrict__ A, RowMap amap, int a_rps,
                                                          const T* __restrict__ W, int R, int N, int K, Epi epi) {
+    pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int n0 = warp * 2;
     if (n0 >= N) return;
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(256) gemv_small_kernel(const T* __restrict__ A
 __global__ void __launch_bounds__(256) conv_n1_kernel(const __half* __restrict__ A, RowMap amap, int rps,
                                                       const __half* __restrict__ W, const float* __restrict__ bias,
                                                       int R, int K, float* __restrict__ out) {
+    pdl_prologue();
     const int gl = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = gl >> 2, g = gl & 3;                       // output sample, channel group (16 channels)
     const bool live = row < R;

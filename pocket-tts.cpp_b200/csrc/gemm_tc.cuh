@@ -8,7 +8,8 @@
 //
 // A operand: channel-last activations [slot][rows][C]. A causal conv window (K = taps * C) is NOT materialised:
 // k-block kb = (tap, c0) is loaded at row offset +tap, so a conv is the same kernel as a linear (taps == 1).
-// 128 GEMM rows are fetched as 128/CH chunks of CH consecutive rows so that tiles may span slots (T % CH == 0).
+// An M tile is ONE TMA box: 128 rows of one slot when a slot has >= 128 GEMM rows (the last tile of a slot is partly
+// out of bounds = zero-filled, its extra rows are discarded), or {T rows x floor(128/T) slots} when a slot has T < 128 rows.
 #pragma once
 #include "common.cuh"
 #include "gemm.cuh"
@@ -77,9 +78,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 struct TcParams {
     int R, N, K;
     int kb_per_tap;       // C / 64
-    int CH;               // rows per TMA chunk
-    int cps;              // chunks per slot (T / CH)
-    int total_chunks;     // ceil(R / CH) (plain) or n_slots * cps
+    int T;                // GEMM rows per slot (plain matrix: R)
+    int SB;               // slots per M tile when T < 128 (tile = SB x T rows, one TMA box {64, T, SB}); 1 otherwise
+    int tps;              // M tiles per slot when T >= 128 (tile = 128 rows of one slot, box {64, 128, 1})
+    int tiles_m;
+    uint32_t a_bytes;     // bytes one A box delivers (including zero-filled out-of-bounds rows)
+    int stages;           // shared-memory ring depth (runtime: deeper when only one CTA fits per SM anyway)
     uint32_t idesc;
     int splits;           // deterministic split-K: work item = (tile, split); partial sums go to a workspace
     int kb_per_split;
@@ -221,10 +225,13 @@ __device__ __forceinline__ void epi_qkv32(const Epi& e, int row, int col0, float
 
 template <int BN>
 struct TcCfg {
-    static constexpr int STAGES = (BN >= 128) ? 3 : 4;
+    static constexpr int STAGES_2CTA = (BN >= 128) ? 3 : 4;     // two CTAs per SM (default)
+    static constexpr int MAX_STAGES = 8;
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int W_BYTES = BN * 128;
-    static constexpr int SMEM = STAGES * (A_BYTES + W_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+    static constexpr int STAGES_1CTA = (200 * 1024 / STAGE_BYTES) < MAX_STAGES ? (200 * 1024 / STAGE_BYTES) : MAX_STAGES;
+    static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
     static constexpr int TMEM_COLS = 2 * BN;                   // double-buffered accumulator
 };
 
@@ -234,7 +241,8 @@ template <int BN>
 __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                                          const TcParams p, const Epi epi) {
     using Cfg = TcCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+    const int STAGES = p.stages;
+    pdl_trigger();                                             // the next kernel may start its prologue now
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = base, sW = base + STAGES * Cfg::A_BYTES;
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.K / 64;
     const int tiles_n = p.N / BN;
-    const int total_tiles = tiles_n * ((p.R + 127) / 128) * p.splits;      // work items (tile, split), split fastest
+    const int total_tiles = tiles_n * p.tiles_m * p.splits;                 // work items (tile, split), split fastest
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
@@ -264,29 +272,25 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr) : "memory");
+    pdl_wait();                                                // barriers/TMEM are set up; now wait for the producer kernel's data
 
     if (warp == 0) {
         if (lane == 0) {
-            // ===== TMA producer =====
-            const int cpt = 128 / p.CH;                         // chunks per tile
+            // ===== TMA producer: one A box + one W box per k-block =====
             uint32_t cnt = 0;
+            const uint32_t bytes = p.a_bytes + (uint32_t)Cfg::W_BYTES;
             for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
                 const int split = work % p.splits, tile = work / p.splits;
                 const int tile_n = tile % tiles_n, tile_m = tile / tiles_n;
-                const int g0 = tile_m * cpt;
-                int valid = p.total_chunks - g0; if (valid > cpt) valid = cpt;
-                const uint32_t bytes = (uint32_t)(valid * p.CH * 128 + Cfg::W_BYTES);
+                int slot, t0;
+                if (p.T >= 128) { slot = tile_m / p.tps; t0 = (tile_m % p.tps) * 128; } else { slot = tile_m * p.SB; t0 = 0; }
                 const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; kb++, cnt++) {
                     const int s = cnt % STAGES; const uint32_t ph = (cnt / STAGES) & 1;
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
                     const int tap = kb / p.kb_per_tap, c0 = (kb % p.kb_per_tap) * 64;
                     mbar_expect_tx(full0 + 8 * s, bytes);
-                    for (int c = 0; c < valid; c++) {
-                        const int g = g0 + c;
-                        const int slot = g / p.cps, t0 = (g % p.cps) * p.CH;
-                        tma_load_3d(sA + s * Cfg::A_BYTES + c * p.CH * 128, &tmA, full0 + 8 * s, c0, t0 + tap, slot);
-                    }
+                    tma_load_3d(sA + s * Cfg::A_BYTES, &tmA, full0 + 8 * s, c0, t0 + tap, slot);
                     tma_load_2d(sW + s * Cfg::W_BYTES, &tmW, full0 + 8 * s, kb * 64, tile_n * BN);
                 }
             }
@@ -322,10 +326,14 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
             const int split = work % p.splits, tile = work / p.splits;
             const int tile_n = tile % tiles_n, tile_m = tile / tiles_n;
             const int buf = it & 1;
-            const int row = tile_m * 128 + ew * 32 + lane;
+            int row_base, nvalid;
+            if (p.T >= 128) { const int slot = tile_m / p.tps, t0 = (tile_m % p.tps) * 128; row_base = slot * p.T + t0; nvalid = min(128, p.T - t0); }
+            else { row_base = tile_m * p.SB * p.T; nvalid = min(p.SB * p.T, p.R - row_base); }
+            const int ri = ew * 32 + lane;
+            const int row = row_base + ri;
             mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
             tc_fence_after();
-            const bool live = row < p.R;
+            const bool live = ri < nvalid;
             long long ro = 0, r2 = 0, rr = 0;
             if (live && epi.mode == EPI_GENERIC) {
                 ro = (epi.out ? epi.out_map.off(row, epi.rps) : 0) + (long long)split * p.ws_split_stride;
@@ -354,6 +362,7 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
 
 // Deterministic split-K reduction: sums the partial planes in a fixed order and applies the real epilogue.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long plane, int R, int N, const Epi epi) {
+    pdl_prologue();
     const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (idx >= (long long)R * N) return;
     const int row = (int)(idx / N), col = (int)(idx % N);
@@ -372,6 +381,7 @@ struct LnFuse { const float* w = nullptr; const float* b = nullptr; float eps = 
 
 template <int C>
 __global__ void __launch_bounds__(256) splitk_reduce_ln_kernel(const float* __restrict__ ws, int splits, long long plane, int R, const Epi epi, const LnFuse ln) {
+    pdl_prologue();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= R) return;
     constexpr int Q = C / 128;                                  // float4 groups per lane
@@ -424,6 +434,7 @@ struct TcPlanCache {
     std::map<std::tuple<const void*, long long, long long, long long, long long, int, int>, CUtensorMap> maps;
     bool attr_set[3] = {false, false, false};
     int num_sms = 148;
+    bool pdl = false;
     float* ws = nullptr; size_t ws_elems = 0;   // split-K partial sums
 };
 
@@ -437,7 +448,7 @@ inline TcPlanCache* tc_plan_cache_create() {
 }
 inline void tc_plan_cache_destroy(TcPlanCache* c) { if (c && c->ws) cudaFree(c->ws); delete c; }
 
-struct TcGeom { int C, taps, T, CH, cps, n_slots, rows_per_slot_buf; long long slot_stride; bool ok; };
+struct TcGeom { int C, taps, T, SB, tps, tiles_m, n_slots, rows_per_slot_buf, box_rows; long long slot_stride; bool ok; };
 
 inline TcGeom tc_geometry(int R, int K, const RowMap& amap, int a_rps) {
     TcGeom g{}; g.ok = false;
@@ -446,20 +457,18 @@ inline TcGeom tc_geometry(int R, int K, const RowMap& amap, int a_rps) {
     g.C = (int)C; g.taps = (int)(K / C);
     if (amap.slot_stride == 0) {                       // plain matrix (one "slot")
         if (g.taps != 1) return g;
-        g.T = R; g.CH = 128; g.cps = (R + 127) / 128; g.n_slots = 1; g.rows_per_slot_buf = R; g.slot_stride = (long long)R * C;
-        g.ok = true; return g;
+        g.T = R; g.n_slots = 1; g.rows_per_slot_buf = R; g.slot_stride = (long long)R * C;
+    } else {
+        if (R % a_rps != 0 || amap.slot_stride % C != 0) return g;
+        g.T = a_rps; g.n_slots = R / a_rps; g.slot_stride = amap.slot_stride; g.rows_per_slot_buf = (int)(amap.slot_stride / C);
+        if (g.rows_per_slot_buf < g.T + g.taps - 1) return g;
     }
-    if (R % a_rps != 0 || amap.slot_stride % C != 0) return g;
-    g.T = a_rps; g.n_slots = R / a_rps; g.slot_stride = amap.slot_stride; g.rows_per_slot_buf = (int)(amap.slot_stride / C);
-    if (g.rows_per_slot_buf < g.T + g.taps - 1) return g;
-    for (int ch : {128, 64, 32, 16}) if (g.T % ch == 0) { g.CH = ch; break; }
-    if (!g.CH) return g;
-    g.cps = g.T / g.CH;
+    if (g.T >= 128) { g.SB = 1; g.tps = (g.T + 127) / 128; g.tiles_m = g.n_slots * g.tps; g.box_rows = 128; }
+    else { g.SB = 128 / g.T; g.tps = 0; g.tiles_m = (g.n_slots + g.SB - 1) / g.SB; g.box_rows = g.T; }
     g.ok = true; return g;
 }
 
-inline int tc_pick_bn(int R, int N, int K = 0) {
-    const int tiles_m = (R + 127) / 128;
+inline int tc_pick_bn(int tiles_m, int N, int K = 0) {
     if (tiles_m <= 2 && K >= 512) {            // small-M, long-K: wide tiles + split-K (see tc_gemm_launch)
         for (int bn : {128, 64, 32}) if (N % bn == 0) return bn;
         return 0;
@@ -473,15 +482,16 @@ inline int tc_pick_bn(int R, int N, int K = 0) {
 
 template <typename T>
 inline bool tc_gemm_supported(int R, int N, int K, const RowMap& amap, int a_rps) {
-    if (R < 64 || K % 64 != 0 || N % 32 != 0) return false;
-    if (!tc_geometry(R, K, amap, a_rps).ok) return false;
-    return tc_pick_bn(R, N, K) != 0;
+    if (R < 16 || K % 64 != 0 || N % 32 != 0) return false;   // <16 rows: GEMV / CUDA-core kernels (weight-bandwidth bound anyway)
+    const TcGeom g = tc_geometry(R, K, amap, a_rps);
+    if (!g.ok) return false;
+    return tc_pick_bn(g.tiles_m, N, K) != 0;
 }
 
 inline const CUtensorMap* tc_get_map(TcPlanCache* c, const void* ptr, bool f16, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                                      const cuuint32_t* box) {
     auto key = std::make_tuple(ptr, (long long)dims[0], (long long)dims[1], (long long)(rank > 2 ? dims[2] : 1),
-                               (long long)(rank > 2 ? strides_bytes[1] : 0), (int)(box[1] | (box[0] << 16)), (int)f16);
+                               (long long)(rank > 2 ? strides_bytes[1] : 0), (int)(box[1] | (box[0] << 12) | ((rank > 2 ? box[2] : 1) << 22)), (int)f16);
     auto it = c->maps.find(key);
     if (it != c->maps.end()) return &it->second;
     CUtensorMap m;
@@ -499,18 +509,19 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     if (!c || !c->encode) { fprintf(stderr, "ptts_b200: tensor-map encoder unavailable\n"); abort(); }
     constexpr bool f16 = std::is_same<T, __half>::value;
     const TcGeom g = tc_geometry(R, K, amap, a_rps);
-    const int bn = tc_pick_bn(R, N, K);
+    const int bn = tc_pick_bn(g.tiles_m, N, K);
     cuuint64_t adims[3] = {(cuuint64_t)g.C, (cuuint64_t)g.rows_per_slot_buf, (cuuint64_t)g.n_slots};
     cuuint64_t astr[2] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.slot_stride * 2};
-    cuuint32_t abox[3] = {64, (cuuint32_t)g.CH, 1};
+    cuuint32_t abox[3] = {64, (cuuint32_t)g.box_rows, (cuuint32_t)g.SB};
     const CUtensorMap* ta = tc_get_map(c, A, f16, 3, adims, astr, abox);
     cuuint64_t wdims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t wstr[1] = {(cuuint64_t)K * 2};
     cuuint32_t wbox[2] = {64, (cuuint32_t)bn};
     const CUtensorMap* tw = tc_get_map(c, W, f16, 2, wdims, wstr, wbox);
-    TcParams p; p.R = R; p.N = N; p.K = K; p.kb_per_tap = g.C / 64; p.CH = g.CH; p.cps = g.cps;
+    TcParams p; p.R = R; p.N = N; p.K = K; p.kb_per_tap = g.C / 64; p.T = g.T; p.SB = g.SB; p.tps = g.tps; p.tiles_m = g.tiles_m;
+    p.a_bytes = (uint32_t)(128 * g.box_rows * g.SB);
     // Small-M GEMMs (FlowLM decode: R = batch) cannot fill the SMs with output tiles alone: split K deterministically.
-    const int num_kb = K / 64, tiles = (N / bn) * ((R + 127) / 128);
+    const int num_kb = K / 64, tiles = (N / bn) * g.tiles_m;
     int splits = 1;
     if (tiles * 2 <= c->num_sms && num_kb >= 8) {
         splits = std::min(std::min((2 * c->num_sms + tiles - 1) / tiles, num_kb / 4), 16);
@@ -530,29 +541,31 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     if (splits > 1) {
         kepi = Epi{}; kepi.out = c->ws; kepi.out_map.row_stride = N; p.ws_split_stride = (long long)R * N;
     } else { p.splits = 1; p.kb_per_split = num_kb; }
-    p.total_chunks = (amap.slot_stride == 0) ? (R + 127) / 128 : g.n_slots * g.cps;
     // instruction descriptor (kind::f16): D=f32, A/B = bf16|f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     p.idesc = (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int total_tiles = tiles * splits;
     dim3 grid(std::min(total_tiles, 2 * c->num_sms));
     const int bi = bn == 128 ? 0 : (bn == 64 ? 1 : 2);
-    auto launch = [&](auto kern, int smem) {
-        if (!c->attr_set[bi]) { PTTS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); c->attr_set[bi] = true; }
-        kern<<<grid, 320, smem, stream>>>(*ta, *tw, p, kepi);
+    const bool one_cta = total_tiles <= c->num_sms;             // at most one CTA per SM anyway: spend the whole smem on a deeper ring
+    auto launch = [&](auto kern, auto cfgtag) {
+        using Cfg = decltype(cfgtag);
+        if (!c->attr_set[bi]) { PTTS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(Cfg::STAGES_1CTA))); c->attr_set[bi] = true; }
+        p.stages = one_cta ? Cfg::STAGES_1CTA : Cfg::STAGES_2CTA;
+        launch_k(c->pdl, kern, grid, dim3(320), (size_t)Cfg::smem_bytes(p.stages), stream, *ta, *tw, p, kepi);
     };
-    if (bn == 128) launch(gemm_tc_kernel<128>, TcCfg<128>::SMEM);
-    else if (bn == 64) launch(gemm_tc_kernel<64>, TcCfg<64>::SMEM);
-    else launch(gemm_tc_kernel<32>, TcCfg<32>::SMEM);
+    if (bn == 128) launch(gemm_tc_kernel<128>, TcCfg<128>{});
+    else if (bn == 64) launch(gemm_tc_kernel<64>, TcCfg<64>{});
+    else launch(gemm_tc_kernel<32>, TcCfg<32>{});
     if (ln_done) *ln_done = false;
     if (splits > 1) {
         const bool fuse = ln && ln->out && epi.mode == EPI_GENERIC && !epi.rowmul && epi.out2_type == OUT2_NONE && (N == 1024 || N == 512);
         if (fuse) {
-            if (N == 1024) splitk_reduce_ln_kernel<1024><<<(R + 7) / 8, 256, 0, stream>>>(c->ws, splits, (long long)R * N, R, epi, *ln);
-            else splitk_reduce_ln_kernel<512><<<(R + 7) / 8, 256, 0, stream>>>(c->ws, splits, (long long)R * N, R, epi, *ln);
+            if (N == 1024) launch_k(c->pdl, splitk_reduce_ln_kernel<1024>, dim3((R + 7) / 8), dim3(256), 0, stream, (const float*)c->ws, splits, (long long)R * N, R, epi, *ln);
+            else launch_k(c->pdl, splitk_reduce_ln_kernel<512>, dim3((R + 7) / 8), dim3(256), 0, stream, (const float*)c->ws, splits, (long long)R * N, R, epi, *ln);
             if (ln_done) *ln_done = true;
         } else {
             const long long quads = (long long)R * N / 4;
-            splitk_reduce_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(c->ws, splits, (long long)R * N, R, N, epi);
+            launch_k(c->pdl, splitk_reduce_kernel, dim3((unsigned)((quads + 255) / 256)), dim3(256), 0, stream, (const float*)c->ws, splits, (long long)R * N, R, N, epi);
         }
         return 2;
     }

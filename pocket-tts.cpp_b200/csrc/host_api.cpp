@@ -127,6 +127,7 @@ ptts_context_t* ptts_init(ggml_backend*, ggml_backend*, const char* model_path) 
     cfg.mimi_mask_mode = env_int("PTTS_B200_MIMI_CAUSAL", 0);
     cfg.gemm_path = env_int("PTTS_B200_GEMM_PATH", 0);
     cfg.cuda_graphs = env_int("PTTS_B200_CUDA_GRAPHS", 1);
+    cfg.pdl = env_int("PTTS_B200_PDL", 1);
     return init_with_config(model_path, cfg);
 }
 

@@ -11,6 +11,7 @@ namespace ptts {
 // (cos, sin)(pos * freq_i) per row. freq tables are computed on the host exactly like the reference's
 // two RoPE flavours (rope.h:36-38 for FlowLM, ggml_timestep_embedding for Mimi rope.h:8-20).
 __global__ void rope_table_kernel(const int* __restrict__ row_pos, const float* __restrict__ freq, float2* __restrict__ cs, int R) {
+    pdl_prologue();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= R * 32) return;
     const float rad = (float)row_pos[idx >> 5] * freq[idx & 31];
@@ -21,6 +22,7 @@ __global__ void rope_table_kernel(const int* __restrict__ row_pos, const float* 
 __global__ void prepare_step_kernel(int slot0, int n, const int* __restrict__ cur_len, const int* __restrict__ mimi_off,
                                     int* __restrict__ row_slot, int* __restrict__ row_pos,
                                     int* __restrict__ mrow_slot, int* __restrict__ mrow_pos) {
+    pdl_prologue();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < n) { row_slot[idx] = slot0 + idx; row_pos[idx] = cur_len[slot0 + idx]; }
     if (idx < n * M_T) { const int s = slot0 + idx / M_T; mrow_slot[idx] = s; mrow_pos[idx] = mimi_off[s] + idx % M_T; }
@@ -28,6 +30,7 @@ __global__ void prepare_step_kernel(int slot0, int n, const int* __restrict__ cu
 
 // Text prefill: x[r] = float(embed[token[r]])   (ggml_get_rows, reference conditioners/text.h:29-37)
 __global__ void embed_gather_kernel(const __nv_bfloat16* __restrict__ table, const int* __restrict__ tokens, float* __restrict__ x, int R) {
+    pdl_prologue();
     const int r = blockIdx.x;
     if (r >= R) return;
     const __nv_bfloat16* src = table + (long long)tokens[r] * D_MODEL;
@@ -44,6 +47,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         const float* __restrict__ shift, const float* __restrict__ scale, int mod_ld,
                                                         __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+    pdl_prologue();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= R) return;
     constexpr int PER = C / 32;
@@ -79,6 +83,7 @@ template <typename KV>
 __global__ void __launch_bounds__(128) attn_flow_kernel(const float* __restrict__ q, const KV* __restrict__ kc, const KV* __restrict__ vc,
                                                         long long kv_slot_stride, const int* __restrict__ row_slot,
                                                         const int* __restrict__ row_pos, __nv_bfloat16* __restrict__ out) {
+    pdl_prologue();
     extern __shared__ float sc[];                 // [len] scores
     __shared__ float qs[D_HEAD];
     __shared__ float red[4];
@@ -165,6 +170,7 @@ __global__ void __launch_bounds__(288, 1) attn_flow_split_kernel(const float* __
                                                                  const int* __restrict__ row_slot, const int* __restrict__ row_pos, int splits,
                                                                  float* __restrict__ ws_ml, float* __restrict__ ws_acc,
                                                                  __nv_bfloat16* __restrict__ out) {
+    pdl_prologue();
     extern __shared__ __align__(128) uint8_t af_smem[];
     const int row = blockIdx.y, split = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -300,6 +306,7 @@ __global__ void __launch_bounds__(288, 1) attn_flow_split_kernel(const float* __
 
 __global__ void __launch_bounds__(256) attn_flow_merge_kernel(const float* __restrict__ ws_ml, const float* __restrict__ ws_acc, int splits,
                                                               __nv_bfloat16* __restrict__ out) {
+    pdl_prologue();
     const int row = blockIdx.x, t = threadIdx.x, h = t >> 4;
     float M = -INFINITY;
     for (int s = 0; s < splits; s++) M = fmaxf(M, ws_ml[((long long)row * splits + s) * 32 + h]);
@@ -344,6 +351,7 @@ constexpr int AM_SMEM = (2 * M_CTX * D_HEAD) * 2 + M_T * 256 * 4 + M_T * D_HEAD 
 __global__ void __launch_bounds__(256) attn_mimi_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
                                                         const __nv_bfloat16* __restrict__ vc, long long kv_slot_stride, int slot0,
                                                         const int* __restrict__ mimi_off, int mask_mode, __nv_bfloat16* __restrict__ out) {
+    pdl_prologue();
     extern __shared__ __align__(16) uint8_t am_smem[];
     uint4* sK = reinterpret_cast<uint4*>(am_smem);                               // [250][8 chunks], chunk index XOR (row & 7)
     uint4* sV = sK + M_CTX * 8;                                                  // [250][8 chunks]
@@ -437,6 +445,7 @@ __global__ void __launch_bounds__(256) attn_mimi_kernel(const __nv_bfloat16* __r
 __global__ void __launch_bounds__(256) head_pre_kernel(const float* __restrict__ h, int R, const float* __restrict__ w, const float* __restrict__ b,
                                                        const __nv_bfloat16* __restrict__ w_eos, const float* __restrict__ b_eos,
                                                        __nv_bfloat16* __restrict__ c_bf16, float* __restrict__ eos) {
+    pdl_prologue();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= R) return;
     constexpr int PER = D_MODEL / 32;
@@ -480,6 +489,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
 
 __global__ void noise_kernel(int slot0, int n, const float* __restrict__ injected, const unsigned long long* __restrict__ seed_ptr, const float* __restrict__ temp,
                              const int* __restrict__ gen_step, float* __restrict__ noise_f32, __nv_bfloat16* __restrict__ noise_bf16) {
+    pdl_prologue();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * LDIM) return;
     const int r = idx / LDIM, i = idx % LDIM, slot = slot0 + r;
@@ -513,6 +523,7 @@ __global__ void step_logic_kernel(int slot0, int n, const float* __restrict__ eo
                                   const int* __restrict__ max_gen, const int* __restrict__ fae, int* __restrict__ active,
                                   __nv_bfloat16* __restrict__ lat_in_bf16, float* __restrict__ lat_f32, int* __restrict__ produced,
                                   float* __restrict__ eos_out) {
+    pdl_prologue();
     const int r = blockIdx.x, slot = slot0 + r, i = threadIdx.x;
     if (r >= n) return;
     __shared__ int emit;
@@ -549,6 +560,7 @@ __global__ void __launch_bounds__(512) mimi_front_kernel(int slot0, const float*
                                                          const float* __restrict__ emb_mean, const __half* __restrict__ wq,
                                                          const float* __restrict__ wup, const float* __restrict__ bup,
                                                          float* __restrict__ e_prev, float* __restrict__ x) {
+    pdl_prologue();
     __shared__ float z[LDIM];
     const int slot = slot0 + blockIdx.x, c = threadIdx.x;
     if (c < LDIM) z[c] = __half2float(__float2half_rn(__fadd_rn(__fmul_rn(emb_std[c], lat_f32[slot * LDIM + c]), emb_mean[c])));
@@ -569,6 +581,7 @@ __global__ void __launch_bounds__(512) mimi_front_kernel(int slot0, const float*
 
 // f32 [rows][C] -> f16 copy into a conv input buffer (rows placed after the state rows).
 __global__ void cast_f16_kernel(const float* __restrict__ x, RowMap xmap, __half* __restrict__ out, RowMap omap, int rps, int R, int C) {
+    pdl_prologue();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)R * C) return;
     const int row = (int)(idx / C), col = (int)(idx % C);
@@ -581,6 +594,7 @@ __global__ void cast_f16_kernel(const float* __restrict__ x, RowMap xmap, __half
 struct ShiftDesc { __half* buf; long long slot_stride; int S, T, C; };
 struct ShiftAll { ShiftDesc d[8]; int n; };
 __global__ void shift_states_kernel(ShiftAll sa, int slot0, int* __restrict__ mimi_off) {
+    pdl_prologue();
     const ShiftDesc d = sa.d[blockIdx.y];
     const int slot = slot0 + blockIdx.x;
     __half* base = d.buf + (long long)slot * d.slot_stride;
@@ -593,6 +607,7 @@ __global__ void shift_states_kernel(ShiftAll sa, int slot0, int* __restrict__ mi
 // Sentence start (reference src/pocket_tts.cpp:416-444, models/mimi.h:71-75): zero the carried conv state rows
 // and the upsampler state, reset the Mimi offset. The KV prefix restore is done with device copies by the host.
 __global__ void reset_slot_kernel(ShiftAll sa, int slot, float* __restrict__ e_prev, int* __restrict__ mimi_off) {
+    pdl_prologue();
     const ShiftDesc d = sa.d[blockIdx.y];
     __half* base = d.buf + (long long)slot * d.slot_stride;
     for (int i = threadIdx.x; i < d.S * d.C; i += blockDim.x) base[i] = __float2half_rn(0.f);

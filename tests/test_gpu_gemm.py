@@ -40,6 +40,9 @@ CASES = [
     (2, 480, 2, 256, 640, True),       # transposed conv as 2-tap GEMM, N = 5*128
     (1, 1920, 3, 64, 32, True),        # r9a: C = 64, N = 32
     (2, 1920, 1, 64, 64, True),        # r9b (padded channels)
+    (1, 16, 7, 512, 512, True),        # SEANet conv0 at batch 1 (16 rows, split-K)
+    (1, 16, 1, 512, 1536, False),      # Mimi in_proj at batch 1
+    (1, 32, 1, 1024, 4096, False),     # FlowLM linear1 at batch 32
 ]
 
 
