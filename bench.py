@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--kv-capacity", type=int, default=2048)
     ap.add_argument("--kv-f32", type=int, default=0)
     ap.add_argument("--gemm-path", type=int, default=0)
+    ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--cuda-graphs", type=int, default=1)
     ap.add_argument("--ref-frames-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -149,7 +151,8 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     # tokens of a 40-word paragraph ~ 60-75; voice prefix sized so that voice + text + steps/2 ~ kv_len
-    args.t_voice = max(16, args.kv_len - 70 - (args.steps + args.warmup) // 2)
+    args.untimed = max(args.warmup, 100)             # extended warm-up: also gives the clock sampler a loaded window
+    args.t_voice = max(16, args.kv_len - 45 - args.untimed - args.steps // 2)
 
     if args.impl == "reference":
         if rank != 0:
@@ -182,13 +185,13 @@ def main():
     d = default_model_dir(eos_mode="never", t_voice=args.t_voice, voices=["cosette"])
 
     B = args.batch
-    ctx = P.Context(d, device=local, max_slots=B, max_voices=1, kv_capacity=args.kv_capacity, kv_f32=args.kv_f32, gemm_path=args.gemm_path)
+    ctx = P.Context(d, device=local, max_slots=B, max_voices=1, kv_capacity=args.kv_capacity, kv_f32=args.kv_f32, gemm_path=args.gemm_path, pdl=args.pdl, cuda_graphs=args.cuda_graphs)
     eng = ctx.engine
     st = ctx.stream("cosette", temp=0.7)            # prefill of the (long) voice prefix
     # this rank's utterance slice: global utterance id = rank * B + i
     texts = [synth_paragraph(rank * B + i) for i in range(B)]
     toks = [ctx.tokenize(t) for t in texts]
-    total_steps = args.warmup + args.steps * 3 + 8 + 400  # warm-up + timed + clock-sampling filler + e2e + profiled passes
+    total_steps = args.untimed + args.steps * 3 + 8   # warm-up + timed + e2e + profiled passes
     eng.set_seed(1234 + rank)
     eng.begin_sentences(list(range(B)), [st.voice] * B, toks, [total_steps + 64] * B, [1 << 20] * B, [0.7] * B)
     eng.sync()
@@ -206,7 +209,7 @@ def main():
     sampler = ClockSampler(local); sampler.start()
     time.sleep(0.3)
     steps_done = 0
-    for _ in range(args.warmup):
+    for _ in range(args.untimed):
         eng.step_enqueue(0, B); steps_done += 1
     eng.sync()
     barrier()
@@ -227,11 +230,6 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
-    if ms < 400.0:                                     # keep the GPU under the same load until a few clock samples exist
-        t_end = time.time() + 0.4
-        while time.time() < t_end:
-            eng.step_enqueue(0, B); steps_done += 1
-            eng.sync()
     clocks = sampler.stop()
     mid_step = steps_done + args.steps / 2.0
     steps_done += args.steps

@@ -121,6 +121,10 @@ def _ip(a):
 def default_config(**kw) -> B200Config:
     cfg = B200Config()
     lib().b200_default_config(ctypes.byref(cfg))
+    for k in ("pdl", "cuda_graphs", "gemm_path", "kv_f32"):          # environment overrides, like ptts_init (host_api.cpp)
+        v = os.environ.get("PTTS_B200_" + k.upper())
+        if v not in (None, ""):
+            setattr(cfg, k, int(v))
     for k, v in kw.items():
         if not hasattr(cfg, k):
             raise AttributeError(k)

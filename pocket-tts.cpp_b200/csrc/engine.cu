@@ -35,7 +35,9 @@ struct b200_engine {
     std::map<std::string, HostTensor> host;
     std::vector<void*> allocs;
     bool finalized = false;
-    bool pdl_active = false;   // programmatic dependent launch for the current enqueue (small batches only, see run_graphed)
+    bool pdl_active = false;   // programmatic dependent launch for the kernels being enqueued (see run_graphed)
+    bool pdl_small = false, pdl_chain = false;
+    void set_pdl(bool on) { pdl_active = on; if (tc) tc->pdl = on; }
     long long launches = 0;
     uint64_t seed = 0; unsigned long long* d_seed = nullptr;
     // CUDA graphs of the per-frame step, keyed by (kind, slot0, n, injected); first use runs eagerly (warm-up), second captures
@@ -211,6 +213,8 @@ struct b200_engine {
             else { e.kcache = (__nv_bfloat16*)kc + l * kv_layer_stride; e.vcache = (__nv_bfloat16*)vc + l * kv_layer_stride; }
             lin(n_bf, L.in_proj, R, e);
             const int sg = seg_begin(0);
+            const bool pdl_saved = pdl_active;
+            set_pdl(pdl_small);                                  // the KV-streaming kernel fills the machine: no early dependents around it
             if (cfg.kv_f32) {
                 const size_t smem = (size_t)cfg.kv_capacity * sizeof(float);
                 launch_k(pdl_active, attn_flow_kernel<float>, dim3(R, N_HEADS), dim3(128), (size_t)(smem), stream, q, (const float*)e.kcache, (const float*)e.vcache, kv_slot_stride, row_slot, row_pos, att_bf);
@@ -222,6 +226,7 @@ struct b200_engine {
                 if (splits > 1) { launch_k(pdl_active, attn_flow_merge_kernel, dim3(R), dim3(256), (size_t)(0), stream, af_ml, af_acc, splits, att_bf); launches++; }
             }
             launches++;
+            set_pdl(pdl_saved);
             seg_end(sg);
             Epi eo; eo.resid = h; eo.resid_map = rows(D_MODEL); eo.out = h; eo.out_map = rows(D_MODEL);
             LnFuse f2; f2.w = L.n2w; f2.b = L.n2b; f2.eps = 1e-5f; f2.out = n_bf;
@@ -279,7 +284,9 @@ struct b200_engine {
             Epi e; e.mode = EPI_MIMI_QKV; e.row_slot = mrow_slot; e.row_pos = mrow_pos; e.cs = mcs; e.kv_slot_stride = mkv_slot_stride;
             e.kcache = mkc + l * mkv_layer_stride; e.vcache = mvc + l * mkv_layer_stride; e.q_out_bf16 = mq_bf;
             lin(mn_bf, L.in_proj, R, e);
-            launch_k(pdl_active, attn_mimi_kernel, dim3(n, M_HEADS), dim3(256), (size_t)(AM_SMEM), stream, mq_bf, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, mimi_off, cfg.mimi_mask_mode, matt_bf);
+            if (cfg.gemm_path == 0) launch_k(pdl_active, attn_mimi_mma_kernel, dim3((n * M_HEADS + 3) / 4), dim3(128), (size_t)0, stream, mq_bf, (const __nv_bfloat16*)e.kcache,
+                                             (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, n, mimi_off, cfg.mimi_mask_mode, matt_bf);
+            else launch_k(pdl_active, attn_mimi_kernel, dim3(n, M_HEADS), dim3(256), (size_t)(AM_SMEM), stream, mq_bf, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, mimi_off, cfg.mimi_mask_mode, matt_bf);
             Epi eo; eo.colscale = L.ls1; eo.resid = x; eo.resid_map = rows(M_DIM); eo.out = x; eo.out_map = rows(M_DIM);
             lin(matt_bf, L.out_proj, R, eo);
             launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n2w, L.n2b, nullptr, nullptr, 0, mn_bf, nullptr);
@@ -345,6 +352,7 @@ struct b200_engine {
     // One generation step for slots [slot0, slot0+n) (reference _stream_sentence_step, src/pocket_tts.cpp:446-492).
     void step_enqueue(int slot0, int n, bool injected) {
         const int s_all = seg_begin(5);
+        set_pdl(pdl_small || pdl_chain);
         prepare_step(slot0, n);
         const int s_flow = seg_begin(1);
         Epi e; e.out = h; e.out_map = rows(D_MODEL);
@@ -357,6 +365,7 @@ struct b200_engine {
         launch_k(pdl_active, step_logic_kernel, dim3(n), dim3(32), (size_t)(0), stream, slot0, n, eos, latent, cur_len, gen_step, eos_step, max_gen, fae, active, lat_in_bf16, lat_f32, produced, eos_out);
         launches += 2;
         seg_end(s_head);
+        set_pdl(pdl_small);
         mimi(slot0, n);
         seg_end(s_all);
     }
@@ -364,9 +373,11 @@ struct b200_engine {
     // kind 0 = full generation step, 1 = Mimi-only decode
     void run_graphed(int kind, int slot0, int n, bool injected) {
         // PDL overlaps each kernel's prologue with its predecessor's tail: a large win when the step is launch/latency bound
-        // (batch 1: 0.76 -> 0.25 ms per Mimi step), a small loss once kernels fill the machine (measured at batch >= 16).
-        pdl_active = cfg.pdl != 0 && n <= 8;
-        tc->pdl = pdl_active;
+        // (batch 1), a small loss once kernels fill the machine and the step is replayed as a graph (measured at batch >= 16:
+        // 3.53 ms/step without vs 3.62 ms with PDL at batch 256).
+        pdl_small = cfg.pdl >= 2 || (cfg.pdl == 1 && n <= 8);    // every kernel of the step
+        pdl_chain = cfg.pdl >= 2;                                 // (experiment) the chains of small kernels even at large batch: helps eager launches, hurts graph replay
+        set_pdl(pdl_small);
         auto body = [&]() { if (kind == 0) step_enqueue(slot0, n, injected); else { prepare_step(slot0, n); mimi(slot0, n); } };
         if (!cfg.cuda_graphs || profiling) { body(); return; }
         GraphEntry& g = graphs[std::make_tuple(kind, slot0, n, injected ? 1 : 0)];
@@ -630,7 +641,7 @@ int b200_finalize_weights(b200_engine* e) {
                             (const void*)layernorm_kernel<D_FLOW>, (const void*)gemm_tc_kernel<32>, (const void*)gemm_tc_kernel<64>, (const void*)gemm_tc_kernel<128>,
                             (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
                             (const void*)attn_flow_split_kernel, (const void*)attn_flow_merge_kernel, (const void*)noise_kernel, (const void*)head_pre_kernel,
-                            (const void*)step_logic_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)cast_f16_kernel,
+                            (const void*)step_logic_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma_kernel, (const void*)cast_f16_kernel,
                             (const void*)conv_n1_kernel, (const void*)shift_states_kernel};
         for (const void* k : ks) PTTS_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
@@ -648,7 +659,7 @@ int b200_finalize_weights(b200_engine* e) {
 // ---- ragged FlowLM prefill of `R` rows already staged in pin_i = [slot | pos | token] and (for voice rows) h ----
 static void prefill_rows(b200_engine* e, const std::vector<int>& slots, const std::vector<int>& pos, const std::vector<int>* tokens, const float* x_host) {
     const int total = (int)slots.size();
-    e->pdl_active = false; e->tc->pdl = false;
+    e->set_pdl(false);
     for (int r0 = 0; r0 < total; r0 += e->cfg.max_prefill_rows) {
         const int R = std::min(e->cfg.max_prefill_rows, total - r0);
         e->ensure_pinned(x_host ? (size_t)R * D_MODEL : 1, (size_t)3 * R);
@@ -852,7 +863,7 @@ int b200_debug_gemm(b200_engine* e, int f16, const float* A, int n_slots, int ro
     const RowMap am = (n_slots == 1 && taps == 1) ? b200_engine::rows(C) : b200_engine::smap((long long)rows_buf * C, C, 0);
     const int rps = (n_slots == 1 && taps == 1) ? (1 << 30) : T;
     const int saved = e->cfg.gemm_path; e->cfg.gemm_path = path;
-    e->pdl_active = false; e->tc->pdl = false;
+    e->set_pdl(false);
     int used_tc = 0;
     if (f16) { used_tc = (path == 0 && tc_gemm_supported<__half>(R, N, K, am, rps)); e->gemm<__half>((const __half*)dA, am, rps, (const __half*)dW, R, N, K, ep); }
     else { used_tc = (path == 0 && tc_gemm_supported<__nv_bfloat16>(R, N, K, am, rps)); e->gemm<__nv_bfloat16>((const __nv_bfloat16*)dA, am, rps, (const __nv_bfloat16*)dW, R, N, K, ep); }
