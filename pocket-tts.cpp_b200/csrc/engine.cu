@@ -206,7 +206,7 @@ struct b200_engine {
         bool ln1_done = false;                                   // norm1 of layer l already produced by layer l-1's linear2 reduction
         for (int l = 0; l < N_LAYERS; l++) {
             auto& L = fl[l];
-            if (!ln1_done) { launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n1w, L.n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++; }
+            if (!ln1_done) { launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n1w, L.n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++; }
             Epi e; e.mode = EPI_FLOW_QKV; e.row_slot = row_slot; e.row_pos = row_pos; e.cs = cs; e.kv_f32 = cfg.kv_f32;
             e.kv_slot_stride = kv_slot_stride; e.q_out_f32 = q;
             if (cfg.kv_f32) { e.kcache = (float*)kc + l * kv_layer_stride; e.vcache = (float*)vc + l * kv_layer_stride; }
@@ -231,7 +231,7 @@ struct b200_engine {
             Epi eo; eo.resid = h; eo.resid_map = rows(D_MODEL); eo.out = h; eo.out_map = rows(D_MODEL);
             LnFuse f2; f2.w = L.n2w; f2.b = L.n2b; f2.eps = 1e-5f; f2.out = n_bf;
             if (!lin(att_bf, L.out_proj, R, eo, &f2)) {
-                launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
+                launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
             }
             Epi e1; e1.out2 = ff_bf; e1.out2_map = rows(D_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
             lin(n_bf, L.lin1, R, e1);
@@ -248,7 +248,7 @@ struct b200_engine {
     // out_norm + EOS + 1-step LSD head over R rows of `h` (reference models/flow_lm.h:114-142, modules/mlp.h:233-251).
     void flow_head(int R) {
         const int BIG = 1 << 30;
-        launch_k(pdl_active, head_pre_kernel, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, h, R, onw, onb, w_eos, b_eos, c_bf, eos);
+        launch_k(pdl_active, head_pre_kernel, dim3(R), dim3(256), (size_t)(0), stream, h, R, onw, onb, w_eos, b_eos, c_bf, eos);
         // y = t_combined + cond_embed(c); sy = silu(y)
         Epi ec; ec.resid = t_combined; ec.resid_map = RowMap{}; ec.out2 = sy_bf; ec.out2_map = rows(D_FLOW); ec.out2_type = OUT2_BF16; ec.act = ACT_SILU;
         lin(c_bf, cond_embed, R, ec);
@@ -259,14 +259,14 @@ struct b200_engine {
         lin(noise_bf, input_proj, R, ei);
         for (int r = 0; r < N_RES; r++) {
             const float* m = mod + r * 3 * D_FLOW;
-            launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, rb[r].lnw, rb[r].lnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
+            launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3(R), dim3(D_FLOW / 4), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, rb[r].lnw, rb[r].lnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
             Epi e0; e0.out2 = h1_bf; e0.out2_map = rows(D_FLOW); e0.out2_type = OUT2_BF16; e0.act = ACT_SILU;
             lin(hn_bf, rb[r].mlp0, R, e0);
             Epi e2; e2.rowmul = m + 2 * D_FLOW; e2.rowmul_ld = ada_all.out; e2.resid = xh; e2.resid_map = rows(D_FLOW); e2.out = xh; e2.out_map = rows(D_FLOW);
             lin(h1_bf, rb[r].mlp2, R, e2);
         }
         const float* m = mod + N_RES * 3 * D_FLOW;
-        launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, fnw, fnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
+        launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3(R), dim3(D_FLOW / 4), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, fnw, fnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
         Epi ef; ef.resid = noise_f32; ef.resid_map = rows(LDIM); ef.out = latent; ef.out_map = rows(LDIM);
         lin(hn_bf, final_lin, R, ef);
         launches += 2 + N_RES;
@@ -280,7 +280,7 @@ struct b200_engine {
         const int s_mtf = seg_begin(3);
         for (int l = 0; l < M_LAYERS; l++) {
             auto& L = ml[l];
-            launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n1w, L.n1b, nullptr, nullptr, 0, mn_bf, nullptr);
+            launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3(R), dim3(M_DIM / 4), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n1w, L.n1b, nullptr, nullptr, 0, mn_bf, nullptr);
             Epi e; e.mode = EPI_MIMI_QKV; e.row_slot = mrow_slot; e.row_pos = mrow_pos; e.cs = mcs; e.kv_slot_stride = mkv_slot_stride;
             e.kcache = mkc + l * mkv_layer_stride; e.vcache = mvc + l * mkv_layer_stride; e.q_out_bf16 = mq_bf;
             lin(mn_bf, L.in_proj, R, e);
@@ -289,10 +289,16 @@ struct b200_engine {
             else launch_k(pdl_active, attn_mimi_kernel, dim3(n, M_HEADS), dim3(256), (size_t)(AM_SMEM), stream, mq_bf, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, mimi_off, cfg.mimi_mask_mode, matt_bf);
             Epi eo; eo.colscale = L.ls1; eo.resid = x; eo.resid_map = rows(M_DIM); eo.out = x; eo.out_map = rows(M_DIM);
             lin(matt_bf, L.out_proj, R, eo);
-            launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3((R + 7) / 8), dim3(256), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n2w, L.n2b, nullptr, nullptr, 0, mn_bf, nullptr);
+            launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3(R), dim3(M_DIM / 4), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n2w, L.n2b, nullptr, nullptr, 0, mn_bf, nullptr);
             Epi e1; e1.out2 = mff_bf; e1.out2_map = rows(M_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
             lin(mn_bf, L.lin1, R, e1);
-            Epi e2; e2.colscale = L.ls2; e2.resid = x; e2.resid_map = rows(M_DIM); e2.out = x; e2.out_map = rows(M_DIM);
+            Epi e2; e2.colscale = L.ls2; e2.resid = x; e2.resid_map = rows(M_DIM);
+            if (l + 1 < M_LAYERS) { e2.out = x; e2.out_map = rows(M_DIM); }
+            else {
+                // last layer: the only consumer is SEANet's first conv, so write its f16 input rows (after the 6 carried rows) directly
+                e2.rps = M_T; e2.resid_map = smap((long long)M_T * M_DIM, M_DIM, 0);
+                e2.out2 = buf0 + slot0 * 22LL * 512; e2.out2_map = smap(22LL * 512, 512, 6 * 512); e2.out2_type = OUT2_F16;
+            }
             lin(mff_bf, L.lin2, R, e2);
             launches += 3;
         }
@@ -303,10 +309,6 @@ struct b200_engine {
         const long long s0 = 22LL * 512, s2 = 17LL * C2, s3a = 98LL * 256, s3b = 96LL * 128, s5 = 97LL * C5, s6a = 482LL * 128, s6b = 480LL * 64,
                         s8 = 481LL * C8, s9a = 1922LL * 64, s9b = 1920LL * 64, s11 = 1922LL * 64;
         const int o2t = cfg.convt_split ? OUT2_F16_SPLIT : OUT2_F16;
-        {
-            const long long tot = (long long)R * M_DIM;
-            launch_k(pdl_active, cast_f16_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), (size_t)(0), stream, x, smap(16LL * 512, 512, 0), buf0 + slot0 * s0, smap(s0, 512, 6 * 512), T0, R, M_DIM);
-        }
         { Epi e; e.rps = T0; e.bias = c0.b; e.act = ACT_ELU; e.out2 = buf2 + slot0 * s2; e.out2_map = smap(s2, C2, C2); e.out2_type = o2t; e.split_off = 512;
           gemm<__half>(buf0 + slot0 * s0, smap(s0, 512, 0), T0, c0.w, n * T0, c0.N, c0.K, e); }
         { Epi e; e.rps = T0; e.bias = t2.b; e.out = y3 + slot0 * 96LL * 256; e.out_map = smap(96LL * 256, 1536, 0);
@@ -338,7 +340,7 @@ struct b200_engine {
             launch_k(pdl_active, conv_n1_kernel, dim3((Rr * 4 + 255) / 256), dim3(256), (size_t)(0), stream, buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm + (long long)slot0 * FRAME);
         }
         launch_k(pdl_active, shift_states_kernel, dim3(n, shifts.n), dim3(128), (size_t)(0), stream, shifts, slot0, mimi_off);
-        launches += 4;
+        launches += 3;
         seg_end(s_sea);
     }
 
@@ -554,9 +556,14 @@ int b200_finalize_weights(b200_engine* e) {
     // Mimi
     {
         auto* q = e->find("mimi.quantizer.output_proj.weight");
-        std::vector<__half> qh(q->f.size()); for (size_t i = 0; i < qh.size(); i++) qh[i] = __float2half_rn(q->f[i]);
+        // both stored transposed ([tap or input][channel]) so that lane = channel reads coalesced lines (mimi_front_kernel)
+        std::vector<__half> qh(q->f.size());
+        for (int c = 0; c < M_DIM; c++) for (int i = 0; i < LDIM; i++) qh[(size_t)i * M_DIM + c] = __float2half_rn(q->f[(size_t)c * LDIM + i]);
         e->wq = e->upload(qh);
-        e->wup = e->up_f32("mimi.upsample.convtr.convtr.weight"); e->bup = e->up_f32("mimi.upsample.convtr.convtr.bias", false);
+        auto* up = e->find("mimi.upsample.convtr.convtr.weight");
+        std::vector<float> ut(up->f.size());
+        for (int c = 0; c < M_DIM; c++) for (int k = 0; k < 32; k++) ut[(size_t)k * M_DIM + c] = up->f[(size_t)c * 32 + k];
+        e->wup = e->upload(ut); e->bup = e->up_f32("mimi.upsample.convtr.convtr.bias", false);
     }
     for (int l = 0; l < M_LAYERS; l++) {
         const std::string p = "mimi.decoder_transformer.transformer.layers." + std::to_string(l) + ".";

@@ -90,77 +90,40 @@ struct TcParams {
     long long ws_split_stride;   // elements between the partial-sum planes of consecutive splits
 };
 
-// ---- GENERIC epilogue for 32 consecutive columns of one row; loads are issued before any arithmetic/stores ----
-__device__ __forceinline__ void epi_generic32(const Epi& e, int row, int col0, float (&v)[32], long long ro, long long r2, long long rr) {
+// ---- GENERIC epilogue for 4 consecutive columns of one row (bias / colscale already loaded for these columns) ----
+// Called after the accumulator chunk was transposed through shared memory, so that the 8 lanes sharing a row cover 128 contiguous
+// bytes (f32) and every warp-level load/store touches 4 full lines instead of 32 partial ones.
+__device__ __forceinline__ void epi_generic4(const Epi& e, int row, int col, float (&v)[4], long long ro, long long r2, long long rr,
+                                             const float4& bias4, const float4& cs4) {
+    v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w;
+    v[0] *= cs4.x; v[1] *= cs4.y; v[2] *= cs4.z; v[3] *= cs4.w;
+    if (e.rowmul) {
+        const float4 b = *reinterpret_cast<const float4*>(e.rowmul + (long long)row * e.rowmul_ld + col);
+        v[0] *= b.x; v[1] *= b.y; v[2] *= b.z; v[3] *= b.w;
+    }
     if (e.resid) {
-        float4 rs[8];
-        const float4* g = reinterpret_cast<const float4*>(e.resid + rr + col0);
-#pragma unroll
-        for (int j = 0; j < 8; j++) rs[j] = g[j];
-        if (e.bias) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j); v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w; }
-        }
-        if (e.colscale) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.colscale + col0) + j); v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w; }
-        }
-        if (e.rowmul) {
-            const float4* gm = reinterpret_cast<const float4*>(e.rowmul + (long long)row * e.rowmul_ld + col0);
-#pragma unroll
-            for (int j = 0; j < 8; j++) { const float4 b = gm[j]; v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w; }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j++) { v[4 * j] += rs[j].x; v[4 * j + 1] += rs[j].y; v[4 * j + 2] += rs[j].z; v[4 * j + 3] += rs[j].w; }
-    } else {
-        if (e.bias) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j); v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w; }
-        }
-        if (e.colscale) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.colscale + col0) + j); v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w; }
-        }
-        if (e.rowmul) {
-            const float4* gm = reinterpret_cast<const float4*>(e.rowmul + (long long)row * e.rowmul_ld + col0);
-#pragma unroll
-            for (int j = 0; j < 8; j++) { const float4 b = gm[j]; v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w; }
-        }
+        const float4 b = *reinterpret_cast<const float4*>(e.resid + rr + col);
+        v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
     }
-    if (e.out) {
-        float4* g = reinterpret_cast<float4*>(e.out + ro + col0);
-#pragma unroll
-        for (int j = 0; j < 8; j++) g[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
+    if (e.out) *reinterpret_cast<float4*>(e.out + ro + col) = make_float4(v[0], v[1], v[2], v[3]);
     if (e.out2_type != OUT2_NONE) {
         if (e.act != ACT_NONE) {
 #pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = apply_act(v[i], e.act);
+            for (int i = 0; i < 4; i++) v[i] = apply_act(v[i], e.act);
         }
         if (e.out2_type == OUT2_BF16) {
-            uint4* g = reinterpret_cast<uint4*>((__nv_bfloat16*)e.out2 + r2 + col0);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                __nv_bfloat162 p[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) p[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
-                g[j] = *reinterpret_cast<uint4*>(p);
-            }
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>((__nv_bfloat16*)e.out2 + r2 + col) = pk;
         } else {
-            uint4* g = reinterpret_cast<uint4*>((__half*)e.out2 + r2 + col0);
-            uint4* gl = reinterpret_cast<uint4*>((__half*)e.out2 + r2 + col0 + e.split_off);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                __half2 hi[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) hi[i] = __floats2half2_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
-                g[j] = *reinterpret_cast<uint4*>(hi);
-                if (e.out2_type == OUT2_F16_SPLIT) {
-                    __half2 lo[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) { const float2 h = __half22float2(hi[i]); lo[i] = __floats2half2_rn(v[8 * j + 2 * i] - h.x, v[8 * j + 2 * i + 1] - h.y); }
-                    gl[j] = *reinterpret_cast<uint4*>(lo);
-                }
+            const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+            uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>((__half*)e.out2 + r2 + col) = pk;
+            if (e.out2_type == OUT2_F16_SPLIT) {
+                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                const __half2 l0 = __floats2half2_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2half2_rn(v[2] - f1.x, v[3] - f1.y);
+                uint2 pl; pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+                *reinterpret_cast<uint2*>((__half*)e.out2 + r2 + col + e.split_off) = pl;
             }
         }
     }
@@ -223,15 +186,20 @@ __device__ __forceinline__ void epi_qkv32(const Epi& e, int row, int col0, float
     }
 }
 
+// Epilogue staging per epilogue warp: a 32 x 32 f32 accumulator chunk transposed through shared memory (rows padded to 36 floats:
+// 16-byte aligned and conflict-free for 128-bit stores by row and 128-bit loads by quarter-row) + (slot, row-in-slot) of its 32 rows.
+constexpr int EPI_WARPS = 8, EPI_STG_LD = 36, EPI_STG_BYTES = 32 * EPI_STG_LD * 4, EPI_ROW_BYTES = 32 * 8;
+constexpr int EPI_SMEM = EPI_WARPS * (EPI_STG_BYTES + EPI_ROW_BYTES);   // 38,912 B
+
 template <int BN>
 struct TcCfg {
-    static constexpr int STAGES_2CTA = (BN >= 128) ? 3 : 4;     // two CTAs per SM (default)
+    static constexpr int STAGES_2CTA = (BN >= 128) ? 2 : 3;     // two CTAs per SM (default): 2 x (ring + staging) must fit 228 KB
     static constexpr int MAX_STAGES = 8;
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int W_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-    static constexpr int STAGES_1CTA = (200 * 1024 / STAGE_BYTES) < MAX_STAGES ? (200 * 1024 / STAGE_BYTES) : MAX_STAGES;
-    static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
+    static constexpr int STAGES_1CTA = ((224 * 1024 - EPI_SMEM - 1280) / STAGE_BYTES) < MAX_STAGES ? ((224 * 1024 - EPI_SMEM - 1280) / STAGE_BYTES) : MAX_STAGES;
+    static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + EPI_SMEM + 1024 /*align*/ + 256 /*barriers*/; }
     static constexpr int TMEM_COLS = 2 * BN;                   // double-buffered accumulator
 };
 
@@ -246,7 +214,8 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = base, sW = base + STAGES * Cfg::A_BYTES;
-    const uint32_t bars = sW + STAGES * Cfg::W_BYTES;          // full[S] | empty[S] | tfull[2] | tempty[2] | tmem_ptr
+    const uint32_t stg0 = sW + STAGES * Cfg::W_BYTES;         // epilogue staging (EPI_SMEM bytes)
+    const uint32_t bars = stg0 + EPI_SMEM;                     // full[S] | empty[S] | tfull[2] | tempty[2] | tmem_ptr
     const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16, tptr = tempty0 + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.K / 64;
@@ -321,6 +290,10 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
     } else {
         // ===== epilogue warps: lane group (warp & 3), 32-column chunks alternate between the two warps of a lane group =====
         const int ew = warp & 3, half = (warp - 2) >> 2;
+        uint8_t* const smem_gen = smem_raw + (stg0 - smem_u32(smem_raw));
+        float* const stg = reinterpret_cast<float*>(smem_gen + (warp - 2) * EPI_STG_BYTES);
+        int2* const rowinfo = reinterpret_cast<int2*>(smem_gen + EPI_WARPS * EPI_STG_BYTES + (warp - 2) * EPI_ROW_BYTES);
+        const int sub = lane >> 3, cq = (lane & 7) * 4;          // coalesced phase: row 4i + sub of the chunk, columns cq..cq+3
         int it = 0;
         for (int work = blockIdx.x; work < total_tiles; work += gridDim.x, it++) {
             const int split = work % p.splits, tile = work / p.splits;
@@ -331,23 +304,42 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
             else { row_base = tile_m * p.SB * p.T; nvalid = min(p.SB * p.T, p.R - row_base); }
             const int ri = ew * 32 + lane;
             const int row = row_base + ri;
+            const bool live = ri < nvalid;
+            if (epi.mode == EPI_GENERIC) {
+                rowinfo[lane] = make_int2(row / epi.rps, row % epi.rps);
+                __syncwarp();
+            }
             mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
             tc_fence_after();
-            const bool live = ri < nvalid;
-            long long ro = 0, r2 = 0, rr = 0;
-            if (live && epi.mode == EPI_GENERIC) {
-                ro = (epi.out ? epi.out_map.off(row, epi.rps) : 0) + (long long)split * p.ws_split_stride;
-                r2 = epi.out2 ? epi.out2_map.off(row, epi.rps) : 0;
-                rr = epi.resid ? epi.resid_map.off(row, epi.rps) : 0;
-            }
+            const long long ws_off = (long long)split * p.ws_split_stride;
 #pragma unroll 1
             for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 float v[32];
                 tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * BN + c0), v);
-                if (live) {
-                    const int col0 = tile_n * BN + c0;
-                    if (epi.mode == EPI_GENERIC) epi_generic32(epi, row, col0, v, ro, r2, rr);
-                    else epi_qkv32(epi, row, col0, v);
+                if (epi.mode == EPI_GENERIC) {
+                    float4* sp = reinterpret_cast<float4*>(stg + lane * EPI_STG_LD);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) sp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
+                    const int col = tile_n * BN + c0 + cq;
+                    const float4 bias4 = epi.bias ? __ldg(reinterpret_cast<const float4*>(epi.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 cs4 = epi.colscale ? __ldg(reinterpret_cast<const float4*>(epi.colscale + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int r = 4 * i + sub;
+                        if (ew * 32 + r < nvalid) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(stg + r * EPI_STG_LD + cq);
+                            const int2 rinfo = rowinfo[r];
+                            float w[4] = {w4.x, w4.y, w4.z, w4.w};
+                            const long long ro = (long long)rinfo.x * epi.out_map.slot_stride + (long long)rinfo.y * epi.out_map.row_stride + epi.out_map.base + ws_off;
+                            const long long r2 = (long long)rinfo.x * epi.out2_map.slot_stride + (long long)rinfo.y * epi.out2_map.row_stride + epi.out2_map.base;
+                            const long long rr = (long long)rinfo.x * epi.resid_map.slot_stride + (long long)rinfo.y * epi.resid_map.row_stride + epi.resid_map.base;
+                            epi_generic4(epi, row_base + ew * 32 + r, col, w, ro, r2, rr, bias4, cs4);
+                        }
+                    }
+                    __syncwarp();                                  // the staging tile is overwritten by the next chunk
+                } else if (live) {
+                    epi_qkv32(epi, row, tile_n * BN + c0, v);
                 }
             }
             tc_fence_before();
@@ -380,47 +372,53 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 struct LnFuse { const float* w = nullptr; const float* b = nullptr; float eps = 0.f; __nv_bfloat16* out = nullptr; };
 
 template <int C>
-__global__ void __launch_bounds__(256) splitk_reduce_ln_kernel(const float* __restrict__ ws, int splits, long long plane, int R, const Epi epi, const LnFuse ln) {
+__global__ void __launch_bounds__(C / 4) splitk_reduce_ln_kernel(const float* __restrict__ ws, int splits, long long plane, int R, const Epi epi, const LnFuse ln) {
+    // One CTA per row, one float4 (4 columns) per thread: R CTAs keep enough loads in flight to stream the partial planes at HBM/L2
+    // speed (one warp per row left 32 CTAs on 148 SMs and took 34 us for linear2's 16 planes).
     pdl_prologue();
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (row >= R) return;
-    constexpr int Q = C / 128;                                  // float4 groups per lane
-    float v[Q][4];
-    const long long rr = epi.resid ? epi.resid_map.off(row, epi.rps) : 0, ro = epi.out ? epi.out_map.off(row, epi.rps) : 0;
-#pragma unroll
-    for (int qd = 0; qd < Q; qd++) {
-        const int col = (qd * 32 + lane) * 4;
-        float4 a = *reinterpret_cast<const float4*>(ws + (long long)row * C + col);
-        for (int s = 1; s < splits; s++) {
-            const float4 b = *reinterpret_cast<const float4*>(ws + (long long)s * plane + (long long)row * C + col);
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-        }
-        v[qd][0] = a.x; v[qd][1] = a.y; v[qd][2] = a.z; v[qd][3] = a.w;
-        if (epi.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col)); v[qd][0] += b.x; v[qd][1] += b.y; v[qd][2] += b.z; v[qd][3] += b.w; }
-        if (epi.colscale) { const float4 b = __ldg(reinterpret_cast<const float4*>(epi.colscale + col)); v[qd][0] *= b.x; v[qd][1] *= b.y; v[qd][2] *= b.z; v[qd][3] *= b.w; }
-        if (epi.resid) { const float4 b = *reinterpret_cast<const float4*>(epi.resid + rr + col); v[qd][0] += b.x; v[qd][1] += b.y; v[qd][2] += b.z; v[qd][3] += b.w; }
-        if (epi.out) *reinterpret_cast<float4*>(epi.out + ro + col) = make_float4(v[qd][0], v[qd][1], v[qd][2], v[qd][3]);
+    constexpr int NW = C / 128;                                 // warps per CTA
+    __shared__ float red[2][NW];
+    const int row = blockIdx.x, col = threadIdx.x * 4, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* p = ws + (long long)row * C + col;
+    float4 a = *reinterpret_cast<const float4*>(p);
+    int s = 1;
+    for (; s + 3 < splits; s += 4) {                            // four independent loads in flight per thread
+        const float4 b0 = *reinterpret_cast<const float4*>(p + (long long)s * plane), b1 = *reinterpret_cast<const float4*>(p + (long long)(s + 1) * plane);
+        const float4 b2 = *reinterpret_cast<const float4*>(p + (long long)(s + 2) * plane), b3 = *reinterpret_cast<const float4*>(p + (long long)(s + 3) * plane);
+        a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w;    // fixed order s, s+1, ...: deterministic
+        a.x += b1.x; a.y += b1.y; a.z += b1.z; a.w += b1.w;
+        a.x += b2.x; a.y += b2.y; a.z += b2.z; a.w += b2.w;
+        a.x += b3.x; a.y += b3.y; a.z += b3.z; a.w += b3.w;
     }
-    float s1 = 0.f;
+    for (; s < splits; s++) { const float4 b = *reinterpret_cast<const float4*>(p + (long long)s * plane); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+    float v[4] = {a.x, a.y, a.z, a.w};
+    if (epi.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col)); v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w; }
+    if (epi.colscale) { const float4 b = __ldg(reinterpret_cast<const float4*>(epi.colscale + col)); v[0] *= b.x; v[1] *= b.y; v[2] *= b.z; v[3] *= b.w; }
+    if (epi.resid) { const float4 b = *reinterpret_cast<const float4*>(epi.resid + epi.resid_map.off(row, epi.rps) + col); v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w; }
+    if (epi.out) *reinterpret_cast<float4*>(epi.out + epi.out_map.off(row, epi.rps) + col) = make_float4(v[0], v[1], v[2], v[3]);
+    float s1 = warp_sum(v[0] + v[1] + v[2] + v[3]);
+    if (lane == 0) red[0][warp] = s1;
+    __syncthreads();
+    float tot = 0.f;
 #pragma unroll
-    for (int qd = 0; qd < Q; qd++) s1 += v[qd][0] + v[qd][1] + v[qd][2] + v[qd][3];
-    const float mean = warp_sum(s1) / C;
+    for (int w = 0; w < NW; w++) tot += red[0][w];
+    const float mean = tot / C;
     float s2 = 0.f;
 #pragma unroll
-    for (int qd = 0; qd < Q; qd++)
+    for (int i = 0; i < 4; i++) { v[i] -= mean; s2 += v[i] * v[i]; }
+    s2 = warp_sum(s2);
+    if (lane == 0) red[1][warp] = s2;
+    __syncthreads();
+    tot = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; i++) { v[qd][i] -= mean; s2 += v[qd][i] * v[qd][i]; }
-    const float rs = 1.0f / sqrtf(warp_sum(s2) / C + ln.eps);
+    for (int w = 0; w < NW; w++) tot += red[1][w];
+    const float rs = 1.0f / sqrtf(tot / C + ln.eps);
+    float y[4];
 #pragma unroll
-    for (int qd = 0; qd < Q; qd++) {
-        const int col = (qd * 32 + lane) * 4;
-        float y[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { y[i] = v[qd][i] * rs; if (ln.w) y[i] *= ln.w[col + i]; if (ln.b) y[i] += ln.b[col + i]; }
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
-        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-        *reinterpret_cast<uint2*>(ln.out + (long long)row * C + col) = pk;
-    }
+    for (int i = 0; i < 4; i++) { y[i] = v[i] * rs; if (ln.w) y[i] *= ln.w[col + i]; if (ln.b) y[i] += ln.b[col + i]; }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
+    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(ln.out + (long long)row * C + col) = pk;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -560,8 +558,8 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     if (splits > 1) {
         const bool fuse = ln && ln->out && epi.mode == EPI_GENERIC && !epi.rowmul && epi.out2_type == OUT2_NONE && (N == 1024 || N == 512);
         if (fuse) {
-            if (N == 1024) launch_k(c->pdl, splitk_reduce_ln_kernel<1024>, dim3((R + 7) / 8), dim3(256), 0, stream, (const float*)c->ws, splits, (long long)R * N, R, epi, *ln);
-            else launch_k(c->pdl, splitk_reduce_ln_kernel<512>, dim3((R + 7) / 8), dim3(256), 0, stream, (const float*)c->ws, splits, (long long)R * N, R, epi, *ln);
+            if (N == 1024) launch_k(c->pdl, splitk_reduce_ln_kernel<1024>, dim3(R), dim3(256), 0, stream, (const float*)c->ws, splits, (long long)R * N, R, epi, *ln);
+            else launch_k(c->pdl, splitk_reduce_ln_kernel<512>, dim3(R), dim3(128), 0, stream, (const float*)c->ws, splits, (long long)R * N, R, epi, *ln);
             if (ln_done) *ln_done = true;
         } else {
             const long long quads = (long long)R * N / 4;

@@ -40,38 +40,51 @@ __global__ void embed_gather_kernel(const __nv_bfloat16* __restrict__ table, con
 // ------------------------------------------------------------------------------------------------
 // LayerNorm (ggml_norm: mean, biased variance of deviations, 1/sqrtf(var+eps); reference src/torch.h:49-60,
 // modules/mlp.h:52-64) with optional affine and optional AdaLN modulate y*(1+scale)+shift (mlp.h:3-9).
-// One warp per row; writes a low-precision copy (the A operand of the following GEMM) and/or f32.
+// Writes a low-precision copy (the A operand of the following GEMM) and/or f32.
 // ------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, RowMap xmap, int rps, int R, float eps,
-                                                        const float* __restrict__ w, const float* __restrict__ b,
-                                                        const float* __restrict__ shift, const float* __restrict__ scale, int mod_ld,
-                                                        __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+__global__ void __launch_bounds__(C / 4) layernorm_kernel(const float* __restrict__ x, RowMap xmap, int rps, int R, float eps,
+                                                          const float* __restrict__ w, const float* __restrict__ b,
+                                                          const float* __restrict__ shift, const float* __restrict__ scale, int mod_ld,
+                                                          __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+    // One CTA (C/4 threads) per row, one float4 per thread: at decode batch sizes (R = 256) a warp-per-row layout leaves most SMs idle.
     pdl_prologue();
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = C / 128;
+    __shared__ float red[2][NW];
+    const int row = blockIdx.x, col = threadIdx.x * 4, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (row >= R) return;
-    constexpr int PER = C / 32;
-    const float* xr = x + xmap.off(row, rps);
-    float v[PER];
-    float s = 0.f;
+    const float4 a = *reinterpret_cast<const float4*>(x + xmap.off(row, rps) + col);
+    float v[4] = {a.x, a.y, a.z, a.w};
+    const float s1 = warp_sum(v[0] + v[1] + v[2] + v[3]);
+    if (lane == 0) red[0][warp] = s1;
+    __syncthreads();
+    float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; i++) { v[i] = xr[lane + 32 * i]; s += v[i]; }
-    const float mean = warp_sum(s) / C;
+    for (int i = 0; i < NW; i++) tot += red[0][i];
+    const float mean = tot / C;
     float s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; i++) { v[i] -= mean; s2 += v[i] * v[i]; }
-    const float var = warp_sum(s2) / C;
-    const float rs = 1.0f / sqrtf(var + eps);
+    for (int i = 0; i < 4; i++) { v[i] -= mean; s2 += v[i] * v[i]; }
+    s2 = warp_sum(s2);
+    if (lane == 0) red[1][warp] = s2;
+    __syncthreads();
+    tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; i++) {
-        const int c = lane + 32 * i;
-        float y = v[i] * rs;
-        if (w) y = y * w[c];
-        if (b) y = y + b[c];
-        if (scale) y = y * (scale[(long long)row * mod_ld + c] + 1.f) + shift[(long long)row * mod_ld + c];
-        if (out_bf16) out_bf16[(long long)row * C + c] = __float2bfloat16_rn(y);
-        if (out_f32) out_f32[(long long)row * C + c] = y;
+    for (int i = 0; i < NW; i++) tot += red[1][i];
+    const float rs = 1.0f / sqrtf(tot / C + eps);
+    float y[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { y[i] = v[i] * rs; if (w) y[i] *= w[col + i]; if (b) y[i] += b[col + i]; }
+    if (scale) {
+        const float4 sc = *reinterpret_cast<const float4*>(scale + (long long)row * mod_ld + col), sh = *reinterpret_cast<const float4*>(shift + (long long)row * mod_ld + col);
+        y[0] = y[0] * (sc.x + 1.f) + sh.x; y[1] = y[1] * (sc.y + 1.f) + sh.y; y[2] = y[2] * (sc.z + 1.f) + sh.z; y[3] = y[3] * (sc.w + 1.f) + sh.w;
     }
+    if (out_bf16) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(out_bf16 + (long long)row * C + col) = pk;
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)row * C + col) = make_float4(y[0], y[1], y[2], y[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -574,35 +587,52 @@ __global__ void __launch_bounds__(128) attn_mimi_mma_kernel(const __nv_bfloat16*
 // Flow head glue
 // ------------------------------------------------------------------------------------------------
 // c = LN(h; out_norm) (bf16 copy for cond_embed) and EOS logit = out_eos(bf16(c)) + bias + 4
-// (reference models/flow_lm.h:114-129). One warp per row.
+// (reference models/flow_lm.h:114-129). One CTA per row.
 __global__ void __launch_bounds__(256) head_pre_kernel(const float* __restrict__ h, int R, const float* __restrict__ w, const float* __restrict__ b,
                                                        const __nv_bfloat16* __restrict__ w_eos, const float* __restrict__ b_eos,
                                                        __nv_bfloat16* __restrict__ c_bf16, float* __restrict__ eos) {
     pdl_prologue();
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    __shared__ float red[3][8];
+    const int row = blockIdx.x, col = threadIdx.x * 4, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (row >= R) return;
-    constexpr int PER = D_MODEL / 32;
-    const float* xr = h + (long long)row * D_MODEL;
-    float v[PER]; float s = 0.f;
+    const float4 a = *reinterpret_cast<const float4*>(h + (long long)row * D_MODEL + col);
+    float v[4] = {a.x, a.y, a.z, a.w};
+    const float s1 = warp_sum(v[0] + v[1] + v[2] + v[3]);
+    if (lane == 0) red[0][warp] = s1;
+    __syncthreads();
+    float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; i++) { v[i] = xr[lane + 32 * i]; s += v[i]; }
-    const float mean = warp_sum(s) / D_MODEL;
+    for (int i = 0; i < 8; i++) tot += red[0][i];
+    const float mean = tot / D_MODEL;
     float s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; i++) { v[i] -= mean; s2 += v[i] * v[i]; }
-    const float rs = 1.0f / sqrtf(warp_sum(s2) / D_MODEL + 1e-5f);
-    float dot = 0.f;
+    for (int i = 0; i < 4; i++) { v[i] -= mean; s2 += v[i] * v[i]; }
+    s2 = warp_sum(s2);
+    if (lane == 0) red[1][warp] = s2;
+    __syncthreads();
+    tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; i++) {
-        const int c = lane + 32 * i;
-        float y = v[i] * rs * w[c];
-        if (b) y += b[c];
-        const __nv_bfloat16 yb = __float2bfloat16_rn(y);
-        c_bf16[(long long)row * D_MODEL + c] = yb;
-        dot = fmaf(__bfloat162float(yb), __bfloat162float(w_eos[c]), dot);
+    for (int i = 0; i < 8; i++) tot += red[1][i];
+    const float rs = 1.0f / sqrtf(tot / D_MODEL + 1e-5f);
+    float dot = 0.f;
+    __nv_bfloat16 yb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float y = v[i] * rs * w[col + i];
+        if (b) y += b[col + i];
+        yb[i] = __float2bfloat16_rn(y);
+        dot = fmaf(__bfloat162float(yb[i]), __bfloat162float(w_eos[col + i]), dot);
     }
+    *reinterpret_cast<uint2*>(c_bf16 + (long long)row * D_MODEL + col) = *reinterpret_cast<uint2*>(yb);
     dot = warp_sum(dot);
-    if (lane == 0) eos[row] = dot + (b_eos ? b_eos[0] : 0.f) + 4.0f;
+    if (lane == 0) red[2][warp] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) d += red[2][i];
+        eos[row] = d + (b_eos ? b_eos[0] : 0.f) + 4.0f;
+    }
 }
 
 // noise -> (f32, bf16) per row. Noise is either injected by the caller (identical-noise parity runs, the
@@ -689,9 +719,11 @@ __global__ void step_logic_kernel(int slot0, int n, const float* __restrict__ eo
 // src/pocket_tts.cpp:472-478, models/mimi.h:77-83); depthwise x16 upsampler on one step with carried state
 // (modules/conv.h:283-331): x[k][c] = e[c]*w[c][k] + e_prev[c]*w[c][16+k] (+bias). State kept = e_prev.
 // ------------------------------------------------------------------------------------------------
+// wq_t is the quantizer projection transposed to [32][512], wup_t the upsampler taps transposed to [32][512]: lane = channel, so
+// every weight load and every store is a coalesced line.
 __global__ void __launch_bounds__(512) mimi_front_kernel(int slot0, const float* __restrict__ lat_f32, const float* __restrict__ emb_std,
-                                                         const float* __restrict__ emb_mean, const __half* __restrict__ wq,
-                                                         const float* __restrict__ wup, const float* __restrict__ bup,
+                                                         const float* __restrict__ emb_mean, const __half* __restrict__ wq_t,
+                                                         const float* __restrict__ wup_t, const float* __restrict__ bup,
                                                          float* __restrict__ e_prev, float* __restrict__ x) {
     pdl_prologue();
     __shared__ float z[LDIM];
@@ -700,14 +732,14 @@ __global__ void __launch_bounds__(512) mimi_front_kernel(int slot0, const float*
     __syncthreads();
     float e = 0.f;
 #pragma unroll
-    for (int i = 0; i < LDIM; i++) e = fmaf(__half2float(wq[c * LDIM + i]), z[i], e);
+    for (int i = 0; i < LDIM; i++) e = fmaf(__half2float(wq_t[i * M_DIM + c]), z[i], e);
     const float ep = e_prev[(long long)slot * M_DIM + c];
     e_prev[(long long)slot * M_DIM + c] = e;
     const float bias = bup ? bup[c] : 0.f;
     float* xo = x + (long long)slot * M_T * M_DIM + c;
 #pragma unroll
     for (int k = 0; k < M_T; k++) {
-        const float y = __fadd_rn(__fmul_rn(e, wup[c * 32 + k]), __fmul_rn(ep, wup[c * 32 + 16 + k]));
+        const float y = __fadd_rn(__fmul_rn(e, wup_t[k * M_DIM + c]), __fmul_rn(ep, wup_t[(16 + k) * M_DIM + c]));
         xo[(long long)k * M_DIM] = y + bias;
     }
 }
