@@ -201,9 +201,8 @@ struct b200_engine {
     }
 
     // FlowLM transformer over R rows held in `h` (reference modules/transformer.h:253-278,363-374).
-    void flow_forward(int R) {
+    void flow_forward(int R, bool ln1_done = false) {              // ln1_done: layer 0's norm1 already in n_bf (decode: flow_in_kernel)
         const int BIG = 1 << 30;
-        bool ln1_done = false;                                   // norm1 of layer l already produced by layer l-1's linear2 reduction
         for (int l = 0; l < N_LAYERS; l++) {
             auto& L = fl[l];
             if (!ln1_done) { launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n1w, L.n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++; }
@@ -255,8 +254,6 @@ struct b200_engine {
         // all seven adaLN projections of silu(y) in one GEMM: [6 x (shift|scale|gate)] + [shift|scale]
         Epi em; em.out = mod; em.out_map = rows(ada_all.out);
         lin(sy_bf, ada_all, R, em);
-        Epi ei; ei.out = xh; ei.out_map = rows(D_FLOW);
-        lin(noise_bf, input_proj, R, ei);
         for (int r = 0; r < N_RES; r++) {
             const float* m = mod + r * 3 * D_FLOW;
             launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3(R), dim3(D_FLOW / 4), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, rb[r].lnw, rb[r].lnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
@@ -357,12 +354,14 @@ struct b200_engine {
         set_pdl(pdl_small || pdl_chain);
         prepare_step(slot0, n);
         const int s_flow = seg_begin(1);
-        Epi e; e.out = h; e.out_map = rows(D_MODEL);
-        lin(lat_in_bf16 + (long long)slot0 * LDIM, input_linear, n, e);
-        flow_forward(n);
+        launch_k(pdl_active, flow_in_kernel, dim3(n), dim3(256), (size_t)0, stream, slot0, n, (const __nv_bfloat16*)lat_in_bf16, (const __nv_bfloat16*)input_linear.w,
+                 (const float*)input_linear.b, (const float*)fl[0].n1w, (const float*)fl[0].n1b, h, n_bf);
+        launches++;
+        flow_forward(n, true);
         seg_end(s_flow);
         const int s_head = seg_begin(2);
-        launch_k(pdl_active, noise_kernel, dim3((n * LDIM + 127) / 128), dim3(128), (size_t)(0), stream, slot0, n, injected ? noise_inj : nullptr, d_seed, temp, gen_step, noise_f32, noise_bf);
+        launch_k(pdl_active, noise_inproj_kernel, dim3(n), dim3(128), (size_t)(0), stream, slot0, n, (const float*)(injected ? noise_inj : nullptr), (const unsigned long long*)d_seed,
+                 (const float*)temp, (const int*)gen_step, noise_f32, (const __nv_bfloat16*)input_proj.w, (const float*)input_proj.b, xh);
         flow_head(n);
         launch_k(pdl_active, step_logic_kernel, dim3(n), dim3(32), (size_t)(0), stream, slot0, n, eos, latent, cur_len, gen_step, eos_step, max_gen, fae, active, lat_in_bf16, lat_f32, produced, eos_out);
         launches += 2;
@@ -439,7 +438,7 @@ extern "C" {
 void b200_default_config(b200_config* c) {
     memset(c, 0, sizeof(*c));
     c->device = 0; c->max_slots = 1; c->max_voices = 8; c->kv_capacity = 2048; c->kv_f32 = 0; c->mimi_mask_mode = 0;
-    c->convt_split = 1; c->gemm_path = 0; c->max_prefill_rows = 512; c->cuda_graphs = 1; c->pdl = 1;
+    c->convt_split = 0; c->gemm_path = 0; c->max_prefill_rows = 512; c->cuda_graphs = 1; c->pdl = 1;
 }
 
 int b200_engine_create(const b200_config* cfg, b200_engine** out) {
@@ -647,7 +646,7 @@ int b200_finalize_weights(b200_engine* e) {
                             (const void*)gemv_small_kernel<__nv_bfloat16, 8>, (const void*)gemv_small_kernel<__half, 8>, (const void*)layernorm_kernel<D_MODEL>,
                             (const void*)layernorm_kernel<D_FLOW>, (const void*)gemm_tc_kernel<32>, (const void*)gemm_tc_kernel<64>, (const void*)gemm_tc_kernel<128>,
                             (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
-                            (const void*)attn_flow_split_kernel, (const void*)attn_flow_merge_kernel, (const void*)noise_kernel, (const void*)head_pre_kernel,
+                            (const void*)attn_flow_split_kernel, (const void*)attn_flow_merge_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
                             (const void*)step_logic_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma_kernel, (const void*)cast_f16_kernel,
                             (const void*)conv_n1_kernel, (const void*)shift_states_kernel};
         for (const void* k : ks) PTTS_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -93,18 +93,10 @@ struct TcParams {
 // ---- GENERIC epilogue for 4 consecutive columns of one row (bias / colscale already loaded for these columns) ----
 // Called after the accumulator chunk was transposed through shared memory, so that the 8 lanes sharing a row cover 128 contiguous
 // bytes (f32) and every warp-level load/store touches 4 full lines instead of 32 partial ones.
-__device__ __forceinline__ void epi_generic4(const Epi& e, int row, int col, float (&v)[4], long long ro, long long r2, long long rr,
-                                             const float4& bias4, const float4& cs4) {
-    v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w;
-    v[0] *= cs4.x; v[1] *= cs4.y; v[2] *= cs4.z; v[3] *= cs4.w;
-    if (e.rowmul) {
-        const float4 b = *reinterpret_cast<const float4*>(e.rowmul + (long long)row * e.rowmul_ld + col);
-        v[0] *= b.x; v[1] *= b.y; v[2] *= b.z; v[3] *= b.w;
-    }
-    if (e.resid) {
-        const float4 b = *reinterpret_cast<const float4*>(e.resid + rr + col);
-        v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-    }
+__device__ __forceinline__ void epi_generic4(const Epi& e, int col, float (&v)[4], long long ro, long long r2,
+                                             const float4& bias4, const float4& cs4, const float4& rm4, const float4& rs4) {
+    v[0] = (v[0] + bias4.x) * cs4.x * rm4.x + rs4.x; v[1] = (v[1] + bias4.y) * cs4.y * rm4.y + rs4.y;
+    v[2] = (v[2] + bias4.z) * cs4.z * rm4.z + rs4.z; v[3] = (v[3] + bias4.w) * cs4.w * rm4.w + rs4.w;
     if (e.out) *reinterpret_cast<float4*>(e.out + ro + col) = make_float4(v[0], v[1], v[2], v[3]);
     if (e.out2_type != OUT2_NONE) {
         if (e.act != ACT_NONE) {
@@ -324,6 +316,18 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
                     const int col = tile_n * BN + c0 + cq;
                     const float4 bias4 = epi.bias ? __ldg(reinterpret_cast<const float4*>(epi.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     const float4 cs4 = epi.colscale ? __ldg(reinterpret_cast<const float4*>(epi.colscale + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    // the residual loads of the 8 rows are issued before any store: the compiler cannot hoist them itself
+                    // (stores through out/out2 may alias), and serialised load->store pairs cost ~1 us each
+                    float4 rs4[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int r = 4 * i + sub;
+                        rs4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ew * 32 + r < nvalid) {
+                            const int2 rinfo = rowinfo[r];
+                            if (epi.resid) rs4[i] = *reinterpret_cast<const float4*>(epi.resid + ((long long)rinfo.x * epi.resid_map.slot_stride + (long long)rinfo.y * epi.resid_map.row_stride + epi.resid_map.base) + col);
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int r = 4 * i + sub;
@@ -333,8 +337,9 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
                             float w[4] = {w4.x, w4.y, w4.z, w4.w};
                             const long long ro = (long long)rinfo.x * epi.out_map.slot_stride + (long long)rinfo.y * epi.out_map.row_stride + epi.out_map.base + ws_off;
                             const long long r2 = (long long)rinfo.x * epi.out2_map.slot_stride + (long long)rinfo.y * epi.out2_map.row_stride + epi.out2_map.base;
-                            const long long rr = (long long)rinfo.x * epi.resid_map.slot_stride + (long long)rinfo.y * epi.resid_map.row_stride + epi.resid_map.base;
-                            epi_generic4(epi, row_base + ew * 32 + r, col, w, ro, r2, rr, bias4, cs4);
+                            float4 rm4 = make_float4(1.f, 1.f, 1.f, 1.f);      // gate (flow head only: tiny GEMMs, not worth 32 registers of prefetch)
+                            if (epi.rowmul) rm4 = *reinterpret_cast<const float4*>(epi.rowmul + (long long)(row_base + ew * 32 + r) * epi.rowmul_ld + col);
+                            epi_generic4(epi, col, w, ro, r2, bias4, cs4, rm4, rs4[i]);
                         }
                     }
                     __syncwarp();                                  // the staging tile is overwritten by the next chunk
@@ -466,24 +471,47 @@ inline TcGeom tc_geometry(int R, int K, const RowMap& amap, int a_rps) {
     g.ok = true; return g;
 }
 
-inline int tc_pick_bn(int tiles_m, int N, int K = 0) {
-    if (tiles_m <= 2 && K >= 512) {            // small-M, long-K: wide tiles + split-K (see tc_gemm_launch)
-        for (int bn : {128, 64, 32}) if (N % bn == 0) return bn;
-        return 0;
+// Tile width and split-K factor.
+// Small-M GEMMs (decode: R = utterances in flight, at most a few M tiles) cannot fill 148 SMs with output tiles alone and are
+// bounded by fixed latencies, so the choice is made with a small cost model (microseconds):
+//   GEMM    ~ 3 + CTAs-per-SM x bytes one CTA streams / (100 KB/us per SM)       (TMA ingest per SM, launch + pipeline fill)
+//   reduce  ~ 4 + splits x R x N x 4 B / (3 MB/us)   when split (a second kernel; it also does a fused LayerNorm for free)
+//   + 4.5 when a LayerNorm was requested but cannot be fused (no split)
+// Calibrated on the ncu launch lists in profiles/ (r1_v7): e.g. FlowLM in_proj 128x4 splits = 11.6 + 8.3 us vs model 13.6.
+struct TcPlan { int bn; int splits; };
+inline TcPlan tc_plan(int tiles_m, int R, int N, int K, int num_sms, bool want_ln) {
+    TcPlan best{0, 1};
+    const int num_kb = K / 64;
+    if (tiles_m <= 4) {
+        double best_cost = 1e30;
+        for (int bn : {128, 64, 32}) {
+            if (N % bn != 0) continue;
+            const int tiles = tiles_m * (N / bn);
+            for (int sp : {1, 2, 4, 8, 16}) {
+                const int kbps = (num_kb + sp - 1) / sp;
+                if (sp > 1 && (kbps < 4 || (size_t)sp * R * N > ((size_t)32 << 20))) continue;
+                const int ctas = tiles * ((num_kb + kbps - 1) / kbps);
+                const double per_sm = (double)((ctas + num_sms - 1) / num_sms) * kbps * (16.0 + bn / 8.0);      // KB
+                double cost = 3.0 + per_sm / 100.0;
+                if (sp > 1) cost += 4.0 + (double)sp * R * N * 4.0 / 3.0e6;
+                else if (want_ln) cost += 4.5;
+                if (cost < best_cost) { best_cost = cost; best = TcPlan{bn, sp}; }
+            }
+        }
+        return best;
     }
     for (int bn : {128, 64, 32}) {
         if (N % bn != 0) continue;
-        if (tiles_m * (N / bn) >= 120 || bn == 32) return bn;
+        if (tiles_m * (N / bn) >= 120 || bn == 32) { best.bn = bn; break; }
     }
-    return 0;
+    return best;
 }
 
 template <typename T>
 inline bool tc_gemm_supported(int R, int N, int K, const RowMap& amap, int a_rps) {
     if (R < 16 || K % 64 != 0 || N % 32 != 0) return false;   // <16 rows: GEMV / CUDA-core kernels (weight-bandwidth bound anyway)
     const TcGeom g = tc_geometry(R, K, amap, a_rps);
-    if (!g.ok) return false;
-    return tc_pick_bn(g.tiles_m, N, K) != 0;
+    return g.ok;
 }
 
 inline const CUtensorMap* tc_get_map(TcPlanCache* c, const void* ptr, bool f16, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -507,7 +535,9 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     if (!c || !c->encode) { fprintf(stderr, "ptts_b200: tensor-map encoder unavailable\n"); abort(); }
     constexpr bool f16 = std::is_same<T, __half>::value;
     const TcGeom g = tc_geometry(R, K, amap, a_rps);
-    const int bn = tc_pick_bn(g.tiles_m, N, K);
+    const bool ln_ok = ln && ln->out && epi.mode == EPI_GENERIC && !epi.rowmul && epi.out2_type == OUT2_NONE && (N == 1024 || N == 512);
+    const TcPlan plan = tc_plan(g.tiles_m, R, N, K, c->num_sms, ln_ok);
+    const int bn = plan.bn;
     cuuint64_t adims[3] = {(cuuint64_t)g.C, (cuuint64_t)g.rows_per_slot_buf, (cuuint64_t)g.n_slots};
     cuuint64_t astr[2] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.slot_stride * 2};
     cuuint32_t abox[3] = {64, (cuuint32_t)g.box_rows, (cuuint32_t)g.SB};
@@ -520,23 +550,14 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     p.a_bytes = (uint32_t)(128 * g.box_rows * g.SB);
     // Small-M GEMMs (FlowLM decode: R = batch) cannot fill the SMs with output tiles alone: split K deterministically.
     const int num_kb = K / 64, tiles = (N / bn) * g.tiles_m;
-    int splits = 1;
-    if (tiles * 2 <= c->num_sms && num_kb >= 8) {
-        splits = std::min(std::min((2 * c->num_sms + tiles - 1) / tiles, num_kb / 4), 16);
-        if (splits < 2) splits = 1;
-    }
-    p.splits = splits; p.kb_per_split = (num_kb + splits - 1) / splits; p.ws_split_stride = 0;
+    int splits = plan.splits;
+    p.kb_per_split = (num_kb + splits - 1) / splits; p.ws_split_stride = 0;
+    p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
+    splits = p.splits;
     Epi kepi = epi;
     if (splits > 1) {
-        p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
-        splits = p.splits;
         // one fixed workspace for the engine's lifetime (its address is baked into captured CUDA graphs)
         if (!c->ws) { c->ws_elems = (size_t)32 << 20; PTTS_CUDA_CHECK(cudaMalloc(&c->ws, c->ws_elems * sizeof(float))); }
-        while (splits > 1 && (size_t)splits * R * N > c->ws_elems) {
-            p.kb_per_split *= 2; p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split; splits = p.splits;
-        }
-    }
-    if (splits > 1) {
         kepi = Epi{}; kepi.out = c->ws; kepi.out_map.row_stride = N; p.ws_split_stride = (long long)R * N;
     } else { p.splits = 1; p.kb_per_split = num_kb; }
     // instruction descriptor (kind::f16): D=f32, A/B = bf16|f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
@@ -556,8 +577,7 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     else launch(gemm_tc_kernel<32>, TcCfg<32>{});
     if (ln_done) *ln_done = false;
     if (splits > 1) {
-        const bool fuse = ln && ln->out && epi.mode == EPI_GENERIC && !epi.rowmul && epi.out2_type == OUT2_NONE && (N == 1024 || N == 512);
-        if (fuse) {
+        if (ln_ok) {
             if (N == 1024) launch_k(c->pdl, splitk_reduce_ln_kernel<1024>, dim3(R), dim3(256), 0, stream, (const float*)c->ws, splits, (long long)R * N, R, epi, *ln);
             else launch_k(c->pdl, splitk_reduce_ln_kernel<512>, dim3(R), dim3(128), 0, stream, (const float*)c->ws, splits, (long long)R * N, R, epi, *ln);
             if (ln_done) *ln_done = true;

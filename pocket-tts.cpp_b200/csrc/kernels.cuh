@@ -650,31 +650,108 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__global__ void noise_kernel(int slot0, int n, const float* __restrict__ injected, const unsigned long long* __restrict__ seed_ptr, const float* __restrict__ temp,
-                             const int* __restrict__ gen_step, float* __restrict__ noise_f32, __nv_bfloat16* __restrict__ noise_bf16) {
+// One CTA (128 threads) per row: the first 32 threads draw the row's noise, then every thread computes 4 of the 512 outputs of
+// input_proj(bf16(noise)) (32 -> 512, reference modules/mlp.h:236; bf16 operands, fp32 accumulation like every linear here).
+__global__ void __launch_bounds__(128) noise_inproj_kernel(int slot0, int n, const float* __restrict__ injected, const unsigned long long* __restrict__ seed_ptr,
+                                                           const float* __restrict__ temp, const int* __restrict__ gen_step, float* __restrict__ noise_f32,
+                                                           const __nv_bfloat16* __restrict__ w_in, const float* __restrict__ b_in, float* __restrict__ xh) {
     pdl_prologue();
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * LDIM) return;
-    const int r = idx / LDIM, i = idx % LDIM, slot = slot0 + r;
-    float z;
-    if (injected) {
-        z = injected[idx];
-    } else {
-        const float std = sqrtf(temp[slot]);
-        if (std == 0.f) z = 0.f;
-        else {
-            uint32_t o[4];
-            const unsigned long long seed = *seed_ptr;
-            philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)slot, (uint32_t)gen_step[slot], (uint32_t)(i >> 1), 0x5054545Au, o);
-            const float u1 = ((float)(o[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            const float u2 = ((float)(o[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            const float rad = sqrtf(-2.0f * logf(u1));
-            float sn, cn; sincosf(6.28318530717958647692f * u2, &sn, &cn);
-            z = ((i & 1) ? rad * sn : rad * cn) * std;
+    __shared__ float zs[LDIM];
+    const int r = blockIdx.x, slot = slot0 + r, i = threadIdx.x;
+    if (r >= n) return;
+    if (i < LDIM) {
+        float z;
+        if (injected) {
+            z = injected[r * LDIM + i];
+        } else {
+            const float std = sqrtf(temp[slot]);
+            if (std == 0.f) z = 0.f;
+            else {
+                uint32_t o[4];
+                const unsigned long long seed = *seed_ptr;
+                philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)slot, (uint32_t)gen_step[slot], (uint32_t)(i >> 1), 0x5054545Au, o);
+                const float u1 = ((float)(o[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                const float u2 = ((float)(o[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                const float rad = sqrtf(-2.0f * logf(u1));
+                float sn, cn; sincosf(6.28318530717958647692f * u2, &sn, &cn);
+                z = ((i & 1) ? rad * sn : rad * cn) * std;
+            }
         }
+        noise_f32[r * LDIM + i] = z;
+        zs[i] = __bfloat162float(__float2bfloat16_rn(z));
     }
-    noise_f32[idx] = z;
-    noise_bf16[idx] = __float2bfloat16_rn(z);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int o = i * 4 + j;
+        const uint4* wr = reinterpret_cast<const uint4*>(w_in + (long long)o * LDIM);
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 wv = __ldg(wr + q);
+            const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                acc = fmaf(__uint_as_float(w[t] << 16), zs[q * 8 + 2 * t], acc);
+                acc = fmaf(__uint_as_float(w[t] & 0xffff0000u), zs[q * 8 + 2 * t + 1], acc);
+            }
+        }
+        xh[(long long)r * D_FLOW + o] = acc + (b_in ? b_in[o] : 0.f);
+    }
+}
+
+// Decode-step entry of the FlowLM backbone, one CTA (256 threads) per utterance: h = input_linear(bf16(previous latent)) (32 -> 1024,
+// reference models/flow_lm.h:99) followed by layer 0's norm1 (src/torch.h:49-60) -> bf16 A operand of the first in_proj.
+__global__ void __launch_bounds__(256) flow_in_kernel(int slot0, int n, const __nv_bfloat16* __restrict__ lat_in, const __nv_bfloat16* __restrict__ w_in,
+                                                      const float* __restrict__ b_in, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                                                      float* __restrict__ h, __nv_bfloat16* __restrict__ n_bf) {
+    pdl_prologue();
+    __shared__ float xs[LDIM];
+    __shared__ float red[2][8];
+    const int r = blockIdx.x, i = threadIdx.x, warp = i >> 5, lane = i & 31;
+    if (r >= n) return;
+    if (i < LDIM) xs[i] = __bfloat162float(lat_in[(long long)(slot0 + r) * LDIM + i]);
+    __syncthreads();
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int o = i * 4 + j;
+        const uint4* wr = reinterpret_cast<const uint4*>(w_in + (long long)o * LDIM);
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 wv = __ldg(wr + q);
+            const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                acc = fmaf(__uint_as_float(w[t] << 16), xs[q * 8 + 2 * t], acc);
+                acc = fmaf(__uint_as_float(w[t] & 0xffff0000u), xs[q * 8 + 2 * t + 1], acc);
+            }
+        }
+        v[j] = acc + (b_in ? b_in[o] : 0.f);
+    }
+    *reinterpret_cast<float4*>(h + (long long)r * D_MODEL + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    const float s1 = warp_sum(v[0] + v[1] + v[2] + v[3]);
+    if (lane == 0) red[0][warp] = s1;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) tot += red[0][w];
+    const float mean = tot / D_MODEL;
+    float s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { v[j] -= mean; s2 += v[j] * v[j]; }
+    s2 = warp_sum(s2);
+    if (lane == 0) red[1][warp] = s2;
+    __syncthreads();
+    tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) tot += red[1][w];
+    const float rs = 1.0f / sqrtf(tot / D_MODEL + 1e-5f);
+    __nv_bfloat16 yb[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { float y = v[j] * rs * lnw[i * 4 + j]; if (lnb) y += lnb[i * 4 + j]; yb[j] = __float2bfloat16_rn(y); }
+    *reinterpret_cast<uint2*>(n_bf + (long long)r * D_MODEL + i * 4) = *reinterpret_cast<uint2*>(yb);
 }
 
 // Stop rule + bookkeeping after the head (reference src/pocket_tts.cpp:457-467,487-489). Per slot:
