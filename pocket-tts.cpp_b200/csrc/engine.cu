@@ -24,8 +24,9 @@ struct HostTensor { std::vector<float> f; std::vector<int64_t> shape; int dtype;
 inline float h_bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 inline float h_silu(float x) { return x / (1.0f + expf(-x)); }
 
-struct LinW { __nv_bfloat16* w = nullptr; float* b = nullptr; int out = 0, in = 0; };
-struct ConvW { __half* w = nullptr; float* b = nullptr; int N = 0, K = 0; };
+// w: [out][in] row-major (GEMV / CUDA-core paths), wk: k-block-major copy for the tensor-core path (nullptr when in % 64 != 0)
+struct LinW { __nv_bfloat16* w = nullptr; __nv_bfloat16* wk = nullptr; float* b = nullptr; int out = 0, in = 0; };
+struct ConvW { __half* w = nullptr; __half* wk = nullptr; float* b = nullptr; int N = 0, K = 0; };
 
 }  // namespace
 
@@ -54,6 +55,7 @@ struct b200_engine {
     float *emb_std = nullptr, *emb_mean = nullptr;
     std::vector<float> h_bos; float* d_bos = nullptr;
     LinW input_linear, cond_embed, input_proj, ada_all, final_lin;
+    __nv_bfloat16 *input_linear_t = nullptr, *input_proj_t = nullptr;   // [32][out] transposed copies for the fused decode-entry kernels
     float *onw = nullptr, *onb = nullptr; __nv_bfloat16* w_eos = nullptr; float* b_eos = nullptr;
     struct { LinW in_proj, out_proj, lin1, lin2; float *n1w, *n1b, *n2w, *n2b; } fl[N_LAYERS];
     struct { float *lnw, *lnb; LinW mlp0, mlp2; } rb[N_RES];
@@ -141,7 +143,9 @@ struct b200_engine {
         auto* w = find(p + ".weight");
         if ((int64_t)w->f.size() != (int64_t)out * in) { fprintf(stderr, "ptts_b200: error: bad shape for %s\n", p.c_str()); exit(1); }
         LinW L; L.out = out; L.in = in;
-        L.w = upload(to_bf16(w->f));
+        const auto wb = to_bf16(w->f);
+        L.w = upload(wb);
+        if (in % 64 == 0) L.wk = tc->w_kb_major ? upload(tc_kblock_major(wb, out, in)) : L.w;
         L.b = up_f32(p + ".bias", false);
         return L;
     }
@@ -154,6 +158,7 @@ struct b200_engine {
         for (int a = 0; a < co; a++) for (int b = 0; b < ci; b++) for (int c = 0; c < k; c++)
             o[((size_t)a * k + c) * cp + b] = __float2half_rn(w->f[((size_t)a * ci + b) * k + c]);
         ConvW C; C.N = co; C.K = k * cp; C.w = upload(o); C.b = up_f32(p + ".conv.bias", false);
+        if (C.K % 64 == 0) C.wk = tc->w_kb_major ? upload(tc_kblock_major(o, C.N, C.K)) : C.w;
         return C;
     }
     // transposed conv K = 2s (torch [ci][co][k]) as a 2-tap GEMM over [prev row | current row]:
@@ -168,6 +173,7 @@ struct b200_engine {
             o[((size_t)(j * co + c)) * Kw + kk] = __float2half_rn(w->f[((size_t)cin * co + c) * k + tap]);
         }
         ConvW C; C.N = N; C.K = Kw; C.w = upload(o);
+        if (Kw % 64 == 0) C.wk = tc->w_kb_major ? upload(tc_kblock_major(o, N, Kw)) : C.w;
         auto* b = find(p + ".convtr.bias", false);
         if (b) { std::vector<float> bb(N); for (int j = 0; j < s; j++) for (int c = 0; c < co; c++) bb[j * co + c] = b->f[c]; C.b = upload(bb); }
         return C;
@@ -176,11 +182,11 @@ struct b200_engine {
     // ---------------------------------------------------------------------------------------------
     // Returns true when the LayerNorm described by `ln` was fused into the GEMM's split-K reduction.
     template <typename T>
-    bool gemm(const T* A, RowMap amap, int a_rps, const T* W, int R, int N, int K, const Epi& epi, const LnFuse* ln = nullptr) {
+    bool gemm(const T* A, RowMap amap, int a_rps, const T* W, const T* Wk, int R, int N, int K, const Epi& epi, const LnFuse* ln = nullptr) {
         if (R <= 0) return false;
-        if (cfg.gemm_path == 0 && tc_gemm_supported<T>(R, N, K, amap, a_rps)) {
+        if (cfg.gemm_path == 0 && Wk && tc_gemm_supported<T>(R, N, K, amap, a_rps, epi)) {
             bool done = false;
-            launches += tc_gemm_launch<T>(tc, A, amap, a_rps, W, R, N, K, epi, stream, ln, &done);
+            launches += tc_gemm_launch<T>(tc, A, amap, a_rps, Wk, R, N, K, epi, stream, ln, &done);
             return done;
         }
         if (R <= 8) {
@@ -197,7 +203,7 @@ struct b200_engine {
     static RowMap smap(long long slot_stride, long long row_stride, long long base) { RowMap m; m.slot_stride = slot_stride; m.row_stride = row_stride; m.base = base; return m; }
     bool lin(const __nv_bfloat16* A, const LinW& L, int R, Epi epi, const LnFuse* ln = nullptr) {
         if (!epi.bias) epi.bias = L.b;
-        return gemm<__nv_bfloat16>(A, rows(L.in), 1 << 30, L.w, R, L.out, L.in, epi, ln);
+        return gemm<__nv_bfloat16>(A, rows(L.in), 1 << 30, L.w, L.wk, R, L.out, L.in, epi, ln);
     }
 
     // FlowLM transformer over R rows held in `h` (reference modules/transformer.h:253-278,363-374).
@@ -307,31 +313,31 @@ struct b200_engine {
                         s8 = 481LL * C8, s9a = 1922LL * 64, s9b = 1920LL * 64, s11 = 1922LL * 64;
         const int o2t = cfg.convt_split ? OUT2_F16_SPLIT : OUT2_F16;
         { Epi e; e.rps = T0; e.bias = c0.b; e.act = ACT_ELU; e.out2 = buf2 + slot0 * s2; e.out2_map = smap(s2, C2, C2); e.out2_type = o2t; e.split_off = 512;
-          gemm<__half>(buf0 + slot0 * s0, smap(s0, 512, 0), T0, c0.w, n * T0, c0.N, c0.K, e); }
+          gemm<__half>(buf0 + slot0 * s0, smap(s0, 512, 0), T0, c0.w, c0.wk, n * T0, c0.N, c0.K, e); }
         { Epi e; e.rps = T0; e.bias = t2.b; e.out = y3 + slot0 * 96LL * 256; e.out_map = smap(96LL * 256, 1536, 0);
           e.act = ACT_ELU; e.out2 = buf3a + slot0 * s3a; e.out2_map = smap(s3a, 1536, 2 * 256); e.out2_type = OUT2_F16;
-          gemm<__half>(buf2 + slot0 * s2, smap(s2, C2, 0), T0, t2.w, n * T0, t2.N, t2.K, e); }
+          gemm<__half>(buf2 + slot0 * s2, smap(s2, C2, 0), T0, t2.w, t2.wk, n * T0, t2.N, t2.K, e); }
         { Epi e; e.rps = T1; e.bias = r3a.b; e.act = ACT_ELU; e.out2 = buf3b + slot0 * s3b; e.out2_map = smap(s3b, 128, 0); e.out2_type = OUT2_F16;
-          gemm<__half>(buf3a + slot0 * s3a, smap(s3a, 256, 0), T1, r3a.w, n * T1, r3a.N, r3a.K, e); }
+          gemm<__half>(buf3a + slot0 * s3a, smap(s3a, 256, 0), T1, r3a.w, r3a.wk, n * T1, r3a.N, r3a.K, e); }
         { Epi e; e.rps = T1; e.bias = r3b.b; e.resid = y3 + slot0 * 96LL * 256; e.resid_map = smap(96LL * 256, 256, 0);
           e.act = ACT_ELU; e.out2 = buf5 + slot0 * s5; e.out2_map = smap(s5, C5, C5); e.out2_type = o2t; e.split_off = 256;
-          gemm<__half>(buf3b + slot0 * s3b, smap(s3b, 128, 0), T1, r3b.w, n * T1, r3b.N, r3b.K, e); }
+          gemm<__half>(buf3b + slot0 * s3b, smap(s3b, 128, 0), T1, r3b.w, r3b.wk, n * T1, r3b.N, r3b.K, e); }
         { Epi e; e.rps = T1; e.bias = t5.b; e.out = y6 + slot0 * 480LL * 128; e.out_map = smap(480LL * 128, 640, 0);
           e.act = ACT_ELU; e.out2 = buf6a + slot0 * s6a; e.out2_map = smap(s6a, 640, 2 * 128); e.out2_type = OUT2_F16;
-          gemm<__half>(buf5 + slot0 * s5, smap(s5, C5, 0), T1, t5.w, n * T1, t5.N, t5.K, e); }
+          gemm<__half>(buf5 + slot0 * s5, smap(s5, C5, 0), T1, t5.w, t5.wk, n * T1, t5.N, t5.K, e); }
         { Epi e; e.rps = T2; e.bias = r6a.b; e.act = ACT_ELU; e.out2 = buf6b + slot0 * s6b; e.out2_map = smap(s6b, 64, 0); e.out2_type = OUT2_F16;
-          gemm<__half>(buf6a + slot0 * s6a, smap(s6a, 128, 0), T2, r6a.w, n * T2, r6a.N, r6a.K, e); }
+          gemm<__half>(buf6a + slot0 * s6a, smap(s6a, 128, 0), T2, r6a.w, r6a.wk, n * T2, r6a.N, r6a.K, e); }
         { Epi e; e.rps = T2; e.bias = r6b.b; e.resid = y6 + slot0 * 480LL * 128; e.resid_map = smap(480LL * 128, 128, 0);
           e.act = ACT_ELU; e.out2 = buf8 + slot0 * s8; e.out2_map = smap(s8, C8, C8); e.out2_type = o2t; e.split_off = 128;
-          gemm<__half>(buf6b + slot0 * s6b, smap(s6b, 64, 0), T2, r6b.w, n * T2, r6b.N, r6b.K, e); }
+          gemm<__half>(buf6b + slot0 * s6b, smap(s6b, 64, 0), T2, r6b.w, r6b.wk, n * T2, r6b.N, r6b.K, e); }
         { Epi e; e.rps = T2; e.bias = t8.b; e.out = y9 + slot0 * 1920LL * 64; e.out_map = smap(1920LL * 64, 256, 0);
           e.act = ACT_ELU; e.out2 = buf9a + slot0 * s9a; e.out2_map = smap(s9a, 256, 2 * 64); e.out2_type = OUT2_F16;
-          gemm<__half>(buf8 + slot0 * s8, smap(s8, C8, 0), T2, t8.w, n * T2, t8.N, t8.K, e); }
+          gemm<__half>(buf8 + slot0 * s8, smap(s8, C8, 0), T2, t8.w, t8.wk, n * T2, t8.N, t8.K, e); }
         { Epi e; e.rps = T3; e.bias = r9a.b; e.act = ACT_ELU; e.out2 = buf9b + slot0 * s9b; e.out2_map = smap(s9b, 64, 0); e.out2_type = OUT2_F16;
-          gemm<__half>(buf9a + slot0 * s9a, smap(s9a, 64, 0), T3, r9a.w, n * T3, r9a.N, r9a.K, e); }
+          gemm<__half>(buf9a + slot0 * s9a, smap(s9a, 64, 0), T3, r9a.w, r9a.wk, n * T3, r9a.N, r9a.K, e); }
         { Epi e; e.rps = T3; e.bias = r9b.b; e.resid = y9 + slot0 * 1920LL * 64; e.resid_map = smap(1920LL * 64, 64, 0);
           e.act = ACT_ELU; e.out2 = buf11 + slot0 * s11; e.out2_map = smap(s11, 64, 2 * 64); e.out2_type = OUT2_F16;
-          gemm<__half>(buf9b + slot0 * s9b, smap(s9b, 64, 0), T3, r9b.w, n * T3, r9b.N, r9b.K, e); }
+          gemm<__half>(buf9b + slot0 * s9b, smap(s9b, 64, 0), T3, r9b.w, r9b.wk, n * T3, r9b.N, r9b.K, e); }
         {
             const int Rr = n * T3;
             launch_k(pdl_active, conv_n1_kernel, dim3((Rr * 4 + 255) / 256), dim3(256), (size_t)(0), stream, buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm + (long long)slot0 * FRAME);
@@ -354,14 +360,14 @@ struct b200_engine {
         set_pdl(pdl_small || pdl_chain);
         prepare_step(slot0, n);
         const int s_flow = seg_begin(1);
-        launch_k(pdl_active, flow_in_kernel, dim3(n), dim3(256), (size_t)0, stream, slot0, n, (const __nv_bfloat16*)lat_in_bf16, (const __nv_bfloat16*)input_linear.w,
+        launch_k(pdl_active, flow_in_kernel, dim3(n), dim3(256), (size_t)0, stream, slot0, n, (const __nv_bfloat16*)lat_in_bf16, (const __nv_bfloat16*)input_linear_t,
                  (const float*)input_linear.b, (const float*)fl[0].n1w, (const float*)fl[0].n1b, h, n_bf);
         launches++;
         flow_forward(n, true);
         seg_end(s_flow);
         const int s_head = seg_begin(2);
         launch_k(pdl_active, noise_inproj_kernel, dim3(n), dim3(128), (size_t)(0), stream, slot0, n, (const float*)(injected ? noise_inj : nullptr), (const unsigned long long*)d_seed,
-                 (const float*)temp, (const int*)gen_step, noise_f32, (const __nv_bfloat16*)input_proj.w, (const float*)input_proj.b, xh);
+                 (const float*)temp, (const int*)gen_step, noise_f32, (const __nv_bfloat16*)input_proj_t, (const float*)input_proj.b, xh);
         flow_head(n);
         launch_k(pdl_active, step_logic_kernel, dim3(n), dim3(32), (size_t)(0), stream, slot0, n, eos, latent, cur_len, gen_step, eos_step, max_gen, fae, active, lat_in_bf16, lat_f32, produced, eos_out);
         launches += 2;
@@ -499,6 +505,13 @@ int b200_finalize_weights(b200_engine* e) {
     e->emb_std = e->up_f32("flow_lm.emb_std"); e->emb_mean = e->up_f32("flow_lm.emb_mean");
     e->h_bos = e->find("flow_lm.bos_emb")->f; e->d_bos = e->upload(e->h_bos);
     e->input_linear = e->up_lin("flow_lm.input_linear", D_MODEL, LDIM);
+    auto transposed = [&](const std::string& key, int out, int in) {
+        const auto& w = e->find(key)->f;
+        std::vector<float> t((size_t)out * in);
+        for (int o = 0; o < out; o++) for (int k = 0; k < in; k++) t[(size_t)k * out + o] = w[(size_t)o * in + k];
+        return e->upload(b200_engine::to_bf16(t));
+    };
+    e->input_linear_t = transposed("flow_lm.input_linear.weight", D_MODEL, LDIM);
     e->onw = e->up_f32("flow_lm.out_norm.weight"); e->onb = e->up_f32("flow_lm.out_norm.bias", false);
     e->w_eos = e->upload(b200_engine::to_bf16(e->find("flow_lm.out_eos.weight")->f));
     e->b_eos = e->up_f32("flow_lm.out_eos.bias", false);
@@ -512,6 +525,7 @@ int b200_finalize_weights(b200_engine* e) {
     }
     const std::string f = "flow_lm.flow_net.";
     e->input_proj = e->up_lin(f + "input_proj", D_FLOW, LDIM);
+    e->input_proj_t = transposed(f + "input_proj.weight", D_FLOW, LDIM);
     e->cond_embed = e->up_lin(f + "cond_embed", D_FLOW, D_MODEL);
     {   // seven adaLN projections of the same silu(y) fused into one [10240][512] weight
         std::vector<float> w, b; bool has_b = true;
@@ -523,7 +537,8 @@ int b200_finalize_weights(b200_engine* e) {
         }
         (void)has_b;
         e->ada_all.out = (int)(w.size() / D_FLOW); e->ada_all.in = D_FLOW;
-        e->ada_all.w = e->upload(b200_engine::to_bf16(w)); e->ada_all.b = e->upload(b);
+        const auto wb = b200_engine::to_bf16(w);
+        e->ada_all.w = e->upload(wb); e->ada_all.wk = e->tc->w_kb_major ? e->upload(tc_kblock_major(wb, e->ada_all.out, D_FLOW)) : e->ada_all.w; e->ada_all.b = e->upload(b);
     }
     for (int r = 0; r < N_RES; r++) {
         const std::string p = f + "res_blocks." + std::to_string(r) + ".";
@@ -871,8 +886,13 @@ int b200_debug_gemm(b200_engine* e, int f16, const float* A, int n_slots, int ro
     const int saved = e->cfg.gemm_path; e->cfg.gemm_path = path;
     e->set_pdl(false);
     int used_tc = 0;
-    if (f16) { used_tc = (path == 0 && tc_gemm_supported<__half>(R, N, K, am, rps)); e->gemm<__half>((const __half*)dA, am, rps, (const __half*)dW, R, N, K, ep); }
-    else { used_tc = (path == 0 && tc_gemm_supported<__nv_bfloat16>(R, N, K, am, rps)); e->gemm<__nv_bfloat16>((const __nv_bfloat16*)dA, am, rps, (const __nv_bfloat16*)dW, R, N, K, ep); }
+    void* dWk = nullptr;
+    if (K % 64 == 0) {
+        const std::vector<uint16_t> hk = e->tc->w_kb_major ? tc_kblock_major(hw, N, K) : hw;
+        PTTS_CUDA_CHECK(cudaMalloc(&dWk, nw * 2)); PTTS_CUDA_CHECK(cudaMemcpy(dWk, hk.data(), nw * 2, cudaMemcpyHostToDevice));
+    }
+    if (f16) { used_tc = (path == 0 && dWk && tc_gemm_supported<__half>(R, N, K, am, rps, ep)); e->gemm<__half>((const __half*)dA, am, rps, (const __half*)dW, (const __half*)dWk, R, N, K, ep); }
+    else { used_tc = (path == 0 && dWk && tc_gemm_supported<__nv_bfloat16>(R, N, K, am, rps, ep)); e->gemm<__nv_bfloat16>((const __nv_bfloat16*)dA, am, rps, (const __nv_bfloat16*)dW, (const __nv_bfloat16*)dWk, R, N, K, ep); }
     e->cfg.gemm_path = saved;
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     PTTS_CUDA_CHECK(cudaGetLastError());
@@ -882,7 +902,7 @@ int b200_debug_gemm(b200_engine* e, int f16, const float* A, int n_slots, int ro
         PTTS_CUDA_CHECK(cudaMemcpy(h2.data(), dO2, h2.size() * 2, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < h2.size(); i++) out2_as_f32[i] = f16 ? __half2float(*(__half*)&h2[i]) : __bfloat162float(*(__nv_bfloat16*)&h2[i]);
     }
-    cudaFree(dA); cudaFree(dW); cudaFree(dO); cudaFree(dO2); if (dB) cudaFree(dB);
+    cudaFree(dA); cudaFree(dW); cudaFree(dO); cudaFree(dO2); if (dB) cudaFree(dB); if (dWk) cudaFree(dWk);
     return used_tc;
 }
 

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <map>
 #include <tuple>
+#include <vector>
 
 namespace ptts {
 
@@ -42,6 +43,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -88,34 +92,139 @@ struct TcParams {
     int splits;           // deterministic split-K: work item = (tile, split); partial sums go to a workspace
     int kb_per_split;
     long long ws_split_stride;   // elements between the partial-sum planes of consecutive splits
+    int epi_class;               // index into EPI_CLASSES (0 = fully dynamic epilogue)
+    int prefetch;                // 1 = small-M GEMM: prefetch the first work item's whole weight stream into L2 up front
 };
 
-// ---- GENERIC epilogue for 4 consecutive columns of one row (bias / colscale already loaded for these columns) ----
-// Called after the accumulator chunk was transposed through shared memory, so that the 8 lanes sharing a row cover 128 contiguous
-// bytes (f32) and every warp-level load/store touches 4 full lines instead of 32 partial ones.
-__device__ __forceinline__ void epi_generic4(const Epi& e, int col, float (&v)[4], long long ro, long long r2,
-                                             const float4& bias4, const float4& cs4, const float4& rm4, const float4& rs4) {
-    v[0] = (v[0] + bias4.x) * cs4.x * rm4.x + rs4.x; v[1] = (v[1] + bias4.y) * cs4.y * rm4.y + rs4.y;
-    v[2] = (v[2] + bias4.z) * cs4.z * rm4.z + rs4.z; v[3] = (v[3] + bias4.w) * cs4.w * rm4.w + rs4.w;
-    if (e.out) *reinterpret_cast<float4*>(e.out + ro + col) = make_float4(v[0], v[1], v[2], v[3]);
-    if (e.out2_type != OUT2_NONE) {
-        if (e.act != ACT_NONE) {
+// Epilogue staging per epilogue warp: a 32 x 32 f32 accumulator chunk transposed through shared memory (rows padded to 36 floats:
+// 16-byte aligned and conflict-free for 128-bit stores by row and 128-bit loads by quarter-row) + (slot, row-in-slot) of its 32 rows.
+constexpr int EPI_WARPS = 8, EPI_STG_LD = 36, EPI_STG_BYTES = 32 * EPI_STG_LD * 4, EPI_ROW_BYTES = 32 * 8;
+constexpr int EPI_SMEM = EPI_WARPS * (EPI_STG_BYTES + EPI_ROW_BYTES);   // 38,912 B
+
+// ---- GENERIC epilogue, specialised at compile time ----
+// The epilogue description (Epi) is a runtime structure; evaluating its flags per element made the big conv GEMMs instruction-issue bound
+// (ncu r1_v8: 12.7 k warp-instructions per 128x64 tile, issue slots 57 % busy, tensor pipe 2 %). The host therefore maps the Epi to one
+// of a few flag sets (epi_class) that the kernel switches on ONCE per 32-column chunk; everything inside is straight-line code.
+// EF_DYNAMIC keeps the fully general runtime version for anything not in the list.
+enum : unsigned { EF_BIAS = 1, EF_COLSCALE = 2, EF_ROWMUL = 4, EF_RESID = 8, EF_OUT = 16, EF_OUT2_BF16 = 32, EF_OUT2_F16 = 64, EF_SPLIT = 128,
+                  EF_GELU = 256, EF_SILU = 512, EF_ELU = 1024, EF_DYNAMIC = 1u << 31 };
+constexpr unsigned EPI_CLASSES[] = {
+    EF_DYNAMIC,                                             // 0 = not supported by the tensor-core kernel (CUDA-core fallback)
+    EF_ELU | EF_OUT2_F16,                                   // 1 SEANet conv
+    EF_OUT | EF_ELU | EF_OUT2_F16,                          // 2 SEANet transposed conv (f32 skip copy + f16 next input)
+    EF_RESID | EF_ELU | EF_OUT2_F16,                        // 3 SEANet residual-block tail
+    EF_COLSCALE | EF_RESID | EF_OUT,                        // 4 Mimi out_proj / linear2 (layer scale + residual)
+    EF_GELU | EF_OUT2_BF16,                                 // 5 linear1 (+GELU)
+    EF_RESID | EF_OUT,                                      // 6 FlowLM out_proj / linear2 (unsplit), flow head final linear (+noise)
+    EF_OUT,                                                 // 7 split-K partial sums, adaLN projections
+    EF_COLSCALE | EF_RESID | EF_OUT2_F16,                   // 8 last Mimi linear2 (writes SEANet's f16 input)
+    EF_SILU | EF_OUT2_BF16,                                 // 9 flow head mlp.0
+    EF_ROWMUL | EF_RESID | EF_OUT,                          // 10 flow head mlp.2 (gate + residual)
+    EF_RESID | EF_SILU | EF_OUT2_BF16,                      // 11 flow head cond_embed (+ t_combined, SiLU)
+    EF_OUT | EF_ELU | EF_OUT2_BF16,                         // 12 unit tests (bf16 flavour of class 2)
+    EF_ELU | EF_OUT2_F16 | EF_SPLIT,                        // 13 convt_split=1: conv feeding a transposed conv (hi | lo f16)
+    EF_RESID | EF_ELU | EF_OUT2_F16 | EF_SPLIT,             // 14 convt_split=1: residual-block tail feeding a transposed conv
+};
+constexpr int EPI_NCLASSES = sizeof(EPI_CLASSES) / sizeof(EPI_CLASSES[0]);
+
+// The bias is always a runtime option (one uniform branch per chunk), everything else is part of the class key.
+inline unsigned epi_flags_of(const Epi& e) {
+    unsigned f = 0;
+    if (e.colscale) f |= EF_COLSCALE;
+    if (e.rowmul) f |= EF_ROWMUL;
+    if (e.resid) f |= EF_RESID;
+    if (e.out) f |= EF_OUT;
+    if (e.out2_type == OUT2_BF16) f |= EF_OUT2_BF16;
+    if (e.out2_type == OUT2_F16 || e.out2_type == OUT2_F16_SPLIT) f |= EF_OUT2_F16;
+    if (e.out2_type == OUT2_F16_SPLIT) f |= EF_SPLIT;
+    if (e.out2_type != OUT2_NONE) { if (e.act == ACT_GELU) f |= EF_GELU; else if (e.act == ACT_SILU) f |= EF_SILU; else if (e.act == ACT_ELU) f |= EF_ELU; }
+    return f;
+}
+inline int epi_class_of(const Epi& e) {
+    const unsigned f = epi_flags_of(e);
+    for (int i = 1; i < EPI_NCLASSES; i++) if (EPI_CLASSES[i] == f) return i;
+    return 0;
+}
+
+// One 32x32 accumulator chunk, already transposed into `stg` ([32][EPI_STG_LD] f32): lane (sub, cq) handles rows 4i + sub, columns
+// cq..cq+3, so that the 8 lanes sharing a row cover 128 contiguous bytes (f32) and every warp-level access touches 4 full lines.
+template <unsigned F>
+__device__ __forceinline__ void epi_chunk(const Epi& e, const float* stg, const int2* rowinfo, int sub, int cq, int col, int rows_left, int tile_row0, long long ws_off) {
+    constexpr bool DYN = (F & EF_DYNAMIC) != 0;
+    const bool has_bias = e.bias != nullptr;
+    const bool has_cs = DYN ? e.colscale != nullptr : (F & EF_COLSCALE) != 0;
+    const bool has_rm = DYN ? e.rowmul != nullptr : (F & EF_ROWMUL) != 0;
+    const bool has_res = DYN ? e.resid != nullptr : (F & EF_RESID) != 0;
+    const bool has_out = DYN ? e.out != nullptr : (F & EF_OUT) != 0;
+    const bool o2_bf16 = DYN ? e.out2_type == OUT2_BF16 : (F & EF_OUT2_BF16) != 0;
+    const bool o2_f16 = DYN ? (e.out2_type == OUT2_F16 || e.out2_type == OUT2_F16_SPLIT) : (F & EF_OUT2_F16) != 0;
+    const bool o2_split = DYN ? e.out2_type == OUT2_F16_SPLIT : (F & EF_SPLIT) != 0;
+    const int act = DYN ? e.act : ((F & EF_GELU) ? ACT_GELU : (F & EF_SILU) ? ACT_SILU : (F & EF_ELU) ? ACT_ELU : ACT_NONE);
+    const float4 bias4 = has_bias ? __ldg(reinterpret_cast<const float4*>(e.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 cs4 = has_cs ? __ldg(reinterpret_cast<const float4*>(e.colscale + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    // strides fit 32 bits (a slot's buffer is far below 2^31 elements): one IMAD.WIDE per term instead of 64 x 64 multiplies
+    const int res_ss = (int)e.resid_map.slot_stride, res_rs = (int)e.resid_map.row_stride;
+    const int out_ss = (int)e.out_map.slot_stride, out_rs = (int)e.out_map.row_stride;
+    const int o2_ss = (int)e.out2_map.slot_stride, o2_rs = (int)e.out2_map.row_stride;
+    // the residual loads of the 8 rows are issued before any store: the compiler cannot hoist them itself (stores through out/out2
+    // may alias), and serialised load->store pairs cost ~1 us each
 #pragma unroll
-            for (int i = 0; i < 4; i++) v[i] = apply_act(v[i], e.act);
+    for (int half = 0; half < 2; half++) {                      // two passes of 4 rows: 16 registers of residual prefetch instead of 32
+        float4 rs4[4];
+        if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int r = 16 * half + 4 * i + sub;
+                rs4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < rows_left) {
+                    const int2 ri = rowinfo[r];
+                    rs4[i] = *reinterpret_cast<const float4*>(e.resid + ((long long)ri.x * res_ss + (long long)ri.y * res_rs + e.resid_map.base) + col);
+                }
+            }
         }
-        if (e.out2_type == OUT2_BF16) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>((__nv_bfloat16*)e.out2 + r2 + col) = pk;
-        } else {
-            const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-            uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-            *reinterpret_cast<uint2*>((__half*)e.out2 + r2 + col) = pk;
-            if (e.out2_type == OUT2_F16_SPLIT) {
-                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-                const __half2 l0 = __floats2half2_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2half2_rn(v[2] - f1.x, v[3] - f1.y);
-                uint2 pl; pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
-                *reinterpret_cast<uint2*>((__half*)e.out2 + r2 + col + e.split_off) = pl;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int r = 16 * half + 4 * i + sub;
+            if (r < rows_left) {
+                const float4 w4 = *reinterpret_cast<const float4*>(stg + r * EPI_STG_LD + cq);
+                const int2 ri = rowinfo[r];
+                float v[4] = {w4.x, w4.y, w4.z, w4.w};
+                if (has_bias) { v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w; }
+                if (has_cs) { v[0] *= cs4.x; v[1] *= cs4.y; v[2] *= cs4.z; v[3] *= cs4.w; }
+                if (has_rm) {
+                    const float4 m = *reinterpret_cast<const float4*>(e.rowmul + (long long)(tile_row0 + r) * e.rowmul_ld + col);
+                    v[0] *= m.x; v[1] *= m.y; v[2] *= m.z; v[3] *= m.w;
+                }
+                if (has_res) { v[0] += rs4[i].x; v[1] += rs4[i].y; v[2] += rs4[i].z; v[3] += rs4[i].w; }
+                if (has_out) *reinterpret_cast<float4*>(e.out + ((long long)ri.x * out_ss + (long long)ri.y * out_rs + e.out_map.base + ws_off) + col) = make_float4(v[0], v[1], v[2], v[3]);
+                if (o2_bf16 || o2_f16) {
+                    if (act == ACT_GELU) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) v[k] = gelu_ggml(v[k]);
+                    } else if (act == ACT_SILU) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) v[k] = silu_f(v[k]);
+                    } else if (act == ACT_ELU) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) v[k] = elu_f(v[k]);
+                    }
+                    const long long r2 = (long long)ri.x * o2_ss + (long long)ri.y * o2_rs + e.out2_map.base + col;
+                    if (o2_bf16) {
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+                        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                        *reinterpret_cast<uint2*>((__nv_bfloat16*)e.out2 + r2) = pk;
+                    } else {
+                        const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+                        uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                        *reinterpret_cast<uint2*>((__half*)e.out2 + r2) = pk;
+                        if (o2_split) {
+                            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                            const __half2 l0 = __floats2half2_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2half2_rn(v[2] - f1.x, v[3] - f1.y);
+                            uint2 pl; pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+                            *reinterpret_cast<uint2*>((__half*)e.out2 + r2 + e.split_off) = pl;
+                        }
+                    }
+                }
             }
         }
     }
@@ -177,11 +286,6 @@ __device__ __forceinline__ void epi_qkv32(const Epi& e, int row, int col0, float
         }
     }
 }
-
-// Epilogue staging per epilogue warp: a 32 x 32 f32 accumulator chunk transposed through shared memory (rows padded to 36 floats:
-// 16-byte aligned and conflict-free for 128-bit stores by row and 128-bit loads by quarter-row) + (slot, row-in-slot) of its 32 rows.
-constexpr int EPI_WARPS = 8, EPI_STG_LD = 36, EPI_STG_BYTES = 32 * EPI_STG_LD * 4, EPI_ROW_BYTES = 32 * 8;
-constexpr int EPI_SMEM = EPI_WARPS * (EPI_STG_BYTES + EPI_ROW_BYTES);   // 38,912 B
 
 template <int BN>
 struct TcCfg {
@@ -252,7 +356,12 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
                     const int tap = kb / p.kb_per_tap, c0 = (kb % p.kb_per_tap) * 64;
                     mbar_expect_tx(full0 + 8 * s, bytes);
                     tma_load_3d(sA + s * Cfg::A_BYTES, &tmA, full0 + 8 * s, c0, t0 + tap, slot);
-                    tma_load_2d(sW + s * Cfg::W_BYTES, &tmW, full0 + 8 * s, kb * 64, tile_n * BN);
+                    tma_load_3d(sW + s * Cfg::W_BYTES, &tmW, full0 + 8 * s, 0, tile_n * BN, kb);
+                    if (p.prefetch && work == (int)blockIdx.x && kb == min(kb1, kb0 + STAGES) - 1) {
+                        // Decode-sized GEMMs read their weights cold from HBM (the KV stream has flushed L2) and the smem ring alone
+                        // cannot cover DRAM latency x bandwidth: once the ring is full, ask L2 for the rest of this CTA's weight stream.
+                        for (int kp = kb + 1; kp < kb1; kp++) tma_prefetch_3d(&tmW, 0, tile_n * BN, kp);
+                    }
                 }
             }
         }
@@ -313,34 +422,23 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 8; j++) sp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     __syncwarp();
-                    const int col = tile_n * BN + c0 + cq;
-                    const float4 bias4 = epi.bias ? __ldg(reinterpret_cast<const float4*>(epi.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 cs4 = epi.colscale ? __ldg(reinterpret_cast<const float4*>(epi.colscale + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
-                    // the residual loads of the 8 rows are issued before any store: the compiler cannot hoist them itself
-                    // (stores through out/out2 may alias), and serialised load->store pairs cost ~1 us each
-                    float4 rs4[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int r = 4 * i + sub;
-                        rs4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ew * 32 + r < nvalid) {
-                            const int2 rinfo = rowinfo[r];
-                            if (epi.resid) rs4[i] = *reinterpret_cast<const float4*>(epi.resid + ((long long)rinfo.x * epi.resid_map.slot_stride + (long long)rinfo.y * epi.resid_map.row_stride + epi.resid_map.base) + col);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int r = 4 * i + sub;
-                        if (ew * 32 + r < nvalid) {
-                            const float4 w4 = *reinterpret_cast<const float4*>(stg + r * EPI_STG_LD + cq);
-                            const int2 rinfo = rowinfo[r];
-                            float w[4] = {w4.x, w4.y, w4.z, w4.w};
-                            const long long ro = (long long)rinfo.x * epi.out_map.slot_stride + (long long)rinfo.y * epi.out_map.row_stride + epi.out_map.base + ws_off;
-                            const long long r2 = (long long)rinfo.x * epi.out2_map.slot_stride + (long long)rinfo.y * epi.out2_map.row_stride + epi.out2_map.base;
-                            float4 rm4 = make_float4(1.f, 1.f, 1.f, 1.f);      // gate (flow head only: tiny GEMMs, not worth 32 registers of prefetch)
-                            if (epi.rowmul) rm4 = *reinterpret_cast<const float4*>(epi.rowmul + (long long)(row_base + ew * 32 + r) * epi.rowmul_ld + col);
-                            epi_generic4(epi, col, w, ro, r2, bias4, cs4, rm4, rs4[i]);
-                        }
+                    const int col = tile_n * BN + c0 + cq, rows_left = nvalid - ew * 32, tile_row0 = row_base + ew * 32;
+                    switch (p.epi_class) {
+                        case 1: epi_chunk<EPI_CLASSES[1]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 2: epi_chunk<EPI_CLASSES[2]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 3: epi_chunk<EPI_CLASSES[3]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 4: epi_chunk<EPI_CLASSES[4]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 5: epi_chunk<EPI_CLASSES[5]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 6: epi_chunk<EPI_CLASSES[6]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 7: epi_chunk<EPI_CLASSES[7]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 8: epi_chunk<EPI_CLASSES[8]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 9: epi_chunk<EPI_CLASSES[9]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 10: epi_chunk<EPI_CLASSES[10]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 11: epi_chunk<EPI_CLASSES[11]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 12: epi_chunk<EPI_CLASSES[12]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 13: epi_chunk<EPI_CLASSES[13]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        case 14: epi_chunk<EPI_CLASSES[14]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
+                        default: break;                        // class 0 never reaches this kernel (tc_gemm_supported)
                     }
                     __syncwarp();                                  // the staging tile is overwritten by the next chunk
                 } else if (live) {
@@ -437,6 +535,7 @@ struct TcPlanCache {
     std::map<std::tuple<const void*, long long, long long, long long, long long, int, int>, CUtensorMap> maps;
     bool attr_set[3] = {false, false, false};
     int num_sms = 148;
+    bool w_kb_major = true;     // PTTS_B200_WLAYOUT=0: keep tensor-core weights row-major (layout experiment)
     bool pdl = false;
     float* ws = nullptr; size_t ws_elems = 0;   // split-K partial sums
 };
@@ -445,6 +544,7 @@ inline TcPlanCache* tc_plan_cache_create() {
     auto* c = new TcPlanCache;
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) c->encode = (PFN_tmapEncodeTiled)fn;
+    if (const char* v = getenv("PTTS_B200_WLAYOUT")) c->w_kb_major = atoi(v) != 0;
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) c->num_sms = sms;
     return c;
@@ -508,8 +608,13 @@ inline TcPlan tc_plan(int tiles_m, int R, int N, int K, int num_sms, bool want_l
 }
 
 template <typename T>
-inline bool tc_gemm_supported(int R, int N, int K, const RowMap& amap, int a_rps) {
+inline bool tc_gemm_supported(int R, int N, int K, const RowMap& amap, int a_rps, const Epi& epi) {
     if (R < 16 || K % 64 != 0 || N % 32 != 0) return false;   // <16 rows: GEMV / CUDA-core kernels (weight-bandwidth bound anyway)
+    if (epi.mode == EPI_GENERIC && epi_class_of(epi) == 0) {
+        static bool warned = false;
+        if (!warned) { warned = true; fprintf(stderr, "ptts_b200: warning: epilogue flags 0x%x have no tensor-core class; using the CUDA-core GEMM\n", epi_flags_of(epi)); }
+        return false;
+    }
     const TcGeom g = tc_geometry(R, K, amap, a_rps);
     return g.ok;
 }
@@ -529,6 +634,17 @@ inline const CUtensorMap* tc_get_map(TcPlanCache* c, const void* ptr, bool f16, 
     return &(c->maps[key] = m);
 }
 
+// [N][K] row-major -> [K/64][N][64] (host side, at weight upload)
+template <typename T>
+inline std::vector<T> tc_kblock_major(const std::vector<T>& w, int N, int K) {
+    std::vector<T> o(w.size());
+    const int nkb = K / 64;
+    for (int kb = 0; kb < nkb; kb++)
+        for (int n = 0; n < N; n++)
+            for (int j = 0; j < 64; j++) o[((size_t)kb * N + n) * 64 + j] = w[(size_t)n * K + kb * 64 + j];
+    return o;
+}
+
 template <typename T>
 inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, const T* W, int R, int N, int K, const Epi& epi, cudaStream_t stream,
                           const LnFuse* ln = nullptr, bool* ln_done = nullptr) {
@@ -542,10 +658,13 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     cuuint64_t astr[2] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.slot_stride * 2};
     cuuint32_t abox[3] = {64, (cuuint32_t)g.box_rows, (cuuint32_t)g.SB};
     const CUtensorMap* ta = tc_get_map(c, A, f16, 3, adims, astr, abox);
-    cuuint64_t wdims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-    cuuint64_t wstr[1] = {(cuuint64_t)K * 2};
-    cuuint32_t wbox[2] = {64, (cuuint32_t)bn};
-    const CUtensorMap* tw = tc_get_map(c, W, f16, 2, wdims, wstr, wbox);
+    // weights are stored k-block-major, [K/64][N][64] (tc_kblock_major): the box of any tile width is ONE contiguous bn x 128 B run,
+    // so cold weight streams from HBM are page-friendly instead of bn separate 128-byte pieces 2*K bytes apart
+    cuuint64_t wdims[3] = {64, (cuuint64_t)N, (cuuint64_t)(K / 64)};
+    cuuint64_t wstr[2] = {128, (cuuint64_t)N * 128};
+    if (!c->w_kb_major) { wstr[0] = (cuuint64_t)K * 2; wstr[1] = 128; }   // experiment switch: plain [N][K] row-major weights
+    cuuint32_t wbox[3] = {64, (cuuint32_t)bn, 1};
+    const CUtensorMap* tw = tc_get_map(c, W, f16, 3, wdims, wstr, wbox);
     TcParams p; p.R = R; p.N = N; p.K = K; p.kb_per_tap = g.C / 64; p.T = g.T; p.SB = g.SB; p.tps = g.tps; p.tiles_m = g.tiles_m;
     p.a_bytes = (uint32_t)(128 * g.box_rows * g.SB);
     // Small-M GEMMs (FlowLM decode: R = batch) cannot fill the SMs with output tiles alone: split K deterministically.
@@ -560,6 +679,8 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
         if (!c->ws) { c->ws_elems = (size_t)32 << 20; PTTS_CUDA_CHECK(cudaMalloc(&c->ws, c->ws_elems * sizeof(float))); }
         kepi = Epi{}; kepi.out = c->ws; kepi.out_map.row_stride = N; p.ws_split_stride = (long long)R * N;
     } else { p.splits = 1; p.kb_per_split = num_kb; }
+    p.epi_class = kepi.mode == EPI_GENERIC ? epi_class_of(kepi) : 0;
+    p.prefetch = g.tiles_m <= 4 ? 1 : 0;
     // instruction descriptor (kind::f16): D=f32, A/B = bf16|f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     p.idesc = (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int total_tiles = tiles * splits;

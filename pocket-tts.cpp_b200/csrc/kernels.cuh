@@ -654,7 +654,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
 // input_proj(bf16(noise)) (32 -> 512, reference modules/mlp.h:236; bf16 operands, fp32 accumulation like every linear here).
 __global__ void __launch_bounds__(128) noise_inproj_kernel(int slot0, int n, const float* __restrict__ injected, const unsigned long long* __restrict__ seed_ptr,
                                                            const float* __restrict__ temp, const int* __restrict__ gen_step, float* __restrict__ noise_f32,
-                                                           const __nv_bfloat16* __restrict__ w_in, const float* __restrict__ b_in, float* __restrict__ xh) {
+                                                           const __nv_bfloat16* __restrict__ w_in_t, const float* __restrict__ b_in, float* __restrict__ xh) {
     pdl_prologue();
     __shared__ float zs[LDIM];
     const int r = blockIdx.x, slot = slot0 + r, i = threadIdx.x;
@@ -681,28 +681,22 @@ __global__ void __launch_bounds__(128) noise_inproj_kernel(int slot0, int n, con
         zs[i] = __bfloat162float(__float2bfloat16_rn(z));
     }
     __syncthreads();
+    // w_in_t is input_proj.weight transposed to [32][512]: thread i reads 8 contiguous bytes per input k, a warp 256 contiguous bytes
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int o = i * 4 + j;
-        const uint4* wr = reinterpret_cast<const uint4*>(w_in + (long long)o * LDIM);
-        float acc = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint4 wv = __ldg(wr + q);
-            const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                acc = fmaf(__uint_as_float(w[t] << 16), zs[q * 8 + 2 * t], acc);
-                acc = fmaf(__uint_as_float(w[t] & 0xffff0000u), zs[q * 8 + 2 * t + 1], acc);
-            }
-        }
-        xh[(long long)r * D_FLOW + o] = acc + (b_in ? b_in[o] : 0.f);
+    for (int k = 0; k < LDIM; k++) {
+        const uint2 wv = __ldg(reinterpret_cast<const uint2*>(w_in_t + (long long)k * D_FLOW + i * 4));
+        const float z = zs[k];
+        acc[0] = fmaf(__uint_as_float(wv.x << 16), z, acc[0]); acc[1] = fmaf(__uint_as_float(wv.x & 0xffff0000u), z, acc[1]);
+        acc[2] = fmaf(__uint_as_float(wv.y << 16), z, acc[2]); acc[3] = fmaf(__uint_as_float(wv.y & 0xffff0000u), z, acc[3]);
     }
+    if (b_in) { const float4 b = *reinterpret_cast<const float4*>(b_in + i * 4); acc[0] += b.x; acc[1] += b.y; acc[2] += b.z; acc[3] += b.w; }
+    *reinterpret_cast<float4*>(xh + (long long)r * D_FLOW + i * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
 // Decode-step entry of the FlowLM backbone, one CTA (256 threads) per utterance: h = input_linear(bf16(previous latent)) (32 -> 1024,
 // reference models/flow_lm.h:99) followed by layer 0's norm1 (src/torch.h:49-60) -> bf16 A operand of the first in_proj.
-__global__ void __launch_bounds__(256) flow_in_kernel(int slot0, int n, const __nv_bfloat16* __restrict__ lat_in, const __nv_bfloat16* __restrict__ w_in,
+__global__ void __launch_bounds__(256) flow_in_kernel(int slot0, int n, const __nv_bfloat16* __restrict__ lat_in, const __nv_bfloat16* __restrict__ w_in_t,
                                                       const float* __restrict__ b_in, const float* __restrict__ lnw, const float* __restrict__ lnb,
                                                       float* __restrict__ h, __nv_bfloat16* __restrict__ n_bf) {
     pdl_prologue();
@@ -712,24 +706,15 @@ __global__ void __launch_bounds__(256) flow_in_kernel(int slot0, int n, const __
     if (r >= n) return;
     if (i < LDIM) xs[i] = __bfloat162float(lat_in[(long long)(slot0 + r) * LDIM + i]);
     __syncthreads();
-    float v[4];
+    float v[4] = {0.f, 0.f, 0.f, 0.f};                         // w_in_t = input_linear.weight transposed to [32][1024] (coalesced)
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int o = i * 4 + j;
-        const uint4* wr = reinterpret_cast<const uint4*>(w_in + (long long)o * LDIM);
-        float acc = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint4 wv = __ldg(wr + q);
-            const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                acc = fmaf(__uint_as_float(w[t] << 16), xs[q * 8 + 2 * t], acc);
-                acc = fmaf(__uint_as_float(w[t] & 0xffff0000u), xs[q * 8 + 2 * t + 1], acc);
-            }
-        }
-        v[j] = acc + (b_in ? b_in[o] : 0.f);
+    for (int k = 0; k < LDIM; k++) {
+        const uint2 wv = __ldg(reinterpret_cast<const uint2*>(w_in_t + (long long)k * D_MODEL + i * 4));
+        const float z = xs[k];
+        v[0] = fmaf(__uint_as_float(wv.x << 16), z, v[0]); v[1] = fmaf(__uint_as_float(wv.x & 0xffff0000u), z, v[1]);
+        v[2] = fmaf(__uint_as_float(wv.y << 16), z, v[2]); v[3] = fmaf(__uint_as_float(wv.y & 0xffff0000u), z, v[3]);
     }
+    if (b_in) { const float4 b = *reinterpret_cast<const float4*>(b_in + i * 4); v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w; }
     *reinterpret_cast<float4*>(h + (long long)r * D_MODEL + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
     const float s1 = warp_sum(v[0] + v[1] + v[2] + v[3]);
     if (lane == 0) red[0][warp] = s1;

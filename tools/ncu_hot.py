@@ -5,8 +5,8 @@ import subprocess
 import sys
 
 
-def main(path, top=25):
-    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+def main(path, top=25, skip=0):
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--launch-skip", str(skip), "--launch-count", "1"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]
     isrc, isamp = hdr.index("Source"), hdr.index("# Samples")
@@ -25,10 +25,10 @@ def main(path, top=25):
             st = sorted(((int(r[i]) if r[i].isdigit() else 0, h) for i, h in stall_cols), reverse=True)[:2]
             data.append((n, r[isrc][:110], st))
     data.sort(reverse=True)
-    print(f"# {path}: total samples {total}")
+    print(f"# {path} (launch {skip}: {rows[0][1][:60]}): total samples {total}")
     for n, src, st in data[:top]:
         print(f"{n:7d} {100.0 * n / max(total, 1):5.1f}%  {src:110s} {st[0][1]}={st[0][0]} {st[1][1]}={st[1][0]}")
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 25)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 25, int(sys.argv[3]) if len(sys.argv) > 3 else 0)
