@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include <cuda.h>
+#include <cstring>
 #include <algorithm>
 #include <map>
 #include <tuple>
@@ -337,6 +338,14 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr) : "memory");
+    if (p.prefetch && warp == 0 && lane == 0 && (int)blockIdx.x < total_tiles) {
+        // Decode-sized GEMMs read their weights cold from HBM (the KV stream has flushed L2) and the smem ring alone cannot cover
+        // DRAM latency x bandwidth: ask L2 for this CTA's whole weight stream now. Weights do not depend on the previous kernel, so
+        // under programmatic dependent launch this overlaps the predecessor's tail.
+        const int work = blockIdx.x, split = work % p.splits, tile_n = (work / p.splits) % tiles_n;
+        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; kb++) tma_prefetch_3d(&tmW, 0, tile_n * BN, kb);
+    }
     pdl_wait();                                                // barriers/TMEM are set up; now wait for the producer kernel's data
 
     if (warp == 0) {
@@ -357,11 +366,6 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
                     mbar_expect_tx(full0 + 8 * s, bytes);
                     tma_load_3d(sA + s * Cfg::A_BYTES, &tmA, full0 + 8 * s, c0, t0 + tap, slot);
                     tma_load_3d(sW + s * Cfg::W_BYTES, &tmW, full0 + 8 * s, 0, tile_n * BN, kb);
-                    if (p.prefetch && work == (int)blockIdx.x && kb == min(kb1, kb0 + STAGES) - 1) {
-                        // Decode-sized GEMMs read their weights cold from HBM (the KV stream has flushed L2) and the smem ring alone
-                        // cannot cover DRAM latency x bandwidth: once the ring is full, ask L2 for the rest of this CTA's weight stream.
-                        for (int kp = kb + 1; kp < kb1; kp++) tma_prefetch_3d(&tmW, 0, tile_n * BN, kp);
-                    }
                 }
             }
         }
@@ -574,14 +578,25 @@ inline TcGeom tc_geometry(int R, int K, const RowMap& amap, int a_rps) {
 // Tile width and split-K factor.
 // Small-M GEMMs (decode: R = utterances in flight, at most a few M tiles) cannot fill 148 SMs with output tiles alone and are
 // bounded by fixed latencies, so the choice is made with a small cost model (microseconds):
-//   GEMM    ~ 3 + CTAs-per-SM x bytes one CTA streams / (100 KB/us per SM)       (TMA ingest per SM, launch + pipeline fill)
+//   GEMM    ~ 3 + CTAs-per-SM x bytes one CTA streams / (50 KB/us per SM)        (cold TMA ingest per SM, launch + pipeline fill)
 //   reduce  ~ 4 + splits x R x N x 4 B / (3 MB/us)   when split (a second kernel; it also does a fused LayerNorm for free)
 //   + 4.5 when a LayerNorm was requested but cannot be fused (no split)
-// Calibrated on the ncu launch lists in profiles/ (r1_v7): e.g. FlowLM in_proj 128x4 splits = 11.6 + 8.3 us vs model 13.6.
+// Calibrated on the ncu launch lists in profiles/ and on whole-step sweeps with PTTS_B200_PLAN (the step time moves by < 1 % over
+// all sensible choices: these GEMMs are bounded by per-kernel fixed costs, not by the tile shape).
 struct TcPlan { int bn; int splits; };
 inline TcPlan tc_plan(int tiles_m, int R, int N, int K, int num_sms, bool want_ln) {
     TcPlan best{0, 1};
     const int num_kb = K / 64;
+    // tuning hook: PTTS_B200_PLAN="NxK=BNxSPLITS;..." overrides the choice for small-M GEMMs of that shape
+    if (tiles_m <= 4) {
+        if (const char* ov = getenv("PTTS_B200_PLAN")) {
+            char key[64]; snprintf(key, sizeof key, "%dx%d=", N, K);
+            if (const char* q = strstr(ov, key)) {
+                int bn = 0, sp = 0;
+                if (sscanf(q + strlen(key), "%dx%d", &bn, &sp) == 2 && (bn == 32 || bn == 64 || bn == 128) && N % bn == 0 && sp >= 1 && sp <= 16) return TcPlan{bn, sp};
+            }
+        }
+    }
     if (tiles_m <= 4) {
         double best_cost = 1e30;
         for (int bn : {128, 64, 32}) {
@@ -592,7 +607,7 @@ inline TcPlan tc_plan(int tiles_m, int R, int N, int K, int num_sms, bool want_l
                 if (sp > 1 && (kbps < 4 || (size_t)sp * R * N > ((size_t)32 << 20))) continue;
                 const int ctas = tiles * ((num_kb + kbps - 1) / kbps);
                 const double per_sm = (double)((ctas + num_sms - 1) / num_sms) * kbps * (16.0 + bn / 8.0);      // KB
-                double cost = 3.0 + per_sm / 100.0;
+                double cost = 3.0 + per_sm / 50.0;
                 if (sp > 1) cost += 4.0 + (double)sp * R * N * 4.0 / 3.0e6;
                 else if (want_ln) cost += 4.5;
                 if (cost < best_cost) { best_cost = cost; best = TcPlan{bn, sp}; }
