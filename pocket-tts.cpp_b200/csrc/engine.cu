@@ -287,8 +287,8 @@ struct b200_engine {
             Epi e; e.mode = EPI_MIMI_QKV; e.row_slot = mrow_slot; e.row_pos = mrow_pos; e.cs = mcs; e.kv_slot_stride = mkv_slot_stride;
             e.kcache = mkc + l * mkv_layer_stride; e.vcache = mvc + l * mkv_layer_stride; e.q_out_bf16 = mq_bf;
             lin(mn_bf, L.in_proj, R, e);
-            if (cfg.gemm_path == 0) launch_k(pdl_active, attn_mimi_mma_kernel, dim3((n * M_HEADS + 3) / 4), dim3(128), (size_t)0, stream, mq_bf, (const __nv_bfloat16*)e.kcache,
-                                             (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, n, mimi_off, cfg.mimi_mask_mode, matt_bf);
+            if (cfg.gemm_path == 0) launch_k(pdl_active, attn_mimi_mma4_kernel, dim3(n * M_HEADS), dim3(128), (size_t)0, stream, (const __nv_bfloat16*)mq_bf, (const __nv_bfloat16*)e.kcache,
+                                             (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, (const int*)mimi_off, cfg.mimi_mask_mode, matt_bf);
             else launch_k(pdl_active, attn_mimi_kernel, dim3(n, M_HEADS), dim3(256), (size_t)(AM_SMEM), stream, mq_bf, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, mimi_off, cfg.mimi_mask_mode, matt_bf);
             Epi eo; eo.colscale = L.ls1; eo.resid = x; eo.resid_map = rows(M_DIM); eo.out = x; eo.out_map = rows(M_DIM);
             lin(matt_bf, L.out_proj, R, eo);
@@ -662,7 +662,7 @@ int b200_finalize_weights(b200_engine* e) {
                             (const void*)layernorm_kernel<D_FLOW>, (const void*)gemm_tc_kernel<32>, (const void*)gemm_tc_kernel<64>, (const void*)gemm_tc_kernel<128>,
                             (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
                             (const void*)attn_flow_split_kernel, (const void*)attn_flow_merge_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
-                            (const void*)step_logic_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma_kernel, (const void*)cast_f16_kernel,
+                            (const void*)step_logic_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma_kernel, (const void*)attn_mimi_mma4_kernel, (const void*)cast_f16_kernel,
                             (const void*)conv_n1_kernel, (const void*)shift_states_kernel};
         for (const void* k : ks) PTTS_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }

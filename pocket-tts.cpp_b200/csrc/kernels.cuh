@@ -584,6 +584,157 @@ __global__ void __launch_bounds__(128) attn_mimi_mma_kernel(const __nv_bfloat16*
 }
 
 // ------------------------------------------------------------------------------------------------
+// Mimi ring attention, four warps per (slot, head): warp w owns ring slots 64w .. 64w+63 (eight key tiles). Same fragment tricks as
+// attn_mimi_mma_kernel, but K is read ONCE: the warp's 16 x 64 scores stay in registers while the row max / sum are combined across
+// the four warps through shared memory, then P (normalised, rounded to bf16 like ggml's bf16 mul_mat operand) x V for the warp's own
+// keys and a fixed-order (deterministic) sum of the four partial outputs. 4x more warps in flight than the one-warp version, which
+// left ~14 warps per SM to hide HBM latency (74 us per layer at 256 slots for 131 MB of K/V).
+// ------------------------------------------------------------------------------------------------
+constexpr int AM4_LD = 68;                                   // padded row of the partial-output buffers (floats)
+
+__global__ void __launch_bounds__(128) attn_mimi_mma4_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
+                                                             const __nv_bfloat16* __restrict__ vc, long long kv_slot_stride, int slot0,
+                                                             const int* __restrict__ mimi_off, int mask_mode, __nv_bfloat16* __restrict__ out) {
+    pdl_prologue();
+    __shared__ float s_max[4][16], s_sum[4][16];
+    __shared__ __align__(16) float s_o[3][16][AM4_LD];          // partial outputs of warps 1..3
+    const int b = blockIdx.x / M_HEADS, h = blockIdx.x % M_HEADS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int slot = slot0 + b;
+    const int offset = mimi_off[slot];
+    const __nv_bfloat16* K = kc + (long long)slot * kv_slot_stride + h * D_HEAD;
+    const __nv_bfloat16* V = vc + (long long)slot * kv_slot_stride + h * D_HEAD;
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(q + ((long long)b * M_T + g) * M_DIM + h * D_HEAD + 32 * p + 8 * t);
+        const uint4 hi = *reinterpret_cast<const uint4*>(q + ((long long)b * M_T + g + 8) * M_DIM + h * D_HEAD + 32 * p + 8 * t);
+        qa[2 * p][0] = lo.x; qa[2 * p][1] = hi.x; qa[2 * p][2] = lo.y; qa[2 * p][3] = hi.y;
+        qa[2 * p + 1][0] = lo.z; qa[2 * p + 1][1] = hi.z; qa[2 * p + 1][2] = lo.w; qa[2 * p + 1][3] = hi.w;
+    }
+    const MimiMaskRow mr0 = mimi_mask_row(offset, g), mr1 = mimi_mask_row(offset, g + 8);
+    // ---- scores of this warp's 8 key tiles (kept in registers) ----
+    float S[8][4];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        uint4 kv[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int krow = min(64 * warp + 8 * (4 * half + u) + g, M_CTX - 1);        // keys 250..255 do not exist: clamp, mask below
+            const __nv_bfloat16* kr = K + (long long)krow * M_DIM + 8 * t;
+            kv[u][0] = *reinterpret_cast<const uint4*>(kr);
+            kv[u][1] = *reinterpret_cast<const uint4*>(kr + 32);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float (&sc)[4] = S[4 * half + u];
+            sc[0] = sc[1] = sc[2] = sc[3] = 0.f;
+            mma_bf16_16816(sc, qa[0], kv[u][0].x, kv[u][0].y);
+            mma_bf16_16816(sc, qa[1], kv[u][0].z, kv[u][0].w);
+            mma_bf16_16816(sc, qa[2], kv[u][1].x, kv[u][1].y);
+            mma_bf16_16816(sc, qa[3], kv[u][1].z, kv[u][1].w);
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int c = 64 * warp + 8 * (4 * half + u) + 2 * t + e;
+                bool m0, m1;
+                if (mask_mode == 0) { m0 = mimi_masked_fast(mr0, c); m1 = mimi_masked_fast(mr1, c); }
+                else { m0 = c >= M_CTX || mimi_masked(offset, g, c, mask_mode); m1 = c >= M_CTX || mimi_masked(offset, g + 8, c, mask_mode); }
+                sc[e] = m0 ? -INFINITY : sc[e] * 0.125f;
+                sc[2 + e] = m1 ? -INFINITY : sc[2 + e] * 0.125f;
+            }
+        }
+    }
+    // ---- row max over all 250 keys ----
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { mx0 = fmaxf(mx0, fmaxf(S[j][0], S[j][1])); mx1 = fmaxf(mx1, fmaxf(S[j][2], S[j][3])); }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    if (t == 0) { s_max[warp][g] = mx0; s_max[warp][g + 8] = mx1; }
+    __syncthreads();
+    mx0 = fmaxf(fmaxf(s_max[0][g], s_max[1][g]), fmaxf(s_max[2][g], s_max[3][g]));
+    mx1 = fmaxf(fmaxf(s_max[0][g + 8], s_max[1][g + 8]), fmaxf(s_max[2][g + 8], s_max[3][g + 8]));
+    // ---- exp and row sums (every row has at least its own position unmasked, so the max is finite) ----
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        S[j][0] = expf(S[j][0] - mx0); S[j][1] = expf(S[j][1] - mx0); S[j][2] = expf(S[j][2] - mx1); S[j][3] = expf(S[j][3] - mx1);
+        l0 += S[j][0] + S[j][1]; l1 += S[j][2] + S[j][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    if (t == 0) { s_sum[warp][g] = l0; s_sum[warp][g + 8] = l1; }
+    __syncthreads();
+    const float inv0 = 1.0f / (((s_sum[0][g] + s_sum[1][g]) + s_sum[2][g]) + s_sum[3][g]);
+    const float inv1 = 1.0f / (((s_sum[0][g + 8] + s_sum[1][g + 8]) + s_sum[2][g + 8]) + s_sum[3][g + 8]);
+    // ---- O_w = P_w V_w over this warp's 64 keys ----
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; n++) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+#pragma unroll
+    for (int s4 = 0; s4 < 4; s4++) {
+        uint32_t pa[4];
+        {
+            __nv_bfloat162 x;
+            x = __floats2bfloat162_rn(S[2 * s4][0] * inv0, S[2 * s4][1] * inv0); pa[0] = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2bfloat162_rn(S[2 * s4][2] * inv1, S[2 * s4][3] * inv1); pa[1] = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2bfloat162_rn(S[2 * s4 + 1][0] * inv0, S[2 * s4 + 1][1] * inv0); pa[2] = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2bfloat162_rn(S[2 * s4 + 1][2] * inv1, S[2 * s4 + 1][3] * inv1); pa[3] = *reinterpret_cast<uint32_t*>(&x);
+        }
+        const int k0 = 64 * warp + 16 * s4 + 2 * t;
+        const uint4 v0 = *reinterpret_cast<const uint4*>(V + (long long)min(k0, M_CTX - 1) * M_DIM + 8 * g);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(V + (long long)min(k0 + 1, M_CTX - 1) * M_DIM + 8 * g);
+        const uint4 v2 = *reinterpret_cast<const uint4*>(V + (long long)min(k0 + 8, M_CTX - 1) * M_DIM + 8 * g);
+        const uint4 v3 = *reinterpret_cast<const uint4*>(V + (long long)min(k0 + 9, M_CTX - 1) * M_DIM + 8 * g);
+        const uint32_t a0[4] = {v0.x, v0.y, v0.z, v0.w}, a1[4] = {v1.x, v1.y, v1.z, v1.w}, a2[4] = {v2.x, v2.y, v2.z, v2.w}, a3[4] = {v3.x, v3.y, v3.z, v3.w};
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const uint32_t b0_lo = __byte_perm(a0[w], a1[w], 0x5410), b1_lo = __byte_perm(a2[w], a3[w], 0x5410);
+            const uint32_t b0_hi = __byte_perm(a0[w], a1[w], 0x7632), b1_hi = __byte_perm(a2[w], a3[w], 0x7632);
+            mma_bf16_16816(o[2 * w], pa, b0_lo, b1_lo);
+            mma_bf16_16816(o[2 * w + 1], pa, b0_hi, b1_hi);
+        }
+    }
+    // ---- fixed-order sum of the four partial outputs: warps 1..3 publish, warp 0 adds them to its own (0 + 1 + 2 + 3) ----
+    // o[n][e] = O[g][8(2t+e) + n], o[n][2+e] = O[g+8][...]: the lane owns dims 16t .. 16t+15 of rows g and g+8
+    if (warp > 0) {
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                float* dst = &s_o[warp - 1][g + 8 * r][16 * t + 8 * e];
+                *reinterpret_cast<float4*>(dst) = make_float4(o[0][2 * r + e], o[1][2 * r + e], o[2][2 * r + e], o[3][2 * r + e]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4][2 * r + e], o[5][2 * r + e], o[6][2 * r + e], o[7][2 * r + e]);
+            }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            __nv_bfloat162 pk[8];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                float acc[8];
+#pragma unroll
+                for (int n = 0; n < 8; n++) acc[n] = o[n][2 * r + e];
+#pragma unroll
+                for (int w = 0; w < 3; w++) {
+                    const float* src = &s_o[w][g + 8 * r][16 * t + 8 * e];
+                    const float4 x = *reinterpret_cast<const float4*>(src), y = *reinterpret_cast<const float4*>(src + 4);
+                    acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w; acc[4] += y.x; acc[5] += y.y; acc[6] += y.z; acc[7] += y.w;
+                }
+#pragma unroll
+                for (int n = 0; n < 8; n += 2) pk[e * 4 + n / 2] = __floats2bfloat162_rn(acc[n], acc[n + 1]);
+            }
+            __nv_bfloat16* dst = out + ((long long)b * M_T + g + 8 * r) * M_DIM + h * D_HEAD + 16 * t;
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(&pk[0]);
+            *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<uint4*>(&pk[4]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Flow head glue
 // ------------------------------------------------------------------------------------------------
 // c = LN(h; out_norm) (bf16 copy for cond_embed) and EOS logit = out_eos(bf16(c)) + bias + 4
