@@ -67,15 +67,16 @@ __device__ __forceinline__ float warp_max(float v) {
 //
 // ggml_gelu on CPU: tanh form through an f16 table (input and output rounded to f16); reference
 // modules/transformer.h:271, modules/mimi_transformer.h:959 + SURVEY.md Appendix C.
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// tanh.approx (one MUFU op, relative error ~2^-11) saturates to +-1 for large |u|, which reproduces ggml's x <= -10 -> 0 and
+// x >= 10 -> x special cases up to the final f16 rounding; the result is rounded to f16 and then to bf16 (the next GEMM operand).
 __device__ __forceinline__ float gelu_ggml(float x) {
-    if (x <= -10.0f) return 0.0f;
-    if (x >= 10.0f) return x;
     const float xf = __half2float(__float2half_rn(x));
-    const float u = 0.79788456080286535587989211986876f * xf * (1.0f + 0.044715f * xf * xf);
-    const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));          // tanh(u)
-    return __half2float(__float2half_rn(0.5f * xf * (1.0f + t)));
+    const float u = 0.79788456080286535587989211986876f * xf * fmaf(0.044715f * xf, xf, 1.0f);
+    const float hx = 0.5f * xf;
+    return __half2float(__float2half_rn(fmaf(hx, tanh_fast(u), hx)));
 }
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { const float hx = 0.5f * x; return fmaf(hx, tanh_fast(hx), hx); }   // x * sigmoid(x)
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
 __device__ __forceinline__ float apply_act(float v, int act) {
     switch (act) {

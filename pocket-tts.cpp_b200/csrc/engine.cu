@@ -659,7 +659,7 @@ int b200_finalize_weights(b200_engine* e) {
     {
         const void* ks[] = {(const void*)prepare_step_kernel, (const void*)rope_table_kernel, (const void*)gemm_ffma_kernel<__nv_bfloat16>, (const void*)gemm_ffma_kernel<__half>,
                             (const void*)gemv_small_kernel<__nv_bfloat16, 8>, (const void*)gemv_small_kernel<__half, 8>, (const void*)layernorm_kernel<D_MODEL>,
-                            (const void*)layernorm_kernel<D_FLOW>, (const void*)gemm_tc_kernel<32>, (const void*)gemm_tc_kernel<64>, (const void*)gemm_tc_kernel<128>,
+                            (const void*)layernorm_kernel<D_FLOW>, 
                             (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
                             (const void*)attn_flow_split_kernel, (const void*)attn_flow_merge_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
                             (const void*)step_logic_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma_kernel, (const void*)attn_mimi_mma4_kernel, (const void*)cast_f16_kernel,

@@ -232,8 +232,8 @@ __device__ __forceinline__ void epi_chunk(const Epi& e, const float* stg, const 
 }
 
 // ---- QKV epilogue for 32 consecutive columns (= half a head): RoPE with vector loads/stores (see epi_apply for the math) ----
+template <bool mimi>
 __device__ __forceinline__ void epi_qkv32(const Epi& e, int row, int col0, float (&v)[32]) {
-    const bool mimi = (e.mode == EPI_MIMI_QKV);
     const int D = mimi ? M_DIM : D_MODEL;
     if (e.bias) {
 #pragma unroll
@@ -302,10 +302,14 @@ struct TcCfg {
 
 // Persistent: CTA b processes tiles b, b + gridDim.x, ... (tile = tile_m * tiles_n + tile_n). The accumulator is double
 // buffered in TMEM so the epilogue of tile i overlaps the TMA/MMA of tile i+1.
-template <int BN>
+// CLS > 0: generic epilogue class EPI_CLASSES[CLS]; CLS == -1: FlowLM QKV epilogue; CLS == -2: Mimi QKV epilogue. One instantiation per
+// (BN, CLS) keeps each kernel's code small: with a runtime switch over all classes the kernel was 160 KB of SASS and the epilogue
+// warps' top stall was instruction fetch (ncu r1_v11: stalled_no_instruction 2.2 per issue).
+template <int BN, int CLS>
 __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                                          const TcParams p, const Epi epi) {
     using Cfg = TcCfg<BN>;
+    constexpr bool GEN = CLS > 0;
     const int STAGES = p.stages;
     pdl_trigger();                                             // the next kernel may start its prologue now
     extern __shared__ uint8_t smem_raw[];
@@ -410,7 +414,7 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
             const int ri = ew * 32 + lane;
             const int row = row_base + ri;
             const bool live = ri < nvalid;
-            if (epi.mode == EPI_GENERIC) {
+            if constexpr (GEN) {
                 rowinfo[lane] = make_int2(row / epi.rps, row % epi.rps);
                 __syncwarp();
             }
@@ -421,32 +425,16 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
             for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 float v[32];
                 tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * BN + c0), v);
-                if (epi.mode == EPI_GENERIC) {
+                if constexpr (GEN) {
                     float4* sp = reinterpret_cast<float4*>(stg + lane * EPI_STG_LD);
 #pragma unroll
                     for (int j = 0; j < 8; j++) sp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     __syncwarp();
                     const int col = tile_n * BN + c0 + cq, rows_left = nvalid - ew * 32, tile_row0 = row_base + ew * 32;
-                    switch (p.epi_class) {
-                        case 1: epi_chunk<EPI_CLASSES[1]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 2: epi_chunk<EPI_CLASSES[2]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 3: epi_chunk<EPI_CLASSES[3]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 4: epi_chunk<EPI_CLASSES[4]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 5: epi_chunk<EPI_CLASSES[5]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 6: epi_chunk<EPI_CLASSES[6]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 7: epi_chunk<EPI_CLASSES[7]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 8: epi_chunk<EPI_CLASSES[8]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 9: epi_chunk<EPI_CLASSES[9]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 10: epi_chunk<EPI_CLASSES[10]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 11: epi_chunk<EPI_CLASSES[11]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 12: epi_chunk<EPI_CLASSES[12]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 13: epi_chunk<EPI_CLASSES[13]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        case 14: epi_chunk<EPI_CLASSES[14]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off); break;
-                        default: break;                        // class 0 never reaches this kernel (tc_gemm_supported)
-                    }
+                    epi_chunk<EPI_CLASSES[GEN ? CLS : 0]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off);
                     __syncwarp();                                  // the staging tile is overwritten by the next chunk
-                } else if (live) {
-                    epi_qkv32(epi, row, tile_n * BN + c0, v);
+                } else {
+                    if (live) epi_qkv32<CLS == -2>(epi, row, tile_n * BN + c0, v);
                 }
             }
             tc_fence_before();
@@ -458,6 +446,31 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
 }
+
+using TcKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const TcParams, const Epi);
+template <int BN>
+inline TcKernelFn tc_kernel_for(int cls) {
+    switch (cls) {
+        case -2: return gemm_tc_kernel<BN, -2>;
+        case -1: return gemm_tc_kernel<BN, -1>;
+        case 1: return gemm_tc_kernel<BN, 1>;
+        case 2: return gemm_tc_kernel<BN, 2>;
+        case 3: return gemm_tc_kernel<BN, 3>;
+        case 4: return gemm_tc_kernel<BN, 4>;
+        case 5: return gemm_tc_kernel<BN, 5>;
+        case 6: return gemm_tc_kernel<BN, 6>;
+        case 7: return gemm_tc_kernel<BN, 7>;
+        case 8: return gemm_tc_kernel<BN, 8>;
+        case 9: return gemm_tc_kernel<BN, 9>;
+        case 10: return gemm_tc_kernel<BN, 10>;
+        case 11: return gemm_tc_kernel<BN, 11>;
+        case 12: return gemm_tc_kernel<BN, 12>;
+        case 13: return gemm_tc_kernel<BN, 13>;
+        case 14: return gemm_tc_kernel<BN, 14>;
+        default: return nullptr;
+    }
+}
+inline TcKernelFn tc_kernel(int bn, int cls) { return bn == 128 ? tc_kernel_for<128>(cls) : bn == 64 ? tc_kernel_for<64>(cls) : tc_kernel_for<32>(cls); }
 
 // Deterministic split-K reduction: sums the partial planes in a fixed order and applies the real epilogue.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long plane, int R, int N, const Epi epi) {
@@ -537,7 +550,6 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 struct TcPlanCache {
     PFN_tmapEncodeTiled encode = nullptr;
     std::map<std::tuple<const void*, long long, long long, long long, long long, int, int>, CUtensorMap> maps;
-    bool attr_set[3] = {false, false, false};
     int num_sms = 148;
     bool w_kb_major = true;     // PTTS_B200_WLAYOUT=0: keep tensor-core weights row-major (layout experiment)
     bool pdl = false;
@@ -549,6 +561,16 @@ inline TcPlanCache* tc_plan_cache_create() {
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) c->encode = (PFN_tmapEncodeTiled)fn;
     if (const char* v = getenv("PTTS_B200_WLAYOUT")) c->w_kb_major = atoi(v) != 0;
+    // every (tile width, epilogue class) instantiation: opt in to the large dynamic smem and the uniform carve-out (see engine.cu)
+    for (int bn : {128, 64, 32}) {
+        const int st1 = bn == 128 ? TcCfg<128>::STAGES_1CTA : bn == 64 ? TcCfg<64>::STAGES_1CTA : TcCfg<32>::STAGES_1CTA;
+        for (int cls = -2; cls < EPI_NCLASSES; cls++) {
+            TcKernelFn k = tc_kernel(bn, cls);
+            if (!k) continue;
+            PTTS_CUDA_CHECK(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, st1 * (128 * 128 + bn * 128) + EPI_SMEM + 1024 + 256));
+            PTTS_CUDA_CHECK(cudaFuncSetAttribute((const void*)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
+    }
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) c->num_sms = sms;
     return c;
@@ -700,17 +722,15 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     p.idesc = (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int total_tiles = tiles * splits;
     dim3 grid(std::min(total_tiles, 2 * c->num_sms));
-    const int bi = bn == 128 ? 0 : (bn == 64 ? 1 : 2);
     const bool one_cta = total_tiles <= c->num_sms;             // at most one CTA per SM anyway: spend the whole smem on a deeper ring
-    auto launch = [&](auto kern, auto cfgtag) {
-        using Cfg = decltype(cfgtag);
-        if (!c->attr_set[bi]) { PTTS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(Cfg::STAGES_1CTA))); c->attr_set[bi] = true; }
-        p.stages = one_cta ? Cfg::STAGES_1CTA : Cfg::STAGES_2CTA;
-        launch_k(c->pdl, kern, grid, dim3(320), (size_t)Cfg::smem_bytes(p.stages), stream, *ta, *tw, p, kepi);
-    };
-    if (bn == 128) launch(gemm_tc_kernel<128>, TcCfg<128>{});
-    else if (bn == 64) launch(gemm_tc_kernel<64>, TcCfg<64>{});
-    else launch(gemm_tc_kernel<32>, TcCfg<32>{});
+    const int cls = kepi.mode == EPI_GENERIC ? p.epi_class : (kepi.mode == EPI_MIMI_QKV ? -2 : -1);
+    TcKernelFn kern = tc_kernel(bn, cls);
+    if (!kern) { fprintf(stderr, "ptts_b200: no tensor-core kernel for epilogue class %d\n", cls); abort(); }
+    const int st1 = bn == 128 ? TcCfg<128>::STAGES_1CTA : bn == 64 ? TcCfg<64>::STAGES_1CTA : TcCfg<32>::STAGES_1CTA;
+    const int st2 = bn == 128 ? TcCfg<128>::STAGES_2CTA : bn == 64 ? TcCfg<64>::STAGES_2CTA : TcCfg<32>::STAGES_2CTA;
+    const int stage_bytes = 128 * 128 + bn * 128;
+    p.stages = one_cta ? st1 : st2;
+    launch_k(c->pdl, kern, grid, dim3(320), (size_t)(p.stages * stage_bytes + EPI_SMEM + 1024 + 256), stream, *ta, *tw, p, kepi);
     if (ln_done) *ln_done = false;
     if (splits > 1) {
         if (ln_ok) {
