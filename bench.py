@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--gemm-path", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=1)
     ap.add_argument("--cuda-graphs", type=int, default=1)
+    ap.add_argument("--overlap", type=int, default=1, help="two-stream pipeline: Mimi(t) overlaps FlowLM(t+1)")
     ap.add_argument("--ref-frames-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -185,7 +186,7 @@ def main():
     d = default_model_dir(eos_mode="never", t_voice=args.t_voice, voices=["cosette"])
 
     B = args.batch
-    ctx = P.Context(d, device=local, max_slots=B, max_voices=1, kv_capacity=args.kv_capacity, kv_f32=args.kv_f32, gemm_path=args.gemm_path, pdl=args.pdl, cuda_graphs=args.cuda_graphs)
+    ctx = P.Context(d, device=local, max_slots=B, max_voices=1, kv_capacity=args.kv_capacity, kv_f32=args.kv_f32, gemm_path=args.gemm_path, pdl=args.pdl, cuda_graphs=args.cuda_graphs, overlap=args.overlap)
     eng = ctx.engine
     st = ctx.stream("cosette", temp=0.7)            # prefill of the (long) voice prefix
     # this rank's utterance slice: global utterance id = rank * B + i
@@ -211,6 +212,7 @@ def main():
     steps_done = 0
     for _ in range(args.untimed):
         eng.step_enqueue(0, B); steps_done += 1
+    eng.join()
     eng.sync()
     barrier()
     l0 = eng.launch_count()
@@ -223,6 +225,7 @@ def main():
     e0.record(ext)
     for _ in range(args.steps):
         eng.step_enqueue(0, B)
+    eng.join()                                       # the Mimi stream's last frame is inside the timed region
     e1.record(ext)
     eng.sync()
     if ncu_range:

@@ -39,6 +39,7 @@ typedef struct b200_config {
     int max_prefill_rows; /* rows per prefill chunk (0 = default 512)                                               */
     int cuda_graphs;      /* 1 = replay the per-frame step as a CUDA graph (captured on second use of a shape)       */
     int pdl;              /* 1 = programmatic dependent launch: each kernel's prologue overlaps its predecessor's tail  */
+    int overlap;          /* 1 = two-stream pipeline: the Mimi decode of frame t overlaps the FlowLM step of frame t+1   */
 } b200_config;
 
 B200_API void b200_default_config(b200_config* cfg);
@@ -82,6 +83,8 @@ B200_API int  b200_step(b200_engine* e, int slot0, int n, const float* noise, fl
  * engine's device buffers (b200_device_ptr). */
 B200_API int  b200_step_enqueue(b200_engine* e, int slot0, int n, int use_injected_noise);
 B200_API int  b200_sync(b200_engine* e);
+/* main stream waits for the Mimi stream: an event recorded on b200_stream() afterwards covers all enqueued frames incl. PCM */
+B200_API int  b200_join(b200_engine* e);
 
 /* Mimi-only path (BASELINE config 3): decode caller-provided latents [n][32] for slots [slot0, slot0+n). */
 B200_API int  b200_mimi_reset(b200_engine* e, int slot0, int n);

@@ -22,7 +22,7 @@ LDIM = 32
 class B200Config(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("max_slots", ctypes.c_int), ("max_voices", ctypes.c_int), ("kv_capacity", ctypes.c_int),
                 ("kv_f32", ctypes.c_int), ("mimi_mask_mode", ctypes.c_int), ("convt_split", ctypes.c_int), ("gemm_path", ctypes.c_int),
-                ("max_prefill_rows", ctypes.c_int), ("cuda_graphs", ctypes.c_int), ("pdl", ctypes.c_int)]
+                ("max_prefill_rows", ctypes.c_int), ("cuda_graphs", ctypes.c_int), ("pdl", ctypes.c_int), ("overlap", ctypes.c_int)]
 
 
 _lib = None
@@ -58,6 +58,7 @@ def lib():
         "b200_step": (ci, [vp, ci, ci, fp, fp, ip, fp, fp]),
         "b200_step_enqueue": (ci, [vp, ci, ci, ci]),
         "b200_sync": (ci, [vp]),
+        "b200_join": (ci, [vp]),
         "b200_mimi_reset": (ci, [vp, ci, ci]),
         "b200_mimi_decode": (ci, [vp, ci, ci, fp, fp]),
         "b200_mimi_decode_enqueue": (ci, [vp, ci, ci]),
@@ -121,7 +122,7 @@ def _ip(a):
 def default_config(**kw) -> B200Config:
     cfg = B200Config()
     lib().b200_default_config(ctypes.byref(cfg))
-    for k in ("pdl", "cuda_graphs", "gemm_path", "kv_f32"):          # environment overrides, like ptts_init (host_api.cpp)
+    for k in ("pdl", "cuda_graphs", "gemm_path", "kv_f32", "overlap"):          # environment overrides, like ptts_init (host_api.cpp)
         v = os.environ.get("PTTS_B200_" + k.upper())
         if v not in (None, ""):
             setattr(cfg, k, int(v))
@@ -188,6 +189,10 @@ class Engine:
 
     def sync(self):
         self.L.b200_sync(self.h)
+
+    def join(self):
+        """Main stream waits for the Mimi stream: an event recorded on stream_handle() afterwards covers every enqueued frame."""
+        self.L.b200_join(self.h)
 
     def mimi_reset(self, slot0, n):
         assert self.L.b200_mimi_reset(self.h, slot0, n) == 0

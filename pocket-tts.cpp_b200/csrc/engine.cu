@@ -33,6 +33,13 @@ struct ConvW { __half* w = nullptr; __half* wk = nullptr; float* b = nullptr; in
 struct b200_engine {
     b200_config cfg{};
     cudaStream_t stream = nullptr;
+    // Two-stream pipeline: the Mimi decode of frame t (tensor/ALU bound) runs on stream_m while the FlowLM step of frame t+1 (latency
+    // bound small GEMMs + the HBM-bound KV stream) runs on the main stream. Hand-off buffer mx2[t & 1], events per parity.
+    cudaStream_t stream_m = nullptr;
+    cudaEvent_t ev_main[2] = {nullptr, nullptr}, ev_mimi[2] = {nullptr, nullptr};
+    bool ev_mimi_valid[2] = {false, false};
+    unsigned long long pipe_t = 0;       // frames enqueued through the pipeline
+    bool mimi_pending = false;           // stream_m holds work the main stream has not waited for
     std::map<std::string, HostTensor> host;
     std::vector<void*> allocs;
     bool finalized = false;
@@ -84,7 +91,7 @@ struct b200_engine {
     float *eos = nullptr, *ycond = nullptr, *mod = nullptr, *xh = nullptr, *noise_f32 = nullptr, *noise_inj = nullptr, *latent = nullptr;
     int* produced = nullptr; float* eos_out = nullptr;
     // Mimi
-    float* mx = nullptr; __nv_bfloat16 *mn_bf = nullptr, *mq_bf = nullptr, *matt_bf = nullptr, *mff_bf = nullptr;
+    float* mx = nullptr; float* mx2[2] = {nullptr, nullptr}; __nv_bfloat16 *mn_bf = nullptr, *mq_bf = nullptr, *matt_bf = nullptr, *mff_bf = nullptr;
     int *mrow_slot = nullptr, *mrow_pos = nullptr; float2* mcs = nullptr;
     __half *buf0 = nullptr, *buf2 = nullptr, *buf3a = nullptr, *buf3b = nullptr, *buf5 = nullptr, *buf6a = nullptr, *buf6b = nullptr,
            *buf8 = nullptr, *buf9a = nullptr, *buf9b = nullptr, *buf11 = nullptr;
@@ -275,11 +282,17 @@ struct b200_engine {
         launches += 2 + N_RES;
     }
 
-    // Mimi decoder for slots [slot0, slot0+n) from lat_f32 (reference models/mimi.h:85-104).
-    void mimi(int slot0, int n) {
+    // Mimi front end (latent -> 16 transformer input rows, written to `xbuf`), reference models/mimi.h:77-83 + modules/conv.h:283-331.
+    void mimi_front(int slot0, int n, float* xbuf) {
+        launch_k(pdl_active, mimi_front_kernel, dim3(n), dim3(M_DIM), (size_t)(0), stream, slot0, lat_f32, emb_std, emb_mean, wq, wup, bup, e_prev, xbuf);
+        launches++;
+    }
+    // Mimi decoder body for slots [slot0, slot0+n) from the front end's rows in `xbuf` (reference models/mimi.h:85-104).
+    void mimi(int slot0, int n, float* xbuf) {
         const int BIG = 1 << 30, R = n * M_T;
-        launch_k(pdl_active, mimi_front_kernel, dim3(n), dim3(M_DIM), (size_t)(0), stream, slot0, lat_f32, emb_std, emb_mean, wq, wup, bup, e_prev, mx);
-        float* x = mx + (long long)slot0 * M_T * M_DIM;
+        launch_k(pdl_active, prepare_mimi_kernel, dim3((n * M_T * 32 + 255) / 256), dim3(256), (size_t)(0), stream, slot0, n, (const int*)mimi_off, (const float*)freq_mimi, mrow_slot, mrow_pos, mcs);
+        launches++;
+        float* x = xbuf + (long long)slot0 * M_T * M_DIM;
         const int s_mtf = seg_begin(3);
         for (int l = 0; l < M_LAYERS; l++) {
             auto& L = ml[l];
@@ -347,18 +360,16 @@ struct b200_engine {
         seg_end(s_sea);
     }
 
-    void prepare_step(int slot0, int n) {
-        launch_k(pdl_active, prepare_step_kernel, dim3((n * M_T + 255) / 256), dim3(256), (size_t)(0), stream, slot0, n, cur_len, mimi_off, row_slot, row_pos, mrow_slot, mrow_pos);
-        launch_k(pdl_active, rope_table_kernel, dim3((n * 32 + 255) / 256), dim3(256), (size_t)(0), stream, row_pos, freq_flow, cs, n);
-        launch_k(pdl_active, rope_table_kernel, dim3((n * M_T * 32 + 255) / 256), dim3(256), (size_t)(0), stream, mrow_pos, freq_mimi, mcs, n * M_T);
-        launches += 3;
+    void prepare_flow(int slot0, int n) {
+        launch_k(pdl_active, prepare_flow_kernel, dim3((n * 32 + 255) / 256), dim3(256), (size_t)(0), stream, slot0, n, (const int*)cur_len, (const float*)freq_flow, row_slot, row_pos, cs);
+        launches++;
     }
 
     // One generation step for slots [slot0, slot0+n) (reference _stream_sentence_step, src/pocket_tts.cpp:446-492).
-    void step_enqueue(int slot0, int n, bool injected) {
-        const int s_all = seg_begin(5);
+    // FlowLM step + head + stop rule + Mimi front end (everything that consumes / produces the latent hand-off).
+    void flow_part(int slot0, int n, bool injected, float* xbuf) {
         set_pdl(pdl_small || pdl_chain);
-        prepare_step(slot0, n);
+        prepare_flow(slot0, n);
         const int s_flow = seg_begin(1);
         launch_k(pdl_active, flow_in_kernel, dim3(n), dim3(256), (size_t)0, stream, slot0, n, (const __nv_bfloat16*)lat_in_bf16, (const __nv_bfloat16*)input_linear_t,
                  (const float*)input_linear.b, (const float*)fl[0].n1w, (const float*)fl[0].n1b, h, n_bf);
@@ -373,21 +384,31 @@ struct b200_engine {
         launches += 2;
         seg_end(s_head);
         set_pdl(pdl_small);
-        mimi(slot0, n);
+        mimi_front(slot0, n, xbuf);
+    }
+    void step_enqueue(int slot0, int n, bool injected) {       // single-stream form (eager / profiling)
+        const int s_all = seg_begin(5);
+        flow_part(slot0, n, injected, mx);
+        mimi(slot0, n, mx);
         seg_end(s_all);
     }
 
-    // kind 0 = full generation step, 1 = Mimi-only decode
-    void run_graphed(int kind, int slot0, int n, bool injected) {
+    // kind 0 = full generation step (one stream), 1 = Mimi-only decode, 2 = FlowLM part -> mx2[par], 3 = Mimi body from mx2[par].
+    // Runs on the CURRENT `stream` member (run_step swaps in stream_m for kind 3).
+    void run_graphed(int kind, int slot0, int n, bool injected, int par = 0) {
         // PDL overlaps each kernel's prologue with its predecessor's tail: a large win when the step is launch/latency bound
-        // (batch 1), a small loss once kernels fill the machine and the step is replayed as a graph (measured at batch >= 16:
-        // 3.53 ms/step without vs 3.62 ms with PDL at batch 256).
+        // (batch 1), neutral once kernels fill the machine and the step is replayed as a graph.
         pdl_small = cfg.pdl >= 2 || (cfg.pdl == 1 && n <= 8);    // every kernel of the step
-        pdl_chain = cfg.pdl >= 2;                                 // (experiment) the chains of small kernels even at large batch: helps eager launches, hurts graph replay
+        pdl_chain = cfg.pdl >= 2;
         set_pdl(pdl_small);
-        auto body = [&]() { if (kind == 0) step_enqueue(slot0, n, injected); else { prepare_step(slot0, n); mimi(slot0, n); } };
+        auto body = [&]() {
+            if (kind == 0) step_enqueue(slot0, n, injected);
+            else if (kind == 1) { mimi_front(slot0, n, mx); mimi(slot0, n, mx); }
+            else if (kind == 2) flow_part(slot0, n, injected, mx2[par]);
+            else mimi(slot0, n, mx2[par]);
+        };
         if (!cfg.cuda_graphs || profiling) { body(); return; }
-        GraphEntry& g = graphs[std::make_tuple(kind, slot0, n, injected ? 1 : 0)];
+        GraphEntry& g = graphs[std::make_tuple(kind * 2 + par, slot0, n, injected ? 1 : 0)];
         if (g.exec) { PTTS_CUDA_CHECK(cudaGraphLaunch(g.exec, stream)); launches += g.nlaunch; return; }
         if (g.seen++ == 0) { body(); return; }              // eager once: function attributes set, tensor maps encoded
         PTTS_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
@@ -399,6 +420,30 @@ struct b200_engine {
         PTTS_CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
         PTTS_CUDA_CHECK(cudaGraphDestroy(graph));
         PTTS_CUDA_CHECK(cudaGraphLaunch(g.exec, stream)); launches += g.nlaunch;
+    }
+
+    // Main stream waits for everything enqueued on the Mimi stream (before any non-pipelined use of Mimi state / PCM on the main stream).
+    void join_mimi() {
+        if (!mimi_pending) return;
+        const int last = (int)((pipe_t + 1) & 1);            // parity of the most recent frame
+        if (ev_mimi_valid[last]) PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_mimi[last], 0));
+        mimi_pending = false;
+    }
+
+    // One generation step. Pipelined form: FlowLM part of frame t on the main stream, Mimi body of frame t on stream_m, so that it
+    // overlaps the FlowLM part of frame t+1. PCM of frame t is complete after ev_mimi[t & 1] (b200_sync / join_mimi).
+    void run_step(int slot0, int n, bool injected) {
+        if (!cfg.overlap || !cfg.cuda_graphs || profiling) { join_mimi(); run_graphed(0, slot0, n, injected); return; }
+        const int par = (int)(pipe_t & 1);
+        if (ev_mimi_valid[par]) PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_mimi[par], 0));   // mx2[par] free again (frame t-2 decoded)
+        run_graphed(2, slot0, n, injected, par);
+        PTTS_CUDA_CHECK(cudaEventRecord(ev_main[par], stream));
+        PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream_m, ev_main[par], 0));
+        std::swap(stream, stream_m); tc->cur_ws = 1;          // the Mimi stream has its own split-K workspace
+        run_graphed(3, slot0, n, injected, par);
+        std::swap(stream, stream_m); tc->cur_ws = 0;
+        PTTS_CUDA_CHECK(cudaEventRecord(ev_mimi[par], stream_m));
+        ev_mimi_valid[par] = true; mimi_pending = true; pipe_t++;
     }
 
     void ensure_pinned(size_t nf, size_t ni) {
@@ -444,7 +489,7 @@ extern "C" {
 void b200_default_config(b200_config* c) {
     memset(c, 0, sizeof(*c));
     c->device = 0; c->max_slots = 1; c->max_voices = 8; c->kv_capacity = 2048; c->kv_f32 = 0; c->mimi_mask_mode = 0;
-    c->convt_split = 0; c->gemm_path = 0; c->max_prefill_rows = 512; c->cuda_graphs = 1; c->pdl = 1;
+    c->convt_split = 0; c->gemm_path = 0; c->max_prefill_rows = 512; c->cuda_graphs = 1; c->pdl = 1; c->overlap = 1;
 }
 
 int b200_engine_create(const b200_config* cfg, b200_engine** out) {
@@ -458,7 +503,16 @@ int b200_engine_create(const b200_config* cfg, b200_engine** out) {
     if (e->cfg.max_prefill_rows <= 0) e->cfg.max_prefill_rows = 512;
     if (e->cfg.max_voices < 1) e->cfg.max_voices = 1;
     PTTS_CUDA_CHECK(cudaSetDevice(cfg->device));
-    PTTS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    {   // the FlowLM chain is the critical path of a frame: it gets the higher priority, the Mimi decode fills the gaps
+        int lo = 0, hi = 0;
+        PTTS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, hi));
+        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_m, cudaStreamNonBlocking, lo));
+        for (int i = 0; i < 2; i++) {
+            PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_main[i], cudaEventDisableTiming));
+            PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_mimi[i], cudaEventDisableTiming));
+        }
+    }
     e->total_slots = cfg->max_slots + e->cfg.max_voices;
     e->max_rows = std::max(cfg->max_slots, e->cfg.max_prefill_rows);
     e->voice_len.assign(e->cfg.max_voices, 0);
@@ -472,12 +526,14 @@ void b200_engine_destroy(b200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
+    cudaStreamSynchronize(e->stream_m);
     for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (void* p : e->allocs) cudaFree(p);
     if (e->pin_f) cudaFreeHost(e->pin_f);
     if (e->pin_i) cudaFreeHost(e->pin_i);
     tc_plan_cache_destroy(e->tc);
-    cudaStreamDestroy(e->stream);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(e->ev_main[i]); cudaEventDestroy(e->ev_mimi[i]); }
+    cudaStreamDestroy(e->stream); cudaStreamDestroy(e->stream_m);
     delete e;
 }
 
@@ -634,7 +690,7 @@ int b200_finalize_weights(b200_engine* e) {
     e->d_seed = e->dalloc<unsigned long long>(1);
     PTTS_CUDA_CHECK(cudaMemcpyAsync(e->d_seed, &e->seed, sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
     const size_t MRm = (size_t)S * M_T;
-    e->mx = e->dalloc<float>(MRm * M_DIM); e->mn_bf = e->dalloc<__nv_bfloat16>(MRm * M_DIM); e->mq_bf = e->dalloc<__nv_bfloat16>(MRm * M_DIM);
+    e->mx = e->dalloc<float>(MRm * M_DIM); e->mx2[0] = e->dalloc<float>(MRm * M_DIM); e->mx2[1] = e->dalloc<float>(MRm * M_DIM); e->mn_bf = e->dalloc<__nv_bfloat16>(MRm * M_DIM); e->mq_bf = e->dalloc<__nv_bfloat16>(MRm * M_DIM);
     e->matt_bf = e->dalloc<__nv_bfloat16>(MRm * M_DIM); e->mff_bf = e->dalloc<__nv_bfloat16>(MRm * M_FF);
     e->mrow_slot = e->dalloc<int>(MRm); e->mrow_pos = e->dalloc<int>(MRm); e->mcs = e->dalloc<float2>(MRm * 32);
     e->buf0 = e->dalloc<__half>((size_t)S * 22 * 512); e->buf2 = e->dalloc<__half>((size_t)S * 17 * e->C2);
@@ -657,7 +713,7 @@ int b200_finalize_weights(b200_engine* e) {
     // Keep the shared-memory carve-out identical for every kernel of the step: mixed carve-outs force an SM reconfiguration
     // between consecutive launches, which shows up as microseconds of idle time on the ~100 small kernels of a frame.
     {
-        const void* ks[] = {(const void*)prepare_step_kernel, (const void*)rope_table_kernel, (const void*)gemm_ffma_kernel<__nv_bfloat16>, (const void*)gemm_ffma_kernel<__half>,
+        const void* ks[] = {(const void*)prepare_flow_kernel, (const void*)prepare_mimi_kernel, (const void*)rope_table_kernel, (const void*)gemm_ffma_kernel<__nv_bfloat16>, (const void*)gemm_ffma_kernel<__half>,
                             (const void*)gemv_small_kernel<__nv_bfloat16, 8>, (const void*)gemv_small_kernel<__half, 8>, (const void*)layernorm_kernel<D_MODEL>,
                             (const void*)layernorm_kernel<D_FLOW>, 
                             (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
@@ -720,6 +776,7 @@ int b200_begin_sentences(b200_engine* e, int n, const int32_t* slots, const int3
                          const int32_t* tok_off, const int32_t* max_gen_len, const int32_t* frames_after_eos, const float* temp) {
     if (!e || !e->finalized || n < 0) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->join_mimi();                                           // the slot resets below touch Mimi state on the main stream
     const size_t elt = e->cfg.kv_f32 ? 4 : 2;
     std::vector<int> rs, rp, rt;
     for (int i = 0; i < n; i++) {
@@ -766,14 +823,24 @@ int b200_begin_sentence(b200_engine* e, int slot, int voice, const int32_t* toke
 int b200_step_enqueue(b200_engine* e, int slot0, int n, int use_injected_noise) {
     if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
-    e->run_graphed(0, slot0, n, use_injected_noise != 0);
+    e->run_step(slot0, n, use_injected_noise != 0);
     return B200_OK;
 }
 
 int b200_sync(b200_engine* e) {
     if (!e) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream_m));
     PTTS_CUDA_CHECK(cudaGetLastError());
+    return B200_OK;
+}
+
+// Makes the main stream wait for all Mimi-stream work enqueued so far (so that an event recorded on b200_stream() afterwards covers
+// the complete frames, PCM included). Costs nothing when the pipeline is idle.
+int b200_join(b200_engine* e) {
+    if (!e) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->join_mimi();
     return B200_OK;
 }
 
@@ -786,7 +853,8 @@ int b200_step(b200_engine* e, int slot0, int n, const float* noise, float* pcm, 
         memcpy(p_noise, noise, (size_t)n * LDIM * sizeof(float));
         PTTS_CUDA_CHECK(cudaMemcpyAsync(e->noise_inj, p_noise, (size_t)n * LDIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     }
-    e->run_graphed(0, slot0, n, noise != nullptr);
+    e->run_step(slot0, n, noise != nullptr);
+    e->join_mimi();                                           // synchronous API: this frame's PCM is returned by this call
     PTTS_CUDA_CHECK(cudaMemcpyAsync(p_pcm, e->pcm + (size_t)slot0 * FRAME, (size_t)n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     PTTS_CUDA_CHECK(cudaMemcpyAsync(e->pin_i, e->produced, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     if (latents) PTTS_CUDA_CHECK(cudaMemcpyAsync(p_lat, e->latent, (size_t)n * LDIM * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
@@ -802,6 +870,7 @@ int b200_step(b200_engine* e, int slot0, int n, const float* noise, float* pcm, 
 int b200_mimi_reset(b200_engine* e, int slot0, int n) {
     if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->join_mimi();
     for (int s = slot0; s < slot0 + n; s++) launch_k(false, reset_slot_kernel, dim3(1, e->shifts.n), dim3(256), (size_t)(0), e->stream, e->shifts, s, e->e_prev, e->mimi_off);
     e->launches += n;
     return B200_OK;
@@ -810,6 +879,7 @@ int b200_mimi_reset(b200_engine* e, int slot0, int n) {
 int b200_mimi_decode_enqueue(b200_engine* e, int slot0, int n) {
     if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->join_mimi();
     e->run_graphed(1, slot0, n, false);
     return B200_OK;
 }
@@ -817,6 +887,7 @@ int b200_mimi_decode_enqueue(b200_engine* e, int slot0, int n) {
 int b200_mimi_decode(b200_engine* e, int slot0, int n, const float* latents, float* pcm) {
     if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots || !latents || !pcm) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->join_mimi();
     e->ensure_pinned((size_t)n * (FRAME + LDIM), 16);
     memcpy(e->pin_f, latents, (size_t)n * LDIM * sizeof(float));
     PTTS_CUDA_CHECK(cudaMemcpyAsync(e->lat_f32 + (size_t)slot0 * LDIM, e->pin_f, (size_t)n * LDIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
@@ -850,6 +921,7 @@ int b200_slot_position(b200_engine* e, int slot) {
 int b200_debug_set_position(b200_engine* e, int slot0, int n, int pos, int max_gen_len) {
     if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots || pos < 0 || pos + max_gen_len > e->cfg.kv_capacity) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->join_mimi();
     const float* bos = e->d_bos;
     for (int s = slot0; s < slot0 + n; s++) {
         launch_k(false, reset_slot_kernel, dim3(1, e->shifts.n), dim3(256), (size_t)(0), e->stream, e->shifts, s, e->e_prev, e->mimi_off);

@@ -553,7 +553,8 @@ struct TcPlanCache {
     int num_sms = 148;
     bool w_kb_major = true;     // PTTS_B200_WLAYOUT=0: keep tensor-core weights row-major (layout experiment)
     bool pdl = false;
-    float* ws = nullptr; size_t ws_elems = 0;   // split-K partial sums
+    float* ws_buf[2] = {nullptr, nullptr}; size_t ws_elems = (size_t)32 << 20;   // split-K partial sums, one workspace per engine stream
+    int cur_ws = 0;
 };
 
 inline TcPlanCache* tc_plan_cache_create() {
@@ -575,7 +576,7 @@ inline TcPlanCache* tc_plan_cache_create() {
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) c->num_sms = sms;
     return c;
 }
-inline void tc_plan_cache_destroy(TcPlanCache* c) { if (c && c->ws) cudaFree(c->ws); delete c; }
+inline void tc_plan_cache_destroy(TcPlanCache* c) { if (c) for (float* w : c->ws_buf) if (w) cudaFree(w); delete c; }
 
 struct TcGeom { int C, taps, T, SB, tps, tiles_m, n_slots, rows_per_slot_buf, box_rows; long long slot_stride; bool ok; };
 
@@ -713,8 +714,8 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     Epi kepi = epi;
     if (splits > 1) {
         // one fixed workspace for the engine's lifetime (its address is baked into captured CUDA graphs)
-        if (!c->ws) { c->ws_elems = (size_t)32 << 20; PTTS_CUDA_CHECK(cudaMalloc(&c->ws, c->ws_elems * sizeof(float))); }
-        kepi = Epi{}; kepi.out = c->ws; kepi.out_map.row_stride = N; p.ws_split_stride = (long long)R * N;
+        if (!c->ws_buf[c->cur_ws]) PTTS_CUDA_CHECK(cudaMalloc(&c->ws_buf[c->cur_ws], c->ws_elems * sizeof(float)));
+        kepi = Epi{}; kepi.out = c->ws_buf[c->cur_ws]; kepi.out_map.row_stride = N; p.ws_split_stride = (long long)R * N;
     } else { p.splits = 1; p.kb_per_split = num_kb; }
     p.epi_class = kepi.mode == EPI_GENERIC ? epi_class_of(kepi) : 0;
     p.prefetch = g.tiles_m <= 4 ? 1 : 0;
@@ -734,12 +735,12 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     if (ln_done) *ln_done = false;
     if (splits > 1) {
         if (ln_ok) {
-            if (N == 1024) launch_k(c->pdl, splitk_reduce_ln_kernel<1024>, dim3(R), dim3(256), 0, stream, (const float*)c->ws, splits, (long long)R * N, R, epi, *ln);
-            else launch_k(c->pdl, splitk_reduce_ln_kernel<512>, dim3(R), dim3(128), 0, stream, (const float*)c->ws, splits, (long long)R * N, R, epi, *ln);
+            if (N == 1024) launch_k(c->pdl, splitk_reduce_ln_kernel<1024>, dim3(R), dim3(256), 0, stream, (const float*)c->ws_buf[c->cur_ws], splits, (long long)R * N, R, epi, *ln);
+            else launch_k(c->pdl, splitk_reduce_ln_kernel<512>, dim3(R), dim3(128), 0, stream, (const float*)c->ws_buf[c->cur_ws], splits, (long long)R * N, R, epi, *ln);
             if (ln_done) *ln_done = true;
         } else {
             const long long quads = (long long)R * N / 4;
-            launch_k(c->pdl, splitk_reduce_kernel, dim3((unsigned)((quads + 255) / 256)), dim3(256), 0, stream, (const float*)c->ws, splits, (long long)R * N, R, N, epi);
+            launch_k(c->pdl, splitk_reduce_kernel, dim3((unsigned)((quads + 255) / 256)), dim3(256), 0, stream, (const float*)c->ws_buf[c->cur_ws], splits, (long long)R * N, R, N, epi);
         }
         return 2;
     }

@@ -128,6 +128,7 @@ ptts_context_t* ptts_init(ggml_backend*, ggml_backend*, const char* model_path) 
     cfg.gemm_path = env_int("PTTS_B200_GEMM_PATH", 0);
     cfg.cuda_graphs = env_int("PTTS_B200_CUDA_GRAPHS", 1);
     cfg.pdl = env_int("PTTS_B200_PDL", 1);
+    cfg.overlap = env_int("PTTS_B200_OVERLAP", 1);
     return init_with_config(model_path, cfg);
 }
 

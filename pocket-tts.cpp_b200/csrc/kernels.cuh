@@ -18,14 +18,28 @@ __global__ void rope_table_kernel(const int* __restrict__ row_pos, const float* 
     cs[idx] = make_float2(cosf(rad), sinf(rad));
 }
 
-// Decode step: one FlowLM row and 16 Mimi rows per slot in [slot0, slot0+n).
-__global__ void prepare_step_kernel(int slot0, int n, const int* __restrict__ cur_len, const int* __restrict__ mimi_off,
-                                    int* __restrict__ row_slot, int* __restrict__ row_pos,
-                                    int* __restrict__ mrow_slot, int* __restrict__ mrow_pos) {
+// Decode step, FlowLM side: one row per slot in [slot0, slot0+n): slot, position and the row's RoPE table in one launch.
+__global__ void prepare_flow_kernel(int slot0, int n, const int* __restrict__ cur_len, const float* __restrict__ freq,
+                                    int* __restrict__ row_slot, int* __restrict__ row_pos, float2* __restrict__ cs) {
     pdl_prologue();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < n) { row_slot[idx] = slot0 + idx; row_pos[idx] = cur_len[slot0 + idx]; }
-    if (idx < n * M_T) { const int s = slot0 + idx / M_T; mrow_slot[idx] = s; mrow_pos[idx] = mimi_off[s] + idx % M_T; }
+    if (idx >= n * 32) return;
+    const int r = idx >> 5, i = idx & 31, pos = cur_len[slot0 + r];
+    if (i == 0) { row_slot[r] = slot0 + r; row_pos[r] = pos; }
+    const float rad = (float)pos * freq[i];
+    cs[idx] = make_float2(cosf(rad), sinf(rad));
+}
+
+// Decode step, Mimi side: 16 rows per slot (positions mimi_off .. mimi_off+15) and their RoPE table.
+__global__ void prepare_mimi_kernel(int slot0, int n, const int* __restrict__ mimi_off, const float* __restrict__ freq,
+                                    int* __restrict__ mrow_slot, int* __restrict__ mrow_pos, float2* __restrict__ mcs) {
+    pdl_prologue();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * M_T * 32) return;
+    const int r = idx >> 5, i = idx & 31, s = slot0 + r / M_T, pos = mimi_off[s] + r % M_T;
+    if (i == 0) { mrow_slot[r] = s; mrow_pos[r] = pos; }
+    const float rad = (float)pos * freq[i];
+    mcs[idx] = make_float2(cosf(rad), sinf(rad));
 }
 
 // Text prefill: x[r] = float(embed[token[r]])   (ggml_get_rows, reference conditioners/text.h:29-37)
