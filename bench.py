@@ -250,8 +250,16 @@ def main():
         eng.step_into(0, B, noise, pcm, produced); steps_done += 1
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.step_into(0, B, noise, pcm, produced)
+        if args.overlap:
+            # the pipelined public call pair: frame t+1 is submitted before frame t is collected (two frames in flight)
+            eng.submit(0, B, noise)
+            for _ in range(args.steps - 1):
+                eng.submit(0, B, noise)
+                eng.collect_into(pcm, produced)
+            eng.collect_into(pcm, produced)
+        else:
+            for _ in range(args.steps):
+                eng.step_into(0, B, noise, pcm, produced)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         steps_done += args.steps
@@ -260,7 +268,8 @@ def main():
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e = {"value": round(B * world * args.steps / float(t_e.item()), 2), "unit": UNIT, "h2d_bytes_per_step": int(noise.nbytes),
-               "d2h_bytes_per_step": int(pcm.nbytes + produced.nbytes)}
+               "d2h_bytes_per_step": int(pcm.nbytes + produced.nbytes),
+               "api": "b200_submit/b200_collect (two frames in flight)" if args.overlap else "b200_step (synchronous)"}
 
     # ---- roofline of the dominant kernel: profiled pass with event pairs around every FlowLM attention launch ----
     eng.profile(True)

@@ -57,6 +57,8 @@ def lib():
         "b200_begin_sentences": (ci, [vp, ci, ip, ip, ip, ip, ip, ip, fp]),
         "b200_step": (ci, [vp, ci, ci, fp, fp, ip, fp, fp]),
         "b200_step_enqueue": (ci, [vp, ci, ci, ci]),
+        "b200_submit": (ci, [vp, ci, ci, fp]),
+        "b200_collect": (ci, [vp, fp, ip]),
         "b200_sync": (ci, [vp]),
         "b200_join": (ci, [vp]),
         "b200_mimi_reset": (ci, [vp, ci, ci]),
@@ -181,6 +183,19 @@ class Engine:
     def step_into(self, slot0, n, noise, pcm, produced):
         """Zero-allocation variant for the bench's end-to-end leg (host buffers supplied by the caller)."""
         return self.L.b200_step(self.h, slot0, n, _fp(noise) if noise is not None else None, _fp(pcm), _ip(produced), None, None)
+
+    def submit(self, slot0, n, noise=None):
+        """Pipelined b200_step: enqueue one frame for slots [slot0, slot0+n) and return at once (at most two frames in flight)."""
+        rc = self.L.b200_submit(self.h, slot0, n, _fp(noise) if noise is not None else None)
+        if rc != 0:
+            raise RuntimeError(f"b200_submit failed: {rc}")
+
+    def collect_into(self, pcm, produced):
+        """Blocks until the oldest submitted frame is complete; fills pcm [n][1920] and produced [n]; returns n."""
+        rc = self.L.b200_collect(self.h, _fp(pcm), _ip(produced))
+        if rc < 0:
+            raise RuntimeError(f"b200_collect failed: {rc}")
+        return rc
 
     def step_enqueue(self, slot0, n, injected=False):
         rc = self.L.b200_step_enqueue(self.h, slot0, n, 1 if injected else 0)

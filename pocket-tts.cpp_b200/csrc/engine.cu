@@ -100,6 +100,10 @@ struct b200_engine {
     ShiftAll shifts{};
     // pinned staging
     float* pin_f = nullptr; int* pin_i = nullptr; size_t pin_f_n = 0, pin_i_n = 0;
+    // b200_submit / b200_collect: two frames in flight, one pinned staging set per parity
+    struct Pending { float* noise = nullptr; float* pcm = nullptr; int* produced = nullptr; size_t cap = 0; int slot0 = 0, n = 0; bool busy = false;
+                     cudaEvent_t done_main = nullptr, done_mimi = nullptr; } pend[2];
+    unsigned long long submit_t = 0, collect_t = 0;
     TcPlanCache* tc = nullptr;
     // optional per-segment device timing (bench.py roofline leg): event pairs recorded on the engine stream
     bool profiling = false;
@@ -529,6 +533,10 @@ void b200_engine_destroy(b200_engine* e) {
     cudaStreamSynchronize(e->stream_m);
     for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (void* p : e->allocs) cudaFree(p);
+    for (auto& pd : e->pend) {
+        if (pd.noise) cudaFreeHost(pd.noise); if (pd.pcm) cudaFreeHost(pd.pcm); if (pd.produced) cudaFreeHost(pd.produced);
+        if (pd.done_main) cudaEventDestroy(pd.done_main); if (pd.done_mimi) cudaEventDestroy(pd.done_mimi);
+    }
     if (e->pin_f) cudaFreeHost(e->pin_f);
     if (e->pin_i) cudaFreeHost(e->pin_i);
     tc_plan_cache_destroy(e->tc);
@@ -865,6 +873,55 @@ int b200_step(b200_engine* e, int slot0, int n, const float* noise, float* pcm, 
     if (latents) memcpy(latents, p_lat, (size_t)n * LDIM * sizeof(float));
     if (eos_logit) memcpy(eos_logit, p_eos, (size_t)n * sizeof(float));
     return B200_OK;
+}
+
+// Pipelined form of b200_step for throughput serving: b200_submit(t) enqueues frame t (H2D noise, FlowLM part on the main stream, Mimi
+// body on the Mimi stream, D2H of PCM / flags into pinned staging) and returns immediately; b200_collect() blocks until the OLDEST
+// submitted frame is complete and copies it out. At most two frames may be in flight (submit returns B200_ESTATE otherwise), so the
+// Mimi decode + copies of frame t overlap the FlowLM step of frame t+1. Frames come back in submission order.
+int b200_submit(b200_engine* e, int slot0, int n, const float* noise) {
+    if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots) return B200_EINVAL;
+    if (e->submit_t - e->collect_t >= 2) return B200_ESTATE;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    auto& pd = e->pend[e->submit_t & 1];
+    if (pd.cap < (size_t)n) {
+        if (pd.noise) cudaFreeHost(pd.noise); if (pd.pcm) cudaFreeHost(pd.pcm); if (pd.produced) cudaFreeHost(pd.produced);
+        PTTS_CUDA_CHECK(cudaMallocHost(&pd.noise, (size_t)n * LDIM * sizeof(float)));
+        PTTS_CUDA_CHECK(cudaMallocHost(&pd.pcm, (size_t)n * FRAME * sizeof(float)));
+        PTTS_CUDA_CHECK(cudaMallocHost(&pd.produced, (size_t)n * sizeof(int)));
+        pd.cap = n;
+    }
+    if (!pd.done_main) { PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&pd.done_main, cudaEventDisableTiming)); PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&pd.done_mimi, cudaEventDisableTiming)); }
+    if (noise) {
+        memcpy(pd.noise, noise, (size_t)n * LDIM * sizeof(float));
+        PTTS_CUDA_CHECK(cudaMemcpyAsync(e->noise_inj, pd.noise, (size_t)n * LDIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    }
+    e->run_step(slot0, n, noise != nullptr);
+    PTTS_CUDA_CHECK(cudaMemcpyAsync(pd.produced, e->produced, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    PTTS_CUDA_CHECK(cudaEventRecord(pd.done_main, e->stream));
+    const bool piped = e->mimi_pending;                       // Mimi body ran on the Mimi stream (overlap mode)
+    cudaStream_t sp = piped ? e->stream_m : e->stream;
+    PTTS_CUDA_CHECK(cudaMemcpyAsync(pd.pcm, e->pcm + (size_t)slot0 * FRAME, (size_t)n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, sp));
+    PTTS_CUDA_CHECK(cudaEventRecord(pd.done_mimi, sp));
+    if (piped) {   // the D2H above is now the newest Mimi-stream work: later joins must cover it
+        const int par = (int)((e->pipe_t + 1) & 1);
+        PTTS_CUDA_CHECK(cudaEventRecord(e->ev_mimi[par], e->stream_m));
+    }
+    pd.slot0 = slot0; pd.n = n; pd.busy = true; e->submit_t++;
+    return B200_OK;
+}
+
+int b200_collect(b200_engine* e, float* pcm, int32_t* produced) {
+    if (!e || !pcm || !produced) return B200_EINVAL;
+    if (e->collect_t == e->submit_t) return B200_ESTATE;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    auto& pd = e->pend[e->collect_t & 1];
+    PTTS_CUDA_CHECK(cudaEventSynchronize(pd.done_main));
+    PTTS_CUDA_CHECK(cudaEventSynchronize(pd.done_mimi));
+    memcpy(pcm, pd.pcm, (size_t)pd.n * FRAME * sizeof(float));
+    memcpy(produced, pd.produced, (size_t)pd.n * sizeof(int));
+    pd.busy = false; e->collect_t++;
+    return pd.n;
 }
 
 int b200_mimi_reset(b200_engine* e, int slot0, int n) {

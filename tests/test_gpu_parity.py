@@ -189,3 +189,31 @@ def test_device_rng_statistics(ctx, oracle_mod):
     _begin(ctx, oracle_mod, st, BENCH_SENTENCE, 0.7)
     pcm, prod, lat2, eos = eng.step(st.slot, 1, None)
     assert not np.array_equal(outs[0], lat2)
+
+
+def test_pipelined_submit_collect_matches_step(ctx, oracle_mod):
+    """b200_submit/b200_collect (two frames in flight, Mimi of frame t overlapping FlowLM of frame t+1) returns exactly the frames
+    of the synchronous b200_step, in order."""
+    eng = ctx.engine
+    st = ctx.stream("cosette", temp=0.7)
+    texts = ["Hello world.", BENCH_SENTENCE, "Short one."]
+    toks = [ctx.tokenize(t) for t in texts]
+    mg = [oracle_mod.max_gen_len_for(t) for t in texts]
+    fae = [oracle_mod.frames_after_eos_guess(t) for t in texts]
+    rng = np.random.default_rng(11)
+    noise = (rng.standard_normal((8, 3, 32)) * np.sqrt(0.7)).astype(np.float32)
+    eng.begin_sentences([0, 1, 2], [st.voice] * 3, toks, mg, fae, [0.7] * 3)
+    ref = [eng.step(0, 3, noise[i]) for i in range(8)]
+    eng.begin_sentences([0, 1, 2], [st.voice] * 3, toks, mg, fae, [0.7] * 3)
+    pcm = np.zeros((3, 1920), np.float32); prod = np.zeros(3, np.int32)
+    got = []
+    eng.submit(0, 3, noise[0])
+    for i in range(1, 8):
+        eng.submit(0, 3, noise[i])
+        assert eng.collect_into(pcm, prod) == 3
+        got.append((pcm.copy(), prod.copy()))
+    assert eng.collect_into(pcm, prod) == 3
+    got.append((pcm.copy(), prod.copy()))
+    for i in range(8):
+        assert np.array_equal(got[i][1], ref[i][1])
+        assert np.array_equal(got[i][0], ref[i][0]), i
