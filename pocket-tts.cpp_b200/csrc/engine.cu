@@ -40,11 +40,14 @@ struct b200_engine {
     bool ev_mimi_valid[2] = {false, false};
     unsigned long long pipe_t = 0;       // frames enqueued through the pipeline
     bool mimi_pending = false;           // stream_m holds work the main stream has not waited for
+    int last_mimi_par = 0;               // parity of the newest frame whose Mimi decode was enqueued
     std::map<std::string, HostTensor> host;
     std::vector<void*> allocs;
     bool finalized = false;
     bool pdl_active = false;   // programmatic dependent launch for the kernels being enqueued (see run_graphed)
     bool pdl_small = false, pdl_chain = false;
+    bool debug_skip_mimi = getenv("PTTS_B200_DEBUG_SKIP_MIMI") != nullptr;   // diagnosis only: time the FlowLM graph alone
+    int af_splits_override = getenv("PTTS_B200_AF_SPLITS") ? atoi(getenv("PTTS_B200_AF_SPLITS")) : 0;   // tuning hook
     void set_pdl(bool on) { pdl_active = on; if (tc) tc->pdl = on; }
     long long launches = 0;
     uint64_t seed = 0; unsigned long long* d_seed = nullptr;
@@ -87,6 +90,7 @@ struct b200_engine {
     float *h = nullptr, *q = nullptr; __nv_bfloat16 *n_bf = nullptr, *att_bf = nullptr, *ff_bf = nullptr;
     int *row_slot = nullptr, *row_pos = nullptr, *tok = nullptr; float2* cs = nullptr;
     float *af_ml = nullptr, *af_acc = nullptr;   // split-KV attention workspace [rows][splits][32] / [rows][splits][1024]
+    int* af_cnt = nullptr;                       // per-row arrival counters of the in-kernel split merge (zero between launches)
     __nv_bfloat16 *c_bf = nullptr, *sy_bf = nullptr, *hn_bf = nullptr, *h1_bf = nullptr, *noise_bf = nullptr;
     float *eos = nullptr, *ycond = nullptr, *mod = nullptr, *xh = nullptr, *noise_f32 = nullptr, *noise_inj = nullptr, *latent = nullptr;
     int* produced = nullptr; float* eos_out = nullptr;
@@ -218,47 +222,68 @@ struct b200_engine {
     }
 
     // FlowLM transformer over R rows held in `h` (reference modules/transformer.h:253-278,363-374).
+    // ---- FlowLM transformer over R rows held in `h` (reference modules/transformer.h:253-278,363-374), in two pieces per layer so that the
+    //      decode step can be cut into segments at the end of every attention kernel (run_step) ----
+    // in_proj (+RoPE, KV append) and attention of layer l. Expects norm1 of layer l in n_bf.
+    void flow_attn_part(int l, int R) {
+        auto& L = fl[l];
+        Epi e; e.mode = EPI_FLOW_QKV; e.row_slot = row_slot; e.row_pos = row_pos; e.cs = cs; e.kv_f32 = cfg.kv_f32;
+        e.kv_slot_stride = kv_slot_stride; e.q_out_f32 = q;
+        if (cfg.kv_f32) { e.kcache = (float*)kc + l * kv_layer_stride; e.vcache = (float*)vc + l * kv_layer_stride; }
+        else { e.kcache = (__nv_bfloat16*)kc + l * kv_layer_stride; e.vcache = (__nv_bfloat16*)vc + l * kv_layer_stride; }
+        lin(n_bf, L.in_proj, R, e);
+        const int sg = seg_begin(0);
+        const bool pdl_saved = pdl_active;
+        set_pdl(pdl_small);                                  // the KV-streaming kernel fills the machine: no early dependents around it
+        if (cfg.kv_f32) {
+            const size_t smem = (size_t)cfg.kv_capacity * sizeof(float);
+            launch_k(pdl_active, attn_flow_kernel<float>, dim3(R, N_HEADS), dim3(128), (size_t)(smem), stream, q, (const float*)e.kcache, (const float*)e.vcache, kv_slot_stride, row_slot, row_pos, att_bf);
+        } else {
+            // KV splits: at least ~2 CTAs per SM, and among those the split count whose CTA total comes closest to whole waves of
+            // one 128 KB-smem CTA per SM (R = 256: 3 splits = 5.19 waves, the last wave streams on 28 SMs; 4 splits = 6.92 waves,
+            // measured 1.557 -> 1.467 ms per step for the six launches). The last split CTA of a row merges the row's partials.
+            const int sms = tc ? tc->num_sms : 148;
+            int splits = 1; double best = -1.0;
+            for (int sp = 1; sp <= AF_MAX_SPLITS; sp++) {
+                const long long ctas = (long long)R * sp;
+                if (ctas < 2LL * sms && sp < AF_MAX_SPLITS) continue;
+                const double waves = (double)ctas / sms, eff = waves / std::ceil(waves);
+                if (eff > best + 1e-9) { best = eff; splits = sp; }
+                if (ctas >= 8LL * sms) break;
+            }
+            if (af_splits_override > 0) splits = std::min(af_splits_override, AF_MAX_SPLITS);
+            launch_k(pdl_active, attn_flow_split_kernel, dim3(splits, R), dim3(288), (size_t)(AF_SMEM), stream, q, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, kv_slot_stride,
+                                                                              row_slot, row_pos, splits, af_ml, af_acc, att_bf, af_cnt);
+        }
+        launches++;
+        set_pdl(pdl_saved);
+        seg_end(sg);
+    }
+    // out_proj (+residual, norm2), linear1 (+GELU), linear2 (+residual) of layer l; leaves norm1 of layer l+1 in n_bf.
+    void flow_chain_part(int l, int R) {
+        const int BIG = 1 << 30;
+        auto& L = fl[l];
+        Epi eo; eo.resid = h; eo.resid_map = rows(D_MODEL); eo.out = h; eo.out_map = rows(D_MODEL);
+        LnFuse f2; f2.w = L.n2w; f2.b = L.n2b; f2.eps = 1e-5f; f2.out = n_bf;
+        if (!lin(att_bf, L.out_proj, R, eo, &f2)) {
+            launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
+        }
+        Epi e1; e1.out2 = ff_bf; e1.out2_map = rows(D_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
+        lin(n_bf, L.lin1, R, e1);
+        Epi e2; e2.resid = h; e2.resid_map = rows(D_MODEL); e2.out = h; e2.out_map = rows(D_MODEL);
+        if (l + 1 < N_LAYERS) {
+            LnFuse f1; f1.w = fl[l + 1].n1w; f1.b = fl[l + 1].n1b; f1.eps = 1e-5f; f1.out = n_bf;
+            if (!lin(ff_bf, L.lin2, R, e2, &f1)) {
+                launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, fl[l + 1].n1w, fl[l + 1].n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
+            }
+        } else {
+            lin(ff_bf, L.lin2, R, e2);
+        }
+    }
     void flow_forward(int R, bool ln1_done = false) {              // ln1_done: layer 0's norm1 already in n_bf (decode: flow_in_kernel)
         const int BIG = 1 << 30;
-        for (int l = 0; l < N_LAYERS; l++) {
-            auto& L = fl[l];
-            if (!ln1_done) { launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n1w, L.n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++; }
-            Epi e; e.mode = EPI_FLOW_QKV; e.row_slot = row_slot; e.row_pos = row_pos; e.cs = cs; e.kv_f32 = cfg.kv_f32;
-            e.kv_slot_stride = kv_slot_stride; e.q_out_f32 = q;
-            if (cfg.kv_f32) { e.kcache = (float*)kc + l * kv_layer_stride; e.vcache = (float*)vc + l * kv_layer_stride; }
-            else { e.kcache = (__nv_bfloat16*)kc + l * kv_layer_stride; e.vcache = (__nv_bfloat16*)vc + l * kv_layer_stride; }
-            lin(n_bf, L.in_proj, R, e);
-            const int sg = seg_begin(0);
-            const bool pdl_saved = pdl_active;
-            set_pdl(pdl_small);                                  // the KV-streaming kernel fills the machine: no early dependents around it
-            if (cfg.kv_f32) {
-                const size_t smem = (size_t)cfg.kv_capacity * sizeof(float);
-                launch_k(pdl_active, attn_flow_kernel<float>, dim3(R, N_HEADS), dim3(128), (size_t)(smem), stream, q, (const float*)e.kcache, (const float*)e.vcache, kv_slot_stride, row_slot, row_pos, att_bf);
-            } else {
-                // enough CTAs for ~4 waves of one 128 KB-smem CTA per SM; each split streams >= a few dozen cache rows
-                int splits = (148 * 4 + R - 1) / R; splits = std::max(1, std::min(splits, AF_MAX_SPLITS));
-                launch_k(pdl_active, attn_flow_split_kernel, dim3(splits, R), dim3(288), (size_t)(AF_SMEM), stream, q, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, kv_slot_stride,
-                                                                                  row_slot, row_pos, splits, af_ml, af_acc, att_bf);
-                if (splits > 1) { launch_k(pdl_active, attn_flow_merge_kernel, dim3(R), dim3(256), (size_t)(0), stream, af_ml, af_acc, splits, att_bf); launches++; }
-            }
-            launches++;
-            set_pdl(pdl_saved);
-            seg_end(sg);
-            Epi eo; eo.resid = h; eo.resid_map = rows(D_MODEL); eo.out = h; eo.out_map = rows(D_MODEL);
-            LnFuse f2; f2.w = L.n2w; f2.b = L.n2b; f2.eps = 1e-5f; f2.out = n_bf;
-            if (!lin(att_bf, L.out_proj, R, eo, &f2)) {
-                launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
-            }
-            Epi e1; e1.out2 = ff_bf; e1.out2_map = rows(D_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
-            lin(n_bf, L.lin1, R, e1);
-            Epi e2; e2.resid = h; e2.resid_map = rows(D_MODEL); e2.out = h; e2.out_map = rows(D_MODEL);
-            if (l + 1 < N_LAYERS) {
-                LnFuse f1; f1.w = fl[l + 1].n1w; f1.b = fl[l + 1].n1b; f1.eps = 1e-5f; f1.out = n_bf;
-                ln1_done = lin(ff_bf, L.lin2, R, e2, &f1);
-            } else {
-                lin(ff_bf, L.lin2, R, e2);
-            }
-        }
+        if (!ln1_done) { launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, fl[0].n1w, fl[0].n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++; }
+        for (int l = 0; l < N_LAYERS; l++) { flow_attn_part(l, R); flow_chain_part(l, R); }
     }
 
     // out_norm + EOS + 1-step LSD head over R rows of `h` (reference models/flow_lm.h:114-142, modules/mlp.h:233-251).
@@ -292,75 +317,90 @@ struct b200_engine {
         launches++;
     }
     // Mimi decoder body for slots [slot0, slot0+n) from the front end's rows in `xbuf` (reference models/mimi.h:85-104).
-    void mimi(int slot0, int n, float* xbuf) {
+    // chunk < 0: everything; otherwise one of N_MCHUNK pieces of roughly equal duration (run_step interleaves them with the FlowLM segments)
+    static constexpr int N_MCHUNK = 6;
+    void mimi(int slot0, int n, float* xbuf, int chunk = -1) {
         const int BIG = 1 << 30, R = n * M_T;
-        launch_k(pdl_active, prepare_mimi_kernel, dim3((n * M_T * 32 + 255) / 256), dim3(256), (size_t)(0), stream, slot0, n, (const int*)mimi_off, (const float*)freq_mimi, mrow_slot, mrow_pos, mcs);
-        launches++;
+        auto on = [&](int c) { return chunk < 0 || chunk == c; };
+        if (on(0)) {
+            launch_k(pdl_active, prepare_mimi_kernel, dim3((n * M_T * 32 + 255) / 256), dim3(256), (size_t)(0), stream, slot0, n, (const int*)mimi_off, (const float*)freq_mimi, mrow_slot, mrow_pos, mcs);
+            launches++;
+        }
         float* x = xbuf + (long long)slot0 * M_T * M_DIM;
-        const int s_mtf = seg_begin(3);
+        const int s_mtf = chunk < 0 ? seg_begin(3) : -1;
         for (int l = 0; l < M_LAYERS; l++) {
             auto& L = ml[l];
-            launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3(R), dim3(M_DIM / 4), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n1w, L.n1b, nullptr, nullptr, 0, mn_bf, nullptr);
+            // layer 0: [LN1 in_proj attn out_proj] = chunk 0, [LN2 lin1 lin2] = chunk 1; layer 1: [LN1 in_proj] = chunk 1, the rest = chunk 2
+            const int c_qkv = l == 0 ? 0 : 1, c_att = l == 0 ? 0 : 2, c_mlp = l == 0 ? 1 : 2;
             Epi e; e.mode = EPI_MIMI_QKV; e.row_slot = mrow_slot; e.row_pos = mrow_pos; e.cs = mcs; e.kv_slot_stride = mkv_slot_stride;
             e.kcache = mkc + l * mkv_layer_stride; e.vcache = mvc + l * mkv_layer_stride; e.q_out_bf16 = mq_bf;
-            lin(mn_bf, L.in_proj, R, e);
-            if (cfg.gemm_path == 0) launch_k(pdl_active, attn_mimi_mma4_kernel, dim3(n * M_HEADS), dim3(128), (size_t)0, stream, (const __nv_bfloat16*)mq_bf, (const __nv_bfloat16*)e.kcache,
-                                             (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, (const int*)mimi_off, cfg.mimi_mask_mode, matt_bf);
-            else launch_k(pdl_active, attn_mimi_kernel, dim3(n, M_HEADS), dim3(256), (size_t)(AM_SMEM), stream, mq_bf, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, mimi_off, cfg.mimi_mask_mode, matt_bf);
-            Epi eo; eo.colscale = L.ls1; eo.resid = x; eo.resid_map = rows(M_DIM); eo.out = x; eo.out_map = rows(M_DIM);
-            lin(matt_bf, L.out_proj, R, eo);
-            launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3(R), dim3(M_DIM / 4), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n2w, L.n2b, nullptr, nullptr, 0, mn_bf, nullptr);
-            Epi e1; e1.out2 = mff_bf; e1.out2_map = rows(M_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
-            lin(mn_bf, L.lin1, R, e1);
-            Epi e2; e2.colscale = L.ls2; e2.resid = x; e2.resid_map = rows(M_DIM);
-            if (l + 1 < M_LAYERS) { e2.out = x; e2.out_map = rows(M_DIM); }
-            else {
-                // last layer: the only consumer is SEANet's first conv, so write its f16 input rows (after the 6 carried rows) directly
-                e2.rps = M_T; e2.resid_map = smap((long long)M_T * M_DIM, M_DIM, 0);
-                e2.out2 = buf0 + slot0 * 22LL * 512; e2.out2_map = smap(22LL * 512, 512, 6 * 512); e2.out2_type = OUT2_F16;
+            if (on(c_qkv)) {
+                launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3(R), dim3(M_DIM / 4), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n1w, L.n1b, nullptr, nullptr, 0, mn_bf, nullptr);
+                launches++;
+                lin(mn_bf, L.in_proj, R, e);
             }
-            lin(mff_bf, L.lin2, R, e2);
-            launches += 3;
+            if (on(c_att)) {
+                if (cfg.gemm_path == 0) launch_k(pdl_active, attn_mimi_mma4_kernel, dim3(n * M_HEADS), dim3(128), (size_t)0, stream, (const __nv_bfloat16*)mq_bf, (const __nv_bfloat16*)e.kcache,
+                                                 (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, (const int*)mimi_off, cfg.mimi_mask_mode, matt_bf);
+                else launch_k(pdl_active, attn_mimi_kernel, dim3(n, M_HEADS), dim3(256), (size_t)(AM_SMEM), stream, mq_bf, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, mkv_slot_stride, slot0, mimi_off, cfg.mimi_mask_mode, matt_bf);
+                launches++;
+                Epi eo; eo.colscale = L.ls1; eo.resid = x; eo.resid_map = rows(M_DIM); eo.out = x; eo.out_map = rows(M_DIM);
+                lin(matt_bf, L.out_proj, R, eo);
+            }
+            if (on(c_mlp)) {
+                launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3(R), dim3(M_DIM / 4), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n2w, L.n2b, nullptr, nullptr, 0, mn_bf, nullptr);
+                launches++;
+                Epi e1; e1.out2 = mff_bf; e1.out2_map = rows(M_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
+                lin(mn_bf, L.lin1, R, e1);
+                Epi e2; e2.colscale = L.ls2; e2.resid = x; e2.resid_map = rows(M_DIM);
+                if (l + 1 < M_LAYERS) { e2.out = x; e2.out_map = rows(M_DIM); }
+                else {
+                    // last layer: the only consumer is SEANet's first conv, so write its f16 input rows (after the 6 carried rows) directly
+                    e2.rps = M_T; e2.resid_map = smap((long long)M_T * M_DIM, M_DIM, 0);
+                    e2.out2 = buf0 + slot0 * 22LL * 512; e2.out2_map = smap(22LL * 512, 512, 6 * 512); e2.out2_type = OUT2_F16;
+                }
+                lin(mff_bf, L.lin2, R, e2);
+            }
         }
         seg_end(s_mtf);
-        const int s_sea = seg_begin(4);
+        const int s_sea = chunk < 0 ? seg_begin(4) : -1;
         // SEANet (reference modules/seanet.h:187-211); every conv is a GEMM over overlapping channel-last rows.
         const int T0 = 16, T1 = 96, T2 = 480, T3 = 1920;
         const long long s0 = 22LL * 512, s2 = 17LL * C2, s3a = 98LL * 256, s3b = 96LL * 128, s5 = 97LL * C5, s6a = 482LL * 128, s6b = 480LL * 64,
                         s8 = 481LL * C8, s9a = 1922LL * 64, s9b = 1920LL * 64, s11 = 1922LL * 64;
         const int o2t = cfg.convt_split ? OUT2_F16_SPLIT : OUT2_F16;
-        { Epi e; e.rps = T0; e.bias = c0.b; e.act = ACT_ELU; e.out2 = buf2 + slot0 * s2; e.out2_map = smap(s2, C2, C2); e.out2_type = o2t; e.split_off = 512;
+        if (on(3)) { Epi e; e.rps = T0; e.bias = c0.b; e.act = ACT_ELU; e.out2 = buf2 + slot0 * s2; e.out2_map = smap(s2, C2, C2); e.out2_type = o2t; e.split_off = 512;
           gemm<__half>(buf0 + slot0 * s0, smap(s0, 512, 0), T0, c0.w, c0.wk, n * T0, c0.N, c0.K, e); }
-        { Epi e; e.rps = T0; e.bias = t2.b; e.out = y3 + slot0 * 96LL * 256; e.out_map = smap(96LL * 256, 1536, 0);
+        if (on(3)) { Epi e; e.rps = T0; e.bias = t2.b; e.out = y3 + slot0 * 96LL * 256; e.out_map = smap(96LL * 256, 1536, 0);
           e.act = ACT_ELU; e.out2 = buf3a + slot0 * s3a; e.out2_map = smap(s3a, 1536, 2 * 256); e.out2_type = OUT2_F16;
           gemm<__half>(buf2 + slot0 * s2, smap(s2, C2, 0), T0, t2.w, t2.wk, n * T0, t2.N, t2.K, e); }
-        { Epi e; e.rps = T1; e.bias = r3a.b; e.act = ACT_ELU; e.out2 = buf3b + slot0 * s3b; e.out2_map = smap(s3b, 128, 0); e.out2_type = OUT2_F16;
+        if (on(3)) { Epi e; e.rps = T1; e.bias = r3a.b; e.act = ACT_ELU; e.out2 = buf3b + slot0 * s3b; e.out2_map = smap(s3b, 128, 0); e.out2_type = OUT2_F16;
           gemm<__half>(buf3a + slot0 * s3a, smap(s3a, 256, 0), T1, r3a.w, r3a.wk, n * T1, r3a.N, r3a.K, e); }
-        { Epi e; e.rps = T1; e.bias = r3b.b; e.resid = y3 + slot0 * 96LL * 256; e.resid_map = smap(96LL * 256, 256, 0);
+        if (on(3)) { Epi e; e.rps = T1; e.bias = r3b.b; e.resid = y3 + slot0 * 96LL * 256; e.resid_map = smap(96LL * 256, 256, 0);
           e.act = ACT_ELU; e.out2 = buf5 + slot0 * s5; e.out2_map = smap(s5, C5, C5); e.out2_type = o2t; e.split_off = 256;
           gemm<__half>(buf3b + slot0 * s3b, smap(s3b, 128, 0), T1, r3b.w, r3b.wk, n * T1, r3b.N, r3b.K, e); }
-        { Epi e; e.rps = T1; e.bias = t5.b; e.out = y6 + slot0 * 480LL * 128; e.out_map = smap(480LL * 128, 640, 0);
+        if (on(4)) { Epi e; e.rps = T1; e.bias = t5.b; e.out = y6 + slot0 * 480LL * 128; e.out_map = smap(480LL * 128, 640, 0);
           e.act = ACT_ELU; e.out2 = buf6a + slot0 * s6a; e.out2_map = smap(s6a, 640, 2 * 128); e.out2_type = OUT2_F16;
           gemm<__half>(buf5 + slot0 * s5, smap(s5, C5, 0), T1, t5.w, t5.wk, n * T1, t5.N, t5.K, e); }
-        { Epi e; e.rps = T2; e.bias = r6a.b; e.act = ACT_ELU; e.out2 = buf6b + slot0 * s6b; e.out2_map = smap(s6b, 64, 0); e.out2_type = OUT2_F16;
+        if (on(4)) { Epi e; e.rps = T2; e.bias = r6a.b; e.act = ACT_ELU; e.out2 = buf6b + slot0 * s6b; e.out2_map = smap(s6b, 64, 0); e.out2_type = OUT2_F16;
           gemm<__half>(buf6a + slot0 * s6a, smap(s6a, 128, 0), T2, r6a.w, r6a.wk, n * T2, r6a.N, r6a.K, e); }
-        { Epi e; e.rps = T2; e.bias = r6b.b; e.resid = y6 + slot0 * 480LL * 128; e.resid_map = smap(480LL * 128, 128, 0);
+        if (on(4)) { Epi e; e.rps = T2; e.bias = r6b.b; e.resid = y6 + slot0 * 480LL * 128; e.resid_map = smap(480LL * 128, 128, 0);
           e.act = ACT_ELU; e.out2 = buf8 + slot0 * s8; e.out2_map = smap(s8, C8, C8); e.out2_type = o2t; e.split_off = 128;
           gemm<__half>(buf6b + slot0 * s6b, smap(s6b, 64, 0), T2, r6b.w, r6b.wk, n * T2, r6b.N, r6b.K, e); }
-        { Epi e; e.rps = T2; e.bias = t8.b; e.out = y9 + slot0 * 1920LL * 64; e.out_map = smap(1920LL * 64, 256, 0);
+        if (on(5)) { Epi e; e.rps = T2; e.bias = t8.b; e.out = y9 + slot0 * 1920LL * 64; e.out_map = smap(1920LL * 64, 256, 0);
           e.act = ACT_ELU; e.out2 = buf9a + slot0 * s9a; e.out2_map = smap(s9a, 256, 2 * 64); e.out2_type = OUT2_F16;
           gemm<__half>(buf8 + slot0 * s8, smap(s8, C8, 0), T2, t8.w, t8.wk, n * T2, t8.N, t8.K, e); }
-        { Epi e; e.rps = T3; e.bias = r9a.b; e.act = ACT_ELU; e.out2 = buf9b + slot0 * s9b; e.out2_map = smap(s9b, 64, 0); e.out2_type = OUT2_F16;
+        if (on(5)) { Epi e; e.rps = T3; e.bias = r9a.b; e.act = ACT_ELU; e.out2 = buf9b + slot0 * s9b; e.out2_map = smap(s9b, 64, 0); e.out2_type = OUT2_F16;
           gemm<__half>(buf9a + slot0 * s9a, smap(s9a, 64, 0), T3, r9a.w, r9a.wk, n * T3, r9a.N, r9a.K, e); }
-        { Epi e; e.rps = T3; e.bias = r9b.b; e.resid = y9 + slot0 * 1920LL * 64; e.resid_map = smap(1920LL * 64, 64, 0);
+        if (on(5)) { Epi e; e.rps = T3; e.bias = r9b.b; e.resid = y9 + slot0 * 1920LL * 64; e.resid_map = smap(1920LL * 64, 64, 0);
           e.act = ACT_ELU; e.out2 = buf11 + slot0 * s11; e.out2_map = smap(s11, 64, 2 * 64); e.out2_type = OUT2_F16;
           gemm<__half>(buf9b + slot0 * s9b, smap(s9b, 64, 0), T3, r9b.w, r9b.wk, n * T3, r9b.N, r9b.K, e); }
-        {
+        if (on(5)) {
             const int Rr = n * T3;
             launch_k(pdl_active, conv_n1_kernel, dim3((Rr * 4 + 255) / 256), dim3(256), (size_t)(0), stream, buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm + (long long)slot0 * FRAME);
+            launch_k(pdl_active, shift_states_kernel, dim3(n, shifts.n), dim3(128), (size_t)(0), stream, shifts, slot0, mimi_off);
+            launches += 2;
         }
-        launch_k(pdl_active, shift_states_kernel, dim3(n, shifts.n), dim3(128), (size_t)(0), stream, shifts, slot0, mimi_off);
-        launches += 3;
         seg_end(s_sea);
     }
 
@@ -370,25 +410,36 @@ struct b200_engine {
     }
 
     // One generation step for slots [slot0, slot0+n) (reference _stream_sentence_step, src/pocket_tts.cpp:446-492).
-    // FlowLM step + head + stop rule + Mimi front end (everything that consumes / produces the latent hand-off).
-    void flow_part(int slot0, int n, bool injected, float* xbuf) {
+    // FlowLM step + head + stop rule + Mimi front end (everything that consumes / produces the latent hand-off), cut into N_LAYERS + 1
+    // segments: segment l < 6 ends with the attention kernel of layer l, segment 6 is the rest. seg < 0 enqueues all of them.
+    static constexpr int N_SEG = N_LAYERS + 1;
+    void flow_part(int slot0, int n, bool injected, float* xbuf, int seg = -1) {
         set_pdl(pdl_small || pdl_chain);
-        prepare_flow(slot0, n);
-        const int s_flow = seg_begin(1);
-        launch_k(pdl_active, flow_in_kernel, dim3(n), dim3(256), (size_t)0, stream, slot0, n, (const __nv_bfloat16*)lat_in_bf16, (const __nv_bfloat16*)input_linear_t,
-                 (const float*)input_linear.b, (const float*)fl[0].n1w, (const float*)fl[0].n1b, h, n_bf);
-        launches++;
-        flow_forward(n, true);
+        const int s_flow = (seg < 0) ? seg_begin(1) : -1;
+        for (int sg = 0; sg < N_SEG; sg++) {
+            if (seg >= 0 && sg != seg) continue;
+            if (sg == 0) {
+                launch_k(pdl_active, flow_in_kernel, dim3(n), dim3(256), (size_t)0, stream, slot0, n, (const __nv_bfloat16*)lat_in_bf16, (const __nv_bfloat16*)input_linear_t,
+                         (const float*)input_linear.b, (const float*)fl[0].n1w, (const float*)fl[0].n1b, h, n_bf, (const int*)cur_len, (const float*)freq_flow, row_slot, row_pos, cs);
+                launches++;
+            } else {
+                flow_chain_part(sg - 1, n);
+            }
+            if (sg < N_LAYERS) flow_attn_part(sg, n);
+        }
+        if (seg >= 0 && seg != N_SEG - 1) return;
         seg_end(s_flow);
         const int s_head = seg_begin(2);
         launch_k(pdl_active, noise_inproj_kernel, dim3(n), dim3(128), (size_t)(0), stream, slot0, n, (const float*)(injected ? noise_inj : nullptr), (const unsigned long long*)d_seed,
                  (const float*)temp, (const int*)gen_step, noise_f32, (const __nv_bfloat16*)input_proj_t, (const float*)input_proj.b, xh);
         flow_head(n);
-        launch_k(pdl_active, step_logic_kernel, dim3(n), dim3(32), (size_t)(0), stream, slot0, n, eos, latent, cur_len, gen_step, eos_step, max_gen, fae, active, lat_in_bf16, lat_f32, produced, eos_out);
-        launches += 2;
+        launches += 1;
         seg_end(s_head);
         set_pdl(pdl_small);
-        mimi_front(slot0, n, xbuf);
+        // stop rule + latent hand-off + Mimi front end (writes the 16 transformer input rows of every slot to xbuf)
+        launch_k(pdl_active, step_front_kernel, dim3(n), dim3(M_DIM), (size_t)(0), stream, slot0, n, (const float*)eos, (const float*)latent, cur_len, gen_step, eos_step, (const int*)max_gen,
+                 (const int*)fae, active, lat_in_bf16, lat_f32, produced, eos_out, (const float*)emb_std, (const float*)emb_mean, (const __half*)wq, (const float*)wup, (const float*)bup, e_prev, xbuf);
+        launches++;
     }
     void step_enqueue(int slot0, int n, bool injected) {       // single-stream form (eager / profiling)
         const int s_all = seg_begin(5);
@@ -397,9 +448,9 @@ struct b200_engine {
         seg_end(s_all);
     }
 
-    // kind 0 = full generation step (one stream), 1 = Mimi-only decode, 2 = FlowLM part -> mx2[par], 3 = Mimi body from mx2[par].
-    // Runs on the CURRENT `stream` member (run_step swaps in stream_m for kind 3).
-    void run_graphed(int kind, int slot0, int n, bool injected, int par = 0) {
+    // kind 0 = full generation step (one stream), 1 = Mimi-only decode, 2 = FlowLM segment `part` -> mx2[par], 3 = Mimi chunk `part`
+    // from mx2[par]. Runs on the CURRENT `stream` member (the pipeline swaps in stream_m for kind 3).
+    void run_graphed(int kind, int slot0, int n, bool injected, int par = 0, int part = 0) {
         // PDL overlaps each kernel's prologue with its predecessor's tail: a large win when the step is launch/latency bound
         // (batch 1), neutral once kernels fill the machine and the step is replayed as a graph.
         pdl_small = cfg.pdl >= 2 || (cfg.pdl == 1 && n <= 8);    // every kernel of the step
@@ -408,11 +459,11 @@ struct b200_engine {
         auto body = [&]() {
             if (kind == 0) step_enqueue(slot0, n, injected);
             else if (kind == 1) { mimi_front(slot0, n, mx); mimi(slot0, n, mx); }
-            else if (kind == 2) flow_part(slot0, n, injected, mx2[par]);
-            else mimi(slot0, n, mx2[par]);
+            else if (kind == 2) flow_part(slot0, n, injected, mx2[par], part);
+            else mimi(slot0, n, mx2[par], part);
         };
         if (!cfg.cuda_graphs || profiling) { body(); return; }
-        GraphEntry& g = graphs[std::make_tuple(kind * 2 + par, slot0, n, injected ? 1 : 0)];
+        GraphEntry& g = graphs[std::make_tuple((kind * 2 + par) * 16 + part, slot0, n, injected ? 1 : 0)];
         if (g.exec) { PTTS_CUDA_CHECK(cudaGraphLaunch(g.exec, stream)); launches += g.nlaunch; return; }
         if (g.seen++ == 0) { body(); return; }              // eager once: function attributes set, tensor maps encoded
         PTTS_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
@@ -426,28 +477,70 @@ struct b200_engine {
         PTTS_CUDA_CHECK(cudaGraphLaunch(g.exec, stream)); launches += g.nlaunch;
     }
 
+    // ---- two-stream pipeline -------------------------------------------------------------------------------------------------------
+    // FlowLM(t) runs on the main stream as N_SEG graphs, each ending with an attention kernel (HBM saturated, every SM busy). After
+    // segment l the main stream records an event and the Mimi stream, gated by it, runs chunk l of the PREVIOUS frame's Mimi decode:
+    // the tensor/ALU-bound Mimi work lands in the windows where the main stream runs its latency-bound chain of decode-sized GEMMs
+    // instead of competing with the KV stream for HBM. A frame whose Mimi decode has not been enqueued yet is `pending`; it is
+    // decoded by the next run_step, or right away by flush_pending() (synchronous b200_step, b200_join, b200_sync, b200_collect).
+    struct PendingFrame { bool valid = false; int slot0 = 0, n = 0, par = 0; long long tag = -1; } pending;   // tag = b200_submit index or -1
+    cudaEvent_t ev_seg[8] = {};
+
+    void mimi_chunk_on_side(const PendingFrame& f, int chunk) {
+        std::swap(stream, stream_m); tc->cur_ws = 1;          // the Mimi stream has its own split-K workspace
+        run_graphed(3, f.slot0, f.n, false, f.par, chunk);
+        std::swap(stream, stream_m); tc->cur_ws = 0;
+    }
+    void finish_mimi_frame(const PendingFrame& f) {
+        PTTS_CUDA_CHECK(cudaEventRecord(ev_mimi[f.par], stream_m));
+        ev_mimi_valid[f.par] = true; mimi_pending = true; last_mimi_par = f.par;
+        if (f.tag >= 0) {   // b200_submit frame: its PCM copy follows its Mimi decode on the Mimi stream
+            auto& pd = pend[f.tag & 1];
+            PTTS_CUDA_CHECK(cudaMemcpyAsync(pd.pcm, pcm + (size_t)f.slot0 * FRAME, (size_t)f.n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, stream_m));
+            PTTS_CUDA_CHECK(cudaEventRecord(pd.done_mimi, stream_m));
+            PTTS_CUDA_CHECK(cudaEventRecord(ev_mimi[f.par], stream_m));      // later joins must cover the copy as well
+        }
+    }
+    // Enqueue the whole Mimi decode of the pending frame now (no interleaving partner).
+    void flush_pending() {
+        if (!pending.valid) return;
+        const PendingFrame f = pending; pending.valid = false;
+        if (debug_skip_mimi) return;
+        PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream_m, ev_main[f.par], 0));
+        for (int c = 0; c < N_MCHUNK; c++) mimi_chunk_on_side(f, c);
+        finish_mimi_frame(f);
+    }
     // Main stream waits for everything enqueued on the Mimi stream (before any non-pipelined use of Mimi state / PCM on the main stream).
     void join_mimi() {
+        flush_pending();
         if (!mimi_pending) return;
-        const int last = (int)((pipe_t + 1) & 1);            // parity of the most recent frame
-        if (ev_mimi_valid[last]) PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_mimi[last], 0));
+        if (ev_mimi_valid[last_mimi_par]) PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_mimi[last_mimi_par], 0));
         mimi_pending = false;
     }
 
-    // One generation step. Pipelined form: FlowLM part of frame t on the main stream, Mimi body of frame t on stream_m, so that it
-    // overlaps the FlowLM part of frame t+1. PCM of frame t is complete after ev_mimi[t & 1] (b200_sync / join_mimi).
-    void run_step(int slot0, int n, bool injected) {
+    // One generation step for slots [slot0, slot0+n).
+    void run_step(int slot0, int n, bool injected, long long tag = -1) {
         if (!cfg.overlap || !cfg.cuda_graphs || profiling) { join_mimi(); run_graphed(0, slot0, n, injected); return; }
         const int par = (int)(pipe_t & 1);
-        if (ev_mimi_valid[par]) PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_mimi[par], 0));   // mx2[par] free again (frame t-2 decoded)
-        run_graphed(2, slot0, n, injected, par);
+        PendingFrame prev = pending; pending.valid = false;
+        if (prev.valid && (prev.slot0 != slot0 || prev.n != n)) { pending = prev; flush_pending(); prev.valid = false; }   // different slot range: no interleave
+        if (debug_skip_mimi) prev.valid = false;
+        if (prev.valid) PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream_m, ev_main[prev.par], 0));
+        for (int sg = 0; sg < N_SEG; sg++) {
+            // only the last segment (step_front_kernel) writes the hand-off rows mx2[par]: wait there, not at the start of the step, for
+            // frame t-2's Mimi decode (long finished in steady state; waiting up front would put its tail on the critical path)
+            if (sg == N_SEG - 1 && ev_mimi_valid[par]) PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_mimi[par], 0));
+            run_graphed(2, slot0, n, injected, par, sg);
+            if (prev.valid && sg < N_MCHUNK) {
+                PTTS_CUDA_CHECK(cudaEventRecord(ev_seg[sg], stream));
+                PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream_m, ev_seg[sg], 0));
+                mimi_chunk_on_side(prev, sg);
+            }
+        }
+        if (prev.valid) finish_mimi_frame(prev);
         PTTS_CUDA_CHECK(cudaEventRecord(ev_main[par], stream));
-        PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream_m, ev_main[par], 0));
-        std::swap(stream, stream_m); tc->cur_ws = 1;          // the Mimi stream has its own split-K workspace
-        run_graphed(3, slot0, n, injected, par);
-        std::swap(stream, stream_m); tc->cur_ws = 0;
-        PTTS_CUDA_CHECK(cudaEventRecord(ev_mimi[par], stream_m));
-        ev_mimi_valid[par] = true; mimi_pending = true; pipe_t++;
+        pending.valid = true; pending.slot0 = slot0; pending.n = n; pending.par = par; pending.tag = tag;
+        pipe_t++;
     }
 
     void ensure_pinned(size_t nf, size_t ni) {
@@ -510,12 +603,15 @@ int b200_engine_create(const b200_config* cfg, b200_engine** out) {
     {   // the FlowLM chain is the critical path of a frame: it gets the higher priority, the Mimi decode fills the gaps
         int lo = 0, hi = 0;
         PTTS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, hi));
-        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_m, cudaStreamNonBlocking, lo));
+        const char* pv = getenv("PTTS_B200_PRIO");              // tuning hook: 0 = Mimi stream low (default), 1 = Mimi stream high, 2 = equal
+        const int mode = pv ? atoi(pv) : 0;
+        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, mode == 1 ? lo : hi));
+        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_m, cudaStreamNonBlocking, mode == 0 ? lo : hi));
         for (int i = 0; i < 2; i++) {
             PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_main[i], cudaEventDisableTiming));
             PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_mimi[i], cudaEventDisableTiming));
         }
+        for (auto& ev : e->ev_seg) PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
     e->total_slots = cfg->max_slots + e->cfg.max_voices;
     e->max_rows = std::max(cfg->max_slots, e->cfg.max_prefill_rows);
@@ -541,6 +637,7 @@ void b200_engine_destroy(b200_engine* e) {
     if (e->pin_i) cudaFreeHost(e->pin_i);
     tc_plan_cache_destroy(e->tc);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(e->ev_main[i]); cudaEventDestroy(e->ev_mimi[i]); }
+    for (auto& ev : e->ev_seg) cudaEventDestroy(ev);
     cudaStreamDestroy(e->stream); cudaStreamDestroy(e->stream_m);
     delete e;
 }
@@ -687,7 +784,7 @@ int b200_finalize_weights(b200_engine* e) {
     e->h = e->dalloc<float>((size_t)MR * D_MODEL); e->q = e->dalloc<float>((size_t)MR * D_MODEL);
     e->n_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_MODEL); e->att_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_MODEL);
     e->ff_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_FF);
-    e->af_ml = e->dalloc<float>((size_t)MR * AF_MAX_SPLITS * 32); e->af_acc = e->dalloc<float>((size_t)MR * AF_MAX_SPLITS * D_MODEL);
+    e->af_ml = e->dalloc<float>((size_t)MR * AF_MAX_SPLITS * 32); e->af_acc = e->dalloc<float>((size_t)MR * AF_MAX_SPLITS * D_MODEL); e->af_cnt = e->dalloc<int>(MR);
     e->row_slot = e->dalloc<int>(MR); e->row_pos = e->dalloc<int>(MR); e->tok = e->dalloc<int>(MR); e->cs = e->dalloc<float2>((size_t)MR * 32);
     e->c_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_MODEL); e->sy_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW);
     e->hn_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW); e->h1_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW);
@@ -726,7 +823,7 @@ int b200_finalize_weights(b200_engine* e) {
                             (const void*)layernorm_kernel<D_FLOW>, 
                             (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
                             (const void*)attn_flow_split_kernel, (const void*)attn_flow_merge_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
-                            (const void*)step_logic_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma_kernel, (const void*)attn_mimi_mma4_kernel, (const void*)cast_f16_kernel,
+                            (const void*)step_logic_kernel, (const void*)step_front_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma_kernel, (const void*)attn_mimi_mma4_kernel, (const void*)cast_f16_kernel,
                             (const void*)conv_n1_kernel, (const void*)shift_states_kernel};
         for (const void* k : ks) PTTS_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
@@ -837,6 +934,8 @@ int b200_step_enqueue(b200_engine* e, int slot0, int n, int use_injected_noise) 
 
 int b200_sync(b200_engine* e) {
     if (!e) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->flush_pending();                                      // a frame whose Mimi decode was waiting for an interleaving partner
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream_m));
     PTTS_CUDA_CHECK(cudaGetLastError());
@@ -896,17 +995,13 @@ int b200_submit(b200_engine* e, int slot0, int n, const float* noise) {
         memcpy(pd.noise, noise, (size_t)n * LDIM * sizeof(float));
         PTTS_CUDA_CHECK(cudaMemcpyAsync(e->noise_inj, pd.noise, (size_t)n * LDIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     }
-    e->run_step(slot0, n, noise != nullptr);
+    e->run_step(slot0, n, noise != nullptr, (long long)e->submit_t);
     PTTS_CUDA_CHECK(cudaMemcpyAsync(pd.produced, e->produced, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     PTTS_CUDA_CHECK(cudaEventRecord(pd.done_main, e->stream));
-    const bool piped = e->mimi_pending;                       // Mimi body ran on the Mimi stream (overlap mode)
-    cudaStream_t sp = piped ? e->stream_m : e->stream;
-    PTTS_CUDA_CHECK(cudaMemcpyAsync(pd.pcm, e->pcm + (size_t)slot0 * FRAME, (size_t)n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, sp));
-    PTTS_CUDA_CHECK(cudaEventRecord(pd.done_mimi, sp));
-    if (piped) {   // the D2H above is now the newest Mimi-stream work: later joins must cover it
-        const int par = (int)((e->pipe_t + 1) & 1);
-        PTTS_CUDA_CHECK(cudaEventRecord(e->ev_mimi[par], e->stream_m));
-    }
+    if (!e->pending.valid) {   // non-pipelined step (overlap off): the frame is already decoded on the main stream
+        PTTS_CUDA_CHECK(cudaMemcpyAsync(pd.pcm, e->pcm + (size_t)slot0 * FRAME, (size_t)n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        PTTS_CUDA_CHECK(cudaEventRecord(pd.done_mimi, e->stream));
+    }   // otherwise the PCM copy is enqueued behind the frame's Mimi decode (finish_mimi_frame), by the next submit or by collect
     pd.slot0 = slot0; pd.n = n; pd.busy = true; e->submit_t++;
     return B200_OK;
 }
@@ -916,6 +1011,7 @@ int b200_collect(b200_engine* e, float* pcm, int32_t* produced) {
     if (e->collect_t == e->submit_t) return B200_ESTATE;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     auto& pd = e->pend[e->collect_t & 1];
+    if (e->pending.valid && e->pending.tag == (long long)e->collect_t) e->flush_pending();   // nobody submitted after it: decode it now
     PTTS_CUDA_CHECK(cudaEventSynchronize(pd.done_main));
     PTTS_CUDA_CHECK(cudaEventSynchronize(pd.done_mimi));
     memcpy(pcm, pd.pcm, (size_t)pd.n * FRAME * sizeof(float));

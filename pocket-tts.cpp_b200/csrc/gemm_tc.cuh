@@ -171,7 +171,7 @@ __device__ __forceinline__ void epi_chunk(const Epi& e, const float* stg, const 
     // may alias), and serialised load->store pairs cost ~1 us each
 #pragma unroll
     for (int half = 0; half < 2; half++) {                      // two passes of 4 rows: 16 registers of residual prefetch instead of 32
-        float4 rs4[4];
+        float4 rs4[4], rm4[4];
         if (has_res) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -183,6 +183,14 @@ __device__ __forceinline__ void epi_chunk(const Epi& e, const float* stg, const 
                 }
             }
         }
+        if (has_rm) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int r = 16 * half + 4 * i + sub;
+                rm4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (r < rows_left) rm4[i] = *reinterpret_cast<const float4*>(e.rowmul + (long long)(tile_row0 + r) * e.rowmul_ld + col);
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int r = 16 * half + 4 * i + sub;
@@ -192,10 +200,7 @@ __device__ __forceinline__ void epi_chunk(const Epi& e, const float* stg, const 
                 float v[4] = {w4.x, w4.y, w4.z, w4.w};
                 if (has_bias) { v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w; }
                 if (has_cs) { v[0] *= cs4.x; v[1] *= cs4.y; v[2] *= cs4.z; v[3] *= cs4.w; }
-                if (has_rm) {
-                    const float4 m = *reinterpret_cast<const float4*>(e.rowmul + (long long)(tile_row0 + r) * e.rowmul_ld + col);
-                    v[0] *= m.x; v[1] *= m.y; v[2] *= m.z; v[3] *= m.w;
-                }
+                if (has_rm) { v[0] *= rm4[i].x; v[1] *= rm4[i].y; v[2] *= rm4[i].z; v[3] *= rm4[i].w; }
                 if (has_res) { v[0] += rs4[i].x; v[1] += rs4[i].y; v[2] += rs4[i].z; v[3] += rs4[i].w; }
                 if (has_out) *reinterpret_cast<float4*>(e.out + ((long long)ri.x * out_ss + (long long)ri.y * out_rs + e.out_map.base + ws_off) + col) = make_float4(v[0], v[1], v[2], v[3]);
                 if (o2_bf16 || o2_f16) {
@@ -551,6 +556,7 @@ struct TcPlanCache {
     PFN_tmapEncodeTiled encode = nullptr;
     std::map<std::tuple<const void*, long long, long long, long long, long long, int, int>, CUtensorMap> maps;
     int num_sms = 148;
+    bool coreside = true;       // see tc_gemm_launch (PTTS_B200_CORESIDE=0 restores deep rings / two Mimi CTAs per SM)
     bool w_kb_major = true;     // PTTS_B200_WLAYOUT=0: keep tensor-core weights row-major (layout experiment)
     bool pdl = false;
     float* ws_buf[2] = {nullptr, nullptr}; size_t ws_elems = (size_t)32 << 20;   // split-K partial sums, one workspace per engine stream
@@ -562,6 +568,7 @@ inline TcPlanCache* tc_plan_cache_create() {
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) c->encode = (PFN_tmapEncodeTiled)fn;
     if (const char* v = getenv("PTTS_B200_WLAYOUT")) c->w_kb_major = atoi(v) != 0;
+    if (const char* v = getenv("PTTS_B200_CORESIDE")) c->coreside = atoi(v) != 0;
     // every (tile width, epilogue class) instantiation: opt in to the large dynamic smem and the uniform carve-out (see engine.cu)
     for (int bn : {128, 64, 32}) {
         const int st1 = bn == 128 ? TcCfg<128>::STAGES_1CTA : bn == 64 ? TcCfg<64>::STAGES_1CTA : TcCfg<32>::STAGES_1CTA;
@@ -722,8 +729,12 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     // instruction descriptor (kind::f16): D=f32, A/B = bf16|f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     p.idesc = (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int total_tiles = tiles * splits;
-    dim3 grid(std::min(total_tiles, 2 * c->num_sms));
-    const bool one_cta = total_tiles <= c->num_sms;             // at most one CTA per SM anyway: spend the whole smem on a deeper ring
+    // Co-residency mode (two-stream pipeline): every GEMM CTA takes at most half an SM (the 2-CTA ring depth), and GEMMs of the Mimi
+    // stream launch at most one CTA per SM, so a decode-sized GEMM of the FlowLM chain always finds room next to a persistent Mimi CTA
+    // instead of waiting for it to drain (CTAs are never preempted, stream priority only orders dispatch).
+    const bool side = c->coreside && c->cur_ws == 1;
+    dim3 grid(std::min(total_tiles, (side ? 1 : 2) * c->num_sms));
+    const bool one_cta = !c->coreside && total_tiles <= c->num_sms;   // at most one CTA per SM anyway: spend the whole smem on a deeper ring
     const int cls = kepi.mode == EPI_GENERIC ? p.epi_class : (kepi.mode == EPI_MIMI_QKV ? -2 : -1);
     TcKernelFn kern = tc_kernel(bn, cls);
     if (!kern) { fprintf(stderr, "ptts_b200: no tensor-core kernel for epilogue class %d\n", cls); abort(); }

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(128) attn_flow_kernel(const float* __restrict_
 // combines them (for one split the normalised bf16 output is written directly).
 // Same math as attn_flow_kernel (reference modules/transformer.h:157-199, src/torch.h:128-150).
 // ------------------------------------------------------------------------------------------------
-constexpr int AF_STAGES = 4, AF_KEYS = 8, AF_ROW_BYTES = D_MODEL * 2, AF_STAGE_BYTES = 2 * AF_KEYS * AF_ROW_BYTES;   // 32 KB
+constexpr int AF_STAGES = 3, AF_KEYS = 8, AF_ROW_BYTES = D_MODEL * 2, AF_STAGE_BYTES = 2 * AF_KEYS * AF_ROW_BYTES;   // 32 KB
 constexpr int AF_SMEM = AF_STAGES * AF_STAGE_BYTES + 128;
 constexpr int AF_MAX_SPLITS = 16;
 
@@ -192,11 +192,11 @@ __device__ __forceinline__ void af_mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 
-__global__ void __launch_bounds__(288, 1) attn_flow_split_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
+__global__ void __launch_bounds__(288, 2) attn_flow_split_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
                                                                  const __nv_bfloat16* __restrict__ vc, long long kv_slot_stride,
                                                                  const int* __restrict__ row_slot, const int* __restrict__ row_pos, int splits,
                                                                  float* __restrict__ ws_ml, float* __restrict__ ws_acc,
-                                                                 __nv_bfloat16* __restrict__ out) {
+                                                                 __nv_bfloat16* __restrict__ out, int* __restrict__ merge_cnt) {
     pdl_prologue();
     extern __shared__ __align__(128) uint8_t af_smem[];
     const int row = blockIdx.y, split = blockIdx.x;
@@ -221,6 +221,10 @@ __global__ void __launch_bounds__(288, 1) attn_flow_split_kernel(const float* __
 
     if (warp == 8) {
         if (lane == 0) {
+            // the KV stream is read exactly once per step: mark it evict-first so that it does not push the Mimi stream's operands
+            // (re-read by many tiles) and the next GEMM's prefetched weights out of L2
+            uint64_t pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
             const char* kg = reinterpret_cast<const char*>(kc + slot_off + (long long)j_begin * D_MODEL);
             const char* vg = reinterpret_cast<const char*>(vc + slot_off + (long long)j_begin * D_MODEL);
             for (int it = 0; it < n_stages_total; it++) {
@@ -230,10 +234,10 @@ __global__ void __launch_bounds__(288, 1) attn_flow_split_kernel(const float* __
                 const uint32_t bytes = (uint32_t)nk * AF_ROW_BYTES;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8 * s), "r"(2 * bytes) : "memory");
                 const uint32_t dst = sbase + s * AF_STAGE_BYTES;
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(dst), "l"(kg + (long long)it * AF_KEYS * AF_ROW_BYTES), "r"(bytes), "r"(bars + 8 * s) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(dst + AF_KEYS * AF_ROW_BYTES), "l"(vg + (long long)it * AF_KEYS * AF_ROW_BYTES), "r"(bytes), "r"(bars + 8 * s) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                             ::"r"(dst), "l"(kg + (long long)it * AF_KEYS * AF_ROW_BYTES), "r"(bytes), "r"(bars + 8 * s), "l"(pol) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                             ::"r"(dst + AF_KEYS * AF_ROW_BYTES), "l"(vg + (long long)it * AF_KEYS * AF_ROW_BYTES), "r"(bytes), "r"(bars + 8 * s), "l"(pol) : "memory");
             }
         }
     } else {
@@ -327,6 +331,33 @@ __global__ void __launch_bounds__(288, 1) attn_flow_split_kernel(const float* __
             const long long wo = (long long)row * splits + split;
             if ((t & 15) == 0) { ws_ml[wo * 32 + h] = M; ws_ml[wo * 32 + 16 + h] = L; }
             *reinterpret_cast<float4*>(ws_acc + wo * D_MODEL + 4 * t) = make_float4(o[0], o[1], o[2], o[3]);
+            if (merge_cnt) {
+                // The LAST split CTA of a row to finish merges all of the row's partials (fixed split order: deterministic) and writes the
+                // bf16 output, which removes the separate merge launch from every layer. Release/acquire through the per-row counter.
+                __threadfence();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                int* flag = reinterpret_cast<int*>(af_smem);
+                if (t == 0) { const int prev = atomicAdd(merge_cnt + row, 1); *flag = (prev == splits - 1); if (prev == splits - 1) merge_cnt[row] = 0; }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (*flag) {
+                    __threadfence();
+                    float Mm = -INFINITY;
+                    for (int sp = 0; sp < splits; sp++) Mm = fmaxf(Mm, __ldcg(ws_ml + ((long long)row * splits + sp) * 32 + h));
+                    float Lm = 0.f, om[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int sp = 0; sp < splits; sp++) {
+                        const long long w2 = (long long)row * splits + sp;
+                        const float ms = __ldcg(ws_ml + w2 * 32 + h);
+                        const float sc = (ms == -INFINITY) ? 0.f : expf(ms - Mm);
+                        Lm = fmaf(__ldcg(ws_ml + w2 * 32 + 16 + h), sc, Lm);
+                        const float4 a = __ldcg(reinterpret_cast<const float4*>(ws_acc + w2 * D_MODEL + 4 * t));
+                        om[0] = fmaf(a.x, sc, om[0]); om[1] = fmaf(a.y, sc, om[1]); om[2] = fmaf(a.z, sc, om[2]); om[3] = fmaf(a.w, sc, om[3]);
+                    }
+                    const float inv = 1.0f / Lm;
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(om[0] * inv, om[1] * inv), p1 = __floats2bfloat162_rn(om[2] * inv, om[3] * inv);
+                    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                    *reinterpret_cast<uint2*>(out + (long long)row * D_MODEL + 4 * t) = pk;
+                }
+            }
         }
     }
 }
@@ -863,13 +894,21 @@ __global__ void __launch_bounds__(128) noise_inproj_kernel(int slot0, int n, con
 // reference models/flow_lm.h:99) followed by layer 0's norm1 (src/torch.h:49-60) -> bf16 A operand of the first in_proj.
 __global__ void __launch_bounds__(256) flow_in_kernel(int slot0, int n, const __nv_bfloat16* __restrict__ lat_in, const __nv_bfloat16* __restrict__ w_in_t,
                                                       const float* __restrict__ b_in, const float* __restrict__ lnw, const float* __restrict__ lnb,
-                                                      float* __restrict__ h, __nv_bfloat16* __restrict__ n_bf) {
+                                                      float* __restrict__ h, __nv_bfloat16* __restrict__ n_bf,
+                                                      const int* __restrict__ cur_len, const float* __restrict__ freq,
+                                                      int* __restrict__ row_slot, int* __restrict__ row_pos, float2* __restrict__ cs) {
     pdl_prologue();
     __shared__ float xs[LDIM];
     __shared__ float red[2][8];
     const int r = blockIdx.x, i = threadIdx.x, warp = i >> 5, lane = i & 31;
     if (r >= n) return;
     if (i < LDIM) xs[i] = __bfloat162float(lat_in[(long long)(slot0 + r) * LDIM + i]);
+    if (warp == 1) {                                           // row bookkeeping for the QKV epilogues: slot, position, RoPE table
+        const int pos = cur_len[slot0 + r];
+        if (lane == 0) { row_slot[r] = slot0 + r; row_pos[r] = pos; }
+        const float rad = (float)pos * freq[lane];
+        cs[r * 32 + lane] = make_float2(cosf(rad), sinf(rad));
+    }
     __syncthreads();
     float v[4] = {0.f, 0.f, 0.f, 0.f};                         // w_in_t = input_linear.weight transposed to [32][1024] (coalesced)
 #pragma unroll
@@ -971,6 +1010,58 @@ __global__ void __launch_bounds__(512) mimi_front_kernel(int slot0, const float*
     }
 }
 
+// step_logic_kernel + mimi_front_kernel in one launch (decode step): the stop rule of slot r, the latent hand-off to the next FlowLM
+// step, and the Mimi front end on the latent this step produced.
+__global__ void __launch_bounds__(512) step_front_kernel(int slot0, int n, const float* __restrict__ eos, const float* __restrict__ latent,
+                                                         int* __restrict__ cur_len, int* __restrict__ gen_step, int* __restrict__ eos_step,
+                                                         const int* __restrict__ max_gen, const int* __restrict__ fae, int* __restrict__ active,
+                                                         __nv_bfloat16* __restrict__ lat_in_bf16, float* __restrict__ lat_f32, int* __restrict__ produced,
+                                                         float* __restrict__ eos_out, const float* __restrict__ emb_std, const float* __restrict__ emb_mean,
+                                                         const __half* __restrict__ wq_t, const float* __restrict__ wup_t, const float* __restrict__ bup,
+                                                         float* __restrict__ e_prev, float* __restrict__ x) {
+    pdl_prologue();
+    __shared__ float z[LDIM];
+    __shared__ int emit;
+    const int r = blockIdx.x, slot = slot0 + r, c = threadIdx.x;
+    if (r >= n) return;
+    if (c == 0) {
+        int e = 0;
+        if (active[slot]) {
+            const int g = gen_step[slot];
+            int es = eos_step[slot];
+            if (eos[r] > 0.f && es == -1) es = g;
+            eos_step[slot] = es;
+            cur_len[slot] += 1;                                   // increment_states (pocket_tts.cpp:96)
+            if (es != -1 && g >= es + fae[slot]) { gen_step[slot] = max_gen[slot]; active[slot] = 0; }
+            else {
+                e = 1; gen_step[slot] = g + 1;
+                if (g + 1 >= max_gen[slot]) active[slot] = 0;     // next receive would hit the cap (pocket_tts.cpp:450-453,495)
+            }
+        }
+        emit = e; produced[r] = e; if (eos_out) eos_out[r] = eos[r];
+    }
+    __syncthreads();
+    if (c < LDIM) {
+        float v;
+        if (emit) { v = latent[r * LDIM + c]; lat_f32[slot * LDIM + c] = v; lat_in_bf16[slot * LDIM + c] = __float2bfloat16_rn(v); }
+        else v = lat_f32[slot * LDIM + c];
+        z[c] = __half2float(__float2half_rn(__fadd_rn(__fmul_rn(emb_std[c], v), emb_mean[c])));
+    }
+    __syncthreads();
+    float e = 0.f;
+#pragma unroll
+    for (int i = 0; i < LDIM; i++) e = fmaf(__half2float(wq_t[i * M_DIM + c]), z[i], e);
+    const float ep = e_prev[(long long)slot * M_DIM + c];
+    e_prev[(long long)slot * M_DIM + c] = e;
+    const float bias = bup ? bup[c] : 0.f;
+    float* xo = x + (long long)slot * M_T * M_DIM + c;
+#pragma unroll
+    for (int k = 0; k < M_T; k++) {
+        const float y = __fadd_rn(__fmul_rn(e, wup_t[k * M_DIM + c]), __fmul_rn(ep, wup_t[(16 + k) * M_DIM + c]));
+        xo[(long long)k * M_DIM] = y + bias;
+    }
+}
+
 // f32 [rows][C] -> f16 copy into a conv input buffer (rows placed after the state rows).
 __global__ void cast_f16_kernel(const float* __restrict__ x, RowMap xmap, __half* __restrict__ out, RowMap omap, int rps, int R, int C) {
     pdl_prologue();
@@ -990,9 +1081,11 @@ __global__ void shift_states_kernel(ShiftAll sa, int slot0, int* __restrict__ mi
     const ShiftDesc d = sa.d[blockIdx.y];
     const int slot = slot0 + blockIdx.x;
     __half* base = d.buf + (long long)slot * d.slot_stride;
-    const int n = d.S * d.C;
+    const int n8 = d.S * d.C / 8;                               // 16-byte pieces (every C here is a multiple of 64)
     // source rows [T, T+S) and destination rows [0, S) never overlap because T >= S for every conv here.
-    for (int i = threadIdx.x; i < n; i += blockDim.x) base[i] = base[(long long)d.T * d.C + i];
+    const uint4* src = reinterpret_cast<const uint4*>(base + (long long)d.T * d.C);
+    uint4* dst = reinterpret_cast<uint4*>(base);
+    for (int i = threadIdx.x; i < n8; i += blockDim.x) dst[i] = src[i];
     if (blockIdx.y == 0 && threadIdx.x == 0) mimi_off[slot] += M_T;
 }
 
