@@ -286,10 +286,17 @@ def main():
     Lmid = np.array(L0, np.float64) + prof_step0 + args.steps / 2.0
     bytes_per_launch = float((2 * (Lmid + 1) * 1024 * elt).sum() + B * 1024 * (4 + 2))
     roof = None
+    # DRAM traffic of one attention launch as measured by ncu (--set full capture summarised in profiles/attn_flow_traffic.json by
+    # tools/ncu_kernel_report.py); scaled by the ratio of algorithmic bytes now / at capture, since it is per launch like `achieved`
+    traffic = None
+    tp = os.path.join(REPO, "profiles", "attn_flow_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic = int((tj["dram_bytes_read"] + tj["dram_bytes_write"]) * bytes_per_launch / tj["algorithmic_bytes_at_capture"])
     if attn_n:
         achieved = bytes_per_launch / (attn_ms / attn_n * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "attn_flow (FlowLM decode attention, one layer)", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
-                "frac": round(achieved / hbm, 4), "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": int(bytes_per_launch),
+                "frac": round(achieved / hbm, 4), "traffic": traffic, "peak_source": which, "algorithmic_bytes_per_launch": int(bytes_per_launch),
                 "avg_launch_ms": round(attn_ms / attn_n, 4),
                 "share_of_step": round(attn_ms / max(prof["step"][0], 1e-9), 4),
                 "segments_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items()}}

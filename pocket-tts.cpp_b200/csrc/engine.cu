@@ -160,7 +160,7 @@ struct b200_engine {
         LinW L; L.out = out; L.in = in;
         const auto wb = to_bf16(w->f);
         L.w = upload(wb);
-        if (in % 64 == 0) L.wk = tc->w_kb_major ? upload(tc_kblock_major(wb, out, in)) : L.w;
+        if (in % 64 == 0) L.wk = upload(tc_kblock_major(wb, out, in));
         L.b = up_f32(p + ".bias", false);
         return L;
     }
@@ -173,7 +173,7 @@ struct b200_engine {
         for (int a = 0; a < co; a++) for (int b = 0; b < ci; b++) for (int c = 0; c < k; c++)
             o[((size_t)a * k + c) * cp + b] = __float2half_rn(w->f[((size_t)a * ci + b) * k + c]);
         ConvW C; C.N = co; C.K = k * cp; C.w = upload(o); C.b = up_f32(p + ".conv.bias", false);
-        if (C.K % 64 == 0) C.wk = tc->w_kb_major ? upload(tc_kblock_major(o, C.N, C.K)) : C.w;
+        if (C.K % 64 == 0) C.wk = upload(tc_kblock_major(o, C.N, C.K));
         return C;
     }
     // transposed conv K = 2s (torch [ci][co][k]) as a 2-tap GEMM over [prev row | current row]:
@@ -188,7 +188,7 @@ struct b200_engine {
             o[((size_t)(j * co + c)) * Kw + kk] = __float2half_rn(w->f[((size_t)cin * co + c) * k + tap]);
         }
         ConvW C; C.N = N; C.K = Kw; C.w = upload(o);
-        if (Kw % 64 == 0) C.wk = tc->w_kb_major ? upload(tc_kblock_major(o, N, Kw)) : C.w;
+        if (Kw % 64 == 0) C.wk = upload(tc_kblock_major(o, N, Kw));
         auto* b = find(p + ".convtr.bias", false);
         if (b) { std::vector<float> bb(N); for (int j = 0; j < s; j++) for (int c = 0; c < co; c++) bb[j * co + c] = b->f[c]; C.b = upload(bb); }
         return C;
@@ -603,10 +603,8 @@ int b200_engine_create(const b200_config* cfg, b200_engine** out) {
     {   // the FlowLM chain is the critical path of a frame: it gets the higher priority, the Mimi decode fills the gaps
         int lo = 0, hi = 0;
         PTTS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        const char* pv = getenv("PTTS_B200_PRIO");              // tuning hook: 0 = Mimi stream low (default), 1 = Mimi stream high, 2 = equal
-        const int mode = pv ? atoi(pv) : 0;
-        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, mode == 1 ? lo : hi));
-        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_m, cudaStreamNonBlocking, mode == 0 ? lo : hi));
+        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, hi));
+        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_m, cudaStreamNonBlocking, lo));
         for (int i = 0; i < 2; i++) {
             PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_main[i], cudaEventDisableTiming));
             PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_mimi[i], cudaEventDisableTiming));
@@ -699,7 +697,7 @@ int b200_finalize_weights(b200_engine* e) {
         (void)has_b;
         e->ada_all.out = (int)(w.size() / D_FLOW); e->ada_all.in = D_FLOW;
         const auto wb = b200_engine::to_bf16(w);
-        e->ada_all.w = e->upload(wb); e->ada_all.wk = e->tc->w_kb_major ? e->upload(tc_kblock_major(wb, e->ada_all.out, D_FLOW)) : e->ada_all.w; e->ada_all.b = e->upload(b);
+        e->ada_all.w = e->upload(wb); e->ada_all.wk = e->upload(tc_kblock_major(wb, e->ada_all.out, D_FLOW)); e->ada_all.b = e->upload(b);
     }
     for (int r = 0; r < N_RES; r++) {
         const std::string p = f + "res_blocks." + std::to_string(r) + ".";
@@ -1113,7 +1111,7 @@ int b200_debug_gemm(b200_engine* e, int f16, const float* A, int n_slots, int ro
     int used_tc = 0;
     void* dWk = nullptr;
     if (K % 64 == 0) {
-        const std::vector<uint16_t> hk = e->tc->w_kb_major ? tc_kblock_major(hw, N, K) : hw;
+        const std::vector<uint16_t> hk = tc_kblock_major(hw, N, K);
         PTTS_CUDA_CHECK(cudaMalloc(&dWk, nw * 2)); PTTS_CUDA_CHECK(cudaMemcpy(dWk, hk.data(), nw * 2, cudaMemcpyHostToDevice));
     }
     if (f16) { used_tc = (path == 0 && dWk && tc_gemm_supported<__half>(R, N, K, am, rps, ep)); e->gemm<__half>((const __half*)dA, am, rps, (const __half*)dW, (const __half*)dWk, R, N, K, ep); }

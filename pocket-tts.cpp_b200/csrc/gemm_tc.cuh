@@ -30,11 +30,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm vo
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a large suspend-time hint: the warp sleeps in hardware until the phase flips instead of spinning
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     } while (!ok);
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
@@ -557,7 +558,6 @@ struct TcPlanCache {
     std::map<std::tuple<const void*, long long, long long, long long, long long, int, int>, CUtensorMap> maps;
     int num_sms = 148;
     bool coreside = true;       // see tc_gemm_launch (PTTS_B200_CORESIDE=0 restores deep rings / two Mimi CTAs per SM)
-    bool w_kb_major = true;     // PTTS_B200_WLAYOUT=0: keep tensor-core weights row-major (layout experiment)
     bool pdl = false;
     float* ws_buf[2] = {nullptr, nullptr}; size_t ws_elems = (size_t)32 << 20;   // split-K partial sums, one workspace per engine stream
     int cur_ws = 0;
@@ -567,7 +567,6 @@ inline TcPlanCache* tc_plan_cache_create() {
     auto* c = new TcPlanCache;
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) c->encode = (PFN_tmapEncodeTiled)fn;
-    if (const char* v = getenv("PTTS_B200_WLAYOUT")) c->w_kb_major = atoi(v) != 0;
     if (const char* v = getenv("PTTS_B200_CORESIDE")) c->coreside = atoi(v) != 0;
     // every (tile width, epilogue class) instantiation: opt in to the large dynamic smem and the uniform carve-out (see engine.cu)
     for (int bn : {128, 64, 32}) {
@@ -707,7 +706,6 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     // so cold weight streams from HBM are page-friendly instead of bn separate 128-byte pieces 2*K bytes apart
     cuuint64_t wdims[3] = {64, (cuuint64_t)N, (cuuint64_t)(K / 64)};
     cuuint64_t wstr[2] = {128, (cuuint64_t)N * 128};
-    if (!c->w_kb_major) { wstr[0] = (cuuint64_t)K * 2; wstr[1] = 128; }   // experiment switch: plain [N][K] row-major weights
     cuuint32_t wbox[3] = {64, (cuuint32_t)bn, 1};
     const CUtensorMap* tw = tc_get_map(c, W, f16, 3, wdims, wstr, wbox);
     TcParams p; p.R = R; p.N = N; p.K = K; p.kb_per_tap = g.C / 64; p.T = g.T; p.SB = g.SB; p.tps = g.tps; p.tiles_m = g.tiles_m;

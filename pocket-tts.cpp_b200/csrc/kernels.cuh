@@ -187,8 +187,8 @@ __device__ __forceinline__ uint32_t af_smem_u32(const void* p) { return (uint32_
 __device__ __forceinline__ void af_mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // hardware sleep until the phase flips
     } while (!ok);
 }
 

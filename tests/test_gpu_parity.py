@@ -217,3 +217,28 @@ def test_pipelined_submit_collect_matches_step(ctx, oracle_mod):
     for i in range(8):
         assert np.array_equal(got[i][1], ref[i][1])
         assert np.array_equal(got[i][0], ref[i][0]), i
+
+
+def test_batch64_tensor_core_path_matches_oracle(P, model_dir, orc, oracle_mod):
+    """At batch 64 every GEMM of the step (FlowLM decode included) runs on the tcgen05 kernel and the KV split / merge path of the
+    streaming attention is exercised: slots 0 and 63 (same sentence, same injected noise) must match the oracle and each other."""
+    B = 64
+    c = P.Context(model_dir, max_slots=B, kv_capacity=512)
+    eng = c.engine
+    st = c.stream("cosette", temp=0.7)
+    toks = c.tokenize(BENCH_SENTENCE)
+    eng.begin_sentences(list(range(B)), [st.voice] * B, [toks] * B, [oracle_mod.max_gen_len_for(BENCH_SENTENCE)] * B,
+                        [oracle_mod.frames_after_eos_guess(BENCH_SENTENCE)] * B, [0.7] * B)
+    os_ = orc.stream("cosette", kv_capacity=512)
+    assert os_.sentence_init(BENCH_SENTENCE) == toks
+    rng = np.random.default_rng(3)
+    for i in range(8):
+        noise = (rng.standard_normal(32) * np.sqrt(0.7)).astype(np.float32)
+        ok, lat, pcm, e = os_.step(noise)
+        gp, prod, glat, geos = eng.step(0, B, np.stack([noise] * B))
+        assert ok and prod.all()
+        for k in (0, B - 1):
+            assert np.abs(glat[k] - lat).max() < LAT_MAXABS, (i, k)
+            assert np.linalg.norm(glat[k] - lat) / np.linalg.norm(lat) < LAT_REL, (i, k)
+            assert snr_db(pcm, gp[k]) > SNR_MIN, (i, k)
+        assert np.array_equal(gp[0], gp[B - 1]) and np.array_equal(glat[0], glat[B - 1])      # deterministic, slot independent
