@@ -298,6 +298,7 @@ def main():
         roof = {"bound": "hbm", "kernel": "attn_flow (FlowLM decode attention, one layer)", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
                 "frac": round(achieved / hbm, 4), "traffic": traffic, "peak_source": which, "algorithmic_bytes_per_launch": int(bytes_per_launch),
                 "avg_launch_ms": round(attn_ms / attn_n, 4),
+                "note": "peak = driver-measured copy bandwidth (read+write); a read-only stream such as this kernel can exceed it slightly",
                 "share_of_step": round(attn_ms / max(prof["step"][0], 1e-9), 4),
                 "segments_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items()}}
 
