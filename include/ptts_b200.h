@@ -82,7 +82,7 @@ B200_API int  b200_step(b200_engine* e, int slot0, int n, const float* noise, fl
 /* Device-resident variant: enqueue one step on the engine stream, no copies, no sync. Results stay in the
  * engine's device buffers (b200_device_ptr). */
 B200_API int  b200_step_enqueue(b200_engine* e, int slot0, int n, int use_injected_noise);
-/* Pipelined pair for throughput serving (two frames in flight): submit enqueues a frame and returns at once, collect blocks until the
+/* Pipelined pair for throughput serving (up to three frames in flight): submit enqueues a frame and returns at once, collect blocks until the
    oldest submitted frame is complete and copies out its n x 1920 samples + produced flags; returns n (or a negative error).         */
 B200_API int  b200_submit(b200_engine* e, int slot0, int n, const float* noise /* [n][32] or NULL */);
 B200_API int  b200_collect(b200_engine* e, float* pcm, int32_t* produced);

@@ -185,7 +185,7 @@ class Engine:
         return self.L.b200_step(self.h, slot0, n, _fp(noise) if noise is not None else None, _fp(pcm), _ip(produced), None, None)
 
     def submit(self, slot0, n, noise=None):
-        """Pipelined b200_step: enqueue one frame for slots [slot0, slot0+n) and return at once (at most two frames in flight)."""
+        """Pipelined b200_step: enqueue one frame for slots [slot0, slot0+n) and return at once (at most three frames in flight)."""
         rc = self.L.b200_submit(self.h, slot0, n, _fp(noise) if noise is not None else None)
         if rc != 0:
             raise RuntimeError(f"b200_submit failed: {rc}")

@@ -104,9 +104,9 @@ struct b200_engine {
     ShiftAll shifts{};
     // pinned staging
     float* pin_f = nullptr; int* pin_i = nullptr; size_t pin_f_n = 0, pin_i_n = 0;
-    // b200_submit / b200_collect: two frames in flight, one pinned staging set per parity
+    // b200_submit / b200_collect: up to three frames in flight, a ring of four pinned staging sets
     struct Pending { float* noise = nullptr; float* pcm = nullptr; int* produced = nullptr; size_t cap = 0; int slot0 = 0, n = 0; bool busy = false;
-                     cudaEvent_t done_main = nullptr, done_mimi = nullptr; } pend[2];
+                     cudaEvent_t done_main = nullptr, done_mimi = nullptr; } pend[4];
     unsigned long long submit_t = 0, collect_t = 0;
     TcPlanCache* tc = nullptr;
     // optional per-segment device timing (bench.py roofline leg): event pairs recorded on the engine stream
@@ -495,7 +495,7 @@ struct b200_engine {
         PTTS_CUDA_CHECK(cudaEventRecord(ev_mimi[f.par], stream_m));
         ev_mimi_valid[f.par] = true; mimi_pending = true; last_mimi_par = f.par;
         if (f.tag >= 0) {   // b200_submit frame: its PCM copy follows its Mimi decode on the Mimi stream
-            auto& pd = pend[f.tag & 1];
+            auto& pd = pend[f.tag & 3];
             PTTS_CUDA_CHECK(cudaMemcpyAsync(pd.pcm, pcm + (size_t)f.slot0 * FRAME, (size_t)f.n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, stream_m));
             PTTS_CUDA_CHECK(cudaEventRecord(pd.done_mimi, stream_m));
             PTTS_CUDA_CHECK(cudaEventRecord(ev_mimi[f.par], stream_m));      // later joins must cover the copy as well
@@ -974,13 +974,14 @@ int b200_step(b200_engine* e, int slot0, int n, const float* noise, float* pcm, 
 
 // Pipelined form of b200_step for throughput serving: b200_submit(t) enqueues frame t (H2D noise, FlowLM part on the main stream, Mimi
 // body on the Mimi stream, D2H of PCM / flags into pinned staging) and returns immediately; b200_collect() blocks until the OLDEST
-// submitted frame is complete and copies it out. At most two frames may be in flight (submit returns B200_ESTATE otherwise), so the
-// Mimi decode + copies of frame t overlap the FlowLM step of frame t+1. Frames come back in submission order.
+// submitted frame is complete and copies it out. At most three frames may be in flight (submit returns B200_ESTATE otherwise): the Mimi
+// decode of frame t is interleaved with the FlowLM step of frame t+1 (run_step), so a caller that keeps two submits ahead of its
+// collects never leaves the GPU waiting for the host. Frames come back in submission order.
 int b200_submit(b200_engine* e, int slot0, int n, const float* noise) {
     if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots) return B200_EINVAL;
-    if (e->submit_t - e->collect_t >= 2) return B200_ESTATE;
+    if (e->submit_t - e->collect_t >= 3) return B200_ESTATE;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
-    auto& pd = e->pend[e->submit_t & 1];
+    auto& pd = e->pend[e->submit_t & 3];
     if (pd.cap < (size_t)n) {
         if (pd.noise) cudaFreeHost(pd.noise); if (pd.pcm) cudaFreeHost(pd.pcm); if (pd.produced) cudaFreeHost(pd.produced);
         PTTS_CUDA_CHECK(cudaMallocHost(&pd.noise, (size_t)n * LDIM * sizeof(float)));
@@ -1008,7 +1009,7 @@ int b200_collect(b200_engine* e, float* pcm, int32_t* produced) {
     if (!e || !pcm || !produced) return B200_EINVAL;
     if (e->collect_t == e->submit_t) return B200_ESTATE;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
-    auto& pd = e->pend[e->collect_t & 1];
+    auto& pd = e->pend[e->collect_t & 3];
     if (e->pending.valid && e->pending.tag == (long long)e->collect_t) e->flush_pending();   // nobody submitted after it: decode it now
     PTTS_CUDA_CHECK(cudaEventSynchronize(pd.done_main));
     PTTS_CUDA_CHECK(cudaEventSynchronize(pd.done_mimi));

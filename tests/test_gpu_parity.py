@@ -208,12 +208,14 @@ def test_pipelined_submit_collect_matches_step(ctx, oracle_mod):
     pcm = np.zeros((3, 1920), np.float32); prod = np.zeros(3, np.int32)
     got = []
     eng.submit(0, 3, noise[0])
-    for i in range(1, 8):
-        eng.submit(0, 3, noise[i])
+    eng.submit(0, 3, noise[1])
+    for i in range(2, 8):
+        eng.submit(0, 3, noise[i])                            # submits stay two frames ahead of collects
         assert eng.collect_into(pcm, prod) == 3
         got.append((pcm.copy(), prod.copy()))
-    assert eng.collect_into(pcm, prod) == 3
-    got.append((pcm.copy(), prod.copy()))
+    for _ in range(2):
+        assert eng.collect_into(pcm, prod) == 3
+        got.append((pcm.copy(), prod.copy()))
     for i in range(8):
         assert np.array_equal(got[i][1], ref[i][1])
         assert np.array_equal(got[i][0], ref[i][0]), i
