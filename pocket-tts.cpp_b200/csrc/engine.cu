@@ -958,8 +958,10 @@ int b200_step(b200_engine* e, int slot0, int n, const float* noise, float* pcm, 
         memcpy(p_noise, noise, (size_t)n * LDIM * sizeof(float));
         PTTS_CUDA_CHECK(cudaMemcpyAsync(e->noise_inj, p_noise, (size_t)n * LDIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     }
-    e->run_step(slot0, n, noise != nullptr);
-    e->join_mimi();                                           // synchronous API: this frame's PCM is returned by this call
+    // synchronous API: this frame's PCM is returned by this call, so there is nothing to overlap - replay the whole step as ONE graph
+    // on the main stream (13 graph launches + events per frame would only add host latency, which is what batch-1 streaming feels)
+    e->join_mimi();
+    e->run_graphed(0, slot0, n, noise != nullptr);
     PTTS_CUDA_CHECK(cudaMemcpyAsync(p_pcm, e->pcm + (size_t)slot0 * FRAME, (size_t)n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     PTTS_CUDA_CHECK(cudaMemcpyAsync(e->pin_i, e->produced, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     if (latents) PTTS_CUDA_CHECK(cudaMemcpyAsync(p_lat, e->latent, (size_t)n * LDIM * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
