@@ -507,7 +507,9 @@ struct b200_engine {
         const PendingFrame f = pending; pending.valid = false;
         if (debug_skip_mimi) return;
         PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream_m, ev_main[f.par], 0));
+        tc->coreside = tc->coreside_allowed;                  // same graphs (same launch shapes) as the interleaved form
         for (int c = 0; c < N_MCHUNK; c++) mimi_chunk_on_side(f, c);
+        tc->coreside = false;
         finish_mimi_frame(f);
     }
     // Main stream waits for everything enqueued on the Mimi stream (before any non-pipelined use of Mimi state / PCM on the main stream).
@@ -522,6 +524,7 @@ struct b200_engine {
     void run_step(int slot0, int n, bool injected, long long tag = -1) {
         if (!cfg.overlap || !cfg.cuda_graphs || profiling) { join_mimi(); run_graphed(0, slot0, n, injected); return; }
         const int par = (int)(pipe_t & 1);
+        struct CoresideScope { TcPlanCache* c; CoresideScope(TcPlanCache* c_) : c(c_) { c->coreside = c->coreside_allowed; } ~CoresideScope() { c->coreside = false; } } cs_scope(tc);
         PendingFrame prev = pending; pending.valid = false;
         if (prev.valid && (prev.slot0 != slot0 || prev.n != n)) { pending = prev; flush_pending(); prev.valid = false; }   // different slot range: no interleave
         if (debug_skip_mimi) prev.valid = false;

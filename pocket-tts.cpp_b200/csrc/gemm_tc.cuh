@@ -557,7 +557,8 @@ struct TcPlanCache {
     PFN_tmapEncodeTiled encode = nullptr;
     std::map<std::tuple<const void*, long long, long long, long long, long long, int, int>, CUtensorMap> maps;
     int num_sms = 148;
-    bool coreside = true;       // see tc_gemm_launch (PTTS_B200_CORESIDE=0 restores deep rings / two Mimi CTAs per SM)
+    bool coreside = false;      // see tc_gemm_launch; switched on by the engine while it enqueues the two-stream pipeline
+    bool coreside_allowed = true;   // PTTS_B200_CORESIDE=0: never (deep rings / two Mimi CTAs per SM everywhere)
     bool pdl = false;
     float* ws_buf[2] = {nullptr, nullptr}; size_t ws_elems = (size_t)32 << 20;   // split-K partial sums, one workspace per engine stream
     int cur_ws = 0;
@@ -567,7 +568,7 @@ inline TcPlanCache* tc_plan_cache_create() {
     auto* c = new TcPlanCache;
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) c->encode = (PFN_tmapEncodeTiled)fn;
-    if (const char* v = getenv("PTTS_B200_CORESIDE")) c->coreside = atoi(v) != 0;
+    if (const char* v = getenv("PTTS_B200_CORESIDE")) c->coreside_allowed = atoi(v) != 0;
     // every (tile width, epilogue class) instantiation: opt in to the large dynamic smem and the uniform carve-out (see engine.cu)
     for (int bn : {128, 64, 32}) {
         const int st1 = bn == 128 ? TcCfg<128>::STAGES_1CTA : bn == 64 ? TcCfg<64>::STAGES_1CTA : TcCfg<32>::STAGES_1CTA;
@@ -643,6 +644,13 @@ inline TcPlan tc_plan(int tiles_m, int R, int N, int K, int num_sms, bool want_l
             }
         }
         return best;
+    }
+    if (const char* ov = getenv("PTTS_B200_PLAN")) {           // tuning hook for large GEMMs: "NxK=BNx1"
+        char key[64]; snprintf(key, sizeof key, "%dx%d=", N, K);
+        if (const char* q = strstr(ov, key)) {
+            int bn = 0, sp = 0;
+            if (sscanf(q + strlen(key), "%dx%d", &bn, &sp) == 2 && (bn == 32 || bn == 64 || bn == 128) && N % bn == 0) return TcPlan{bn, 1};
+        }
     }
     for (int bn : {128, 64, 32}) {
         if (N % bn != 0) continue;
