@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 OUT = os.path.join(OUT_DIR, "libptts_b200.so")
+CLI = os.path.join(OUT_DIR, "pocket-tts-b200")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["engine.cu", "host_api.cpp"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
@@ -34,6 +35,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         subprocess.check_call(cmd)
         objs.append(o)
     subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    # command-line driver over the reference API: plain C++, linked against the library just built
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", os.path.join(CSRC, "cli_main.cpp"), "-o", CLI, "-L" + OUT_DIR, "-lptts_b200",
+                           "-Wl,-rpath,$ORIGIN"])
     return OUT
 
 
