@@ -36,7 +36,7 @@ typedef struct b200_config {
     int convt_split;      /* 1 = transposed convs see hi+lo f16 activations (~fp32; reference conv.h:282 is f32); 0 (default) = f16
                              activations like every other conv: Mimi-only SNR 63.8 vs 65.9 dB, full-pipeline SNR unchanged (46.5 dB) */
     int gemm_path;        /* 0 = auto (tcgen05 for large row counts), 1 = CUDA-core only (validation path)          */
-    int max_prefill_rows; /* rows per prefill chunk (0 = default 512)                                               */
+    int max_prefill_rows; /* rows per prefill chunk (0 = default 2048)                                              */
     int cuda_graphs;      /* 1 = replay the per-frame step as a CUDA graph (captured on second use of a shape)       */
     int pdl;              /* 1 = programmatic dependent launch: each kernel's prologue overlaps its predecessor's tail  */
     int overlap;          /* 1 = two-stream pipeline: the Mimi decode of frame t overlaps the FlowLM step of frame t+1   */

@@ -104,6 +104,7 @@ struct b200_engine {
     ShiftAll shifts{};
     // pinned staging
     float* pin_f = nullptr; int* pin_i = nullptr; size_t pin_f_n = 0, pin_i_n = 0;
+    int* begin_meta = nullptr; float* begin_temp = nullptr; size_t begin_cap = 0;   // device copy of b200_begin_sentences' per-sentence metadata
     // b200_submit / b200_collect: up to three frames in flight, a ring of four pinned staging sets
     struct Pending { float* noise = nullptr; float* pcm = nullptr; int* produced = nullptr; size_t cap = 0; int slot0 = 0, n = 0; bool busy = false;
                      cudaEvent_t done_main = nullptr, done_mimi = nullptr; } pend[4];
@@ -562,6 +563,43 @@ __global__ void set_meta_kernel(int slot, int cur, int mg, int f, float t, const
     if (i < LDIM) { lat_f32[slot * LDIM + i] = bos[i]; lat_in_bf16[slot * LDIM + i] = __float2bfloat16_rn(bos[i]); }
 }
 
+// Batched sentence start (b200_begin_sentences): one launch each for all n sentences instead of three launches per sentence.
+// meta = [slot | src voice slot | prefix rows | cur_len | max_gen | frames_after_eos] x n (ints), temps[n].
+__global__ void begin_meta_kernel(int n, const int* __restrict__ meta, const float* __restrict__ temps, const float* bos, int* cur_len, int* gen_step, int* eos_step,
+                                  int* max_gen, int* fae, int* active, float* temp, __nv_bfloat16* lat_in_bf16, float* lat_f32) {
+    const int j = blockIdx.x, i = threadIdx.x;
+    if (j >= n) return;
+    const int slot = meta[j], cur = meta[3 * n + j], mg = meta[4 * n + j], f = meta[5 * n + j];
+    if (i == 0) { cur_len[slot] = cur; gen_step[slot] = 0; eos_step[slot] = -1; max_gen[slot] = mg; fae[slot] = f; active[slot] = mg > 0 ? 1 : 0; temp[slot] = temps[j]; }
+    if (i < LDIM) { lat_f32[slot * LDIM + i] = bos[i]; lat_in_bf16[slot * LDIM + i] = __float2bfloat16_rn(bos[i]); }
+}
+__global__ void begin_copy_prefix_kernel(int n, const int* __restrict__ meta, char* kc, char* vc, long long slot_bytes, long long layer_bytes, long long row_bytes) {
+    const int j = blockIdx.z;
+    const int dst_slot = meta[j], src_slot = meta[n + j];
+    const long long n16 = (long long)meta[2 * n + j] * row_bytes / 16;
+    char* base = (blockIdx.y & 1) ? vc : kc;
+    const int layer = blockIdx.y >> 1;
+    const uint4* src = reinterpret_cast<const uint4*>(base + layer * layer_bytes + src_slot * slot_bytes);
+    uint4* dst = reinterpret_cast<uint4*>(base + layer * layer_bytes + dst_slot * slot_bytes);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {              // four independent 16-byte loads in flight per thread
+        const uint4 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+        dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    }
+    for (; i < n16; i += stride) dst[i] = src[i];
+}
+__global__ void begin_reset_kernel(int n, const int* __restrict__ meta, ShiftAll sa, float* __restrict__ e_prev, int* __restrict__ mimi_off) {
+    const int slot = meta[blockIdx.x];
+    const ShiftDesc d = sa.d[blockIdx.y];
+    __half* base = d.buf + (long long)slot * d.slot_stride;
+    for (int i = threadIdx.x; i < d.S * d.C; i += blockDim.x) base[i] = __float2half_rn(0.f);
+    if (blockIdx.y == 0) {
+        for (int i = threadIdx.x; i < M_DIM; i += blockDim.x) e_prev[(long long)slot * M_DIM + i] = 0.f;
+        if (threadIdx.x == 0) mimi_off[slot] = 0;
+    }
+}
+
 // copy_states (reference models/flow_lm.h:70-78): restore the voice-conditioned prefix rows [0, len) of every layer.
 __global__ void copy_prefix_kernel(char* kc, char* vc, long long slot_bytes, long long layer_bytes, int dst_slot, int src_slot, long long bytes) {
     pdl_prologue();
@@ -589,7 +627,7 @@ extern "C" {
 void b200_default_config(b200_config* c) {
     memset(c, 0, sizeof(*c));
     c->device = 0; c->max_slots = 1; c->max_voices = 8; c->kv_capacity = 2048; c->kv_f32 = 0; c->mimi_mask_mode = 0;
-    c->convt_split = 0; c->gemm_path = 0; c->max_prefill_rows = 512; c->cuda_graphs = 1; c->pdl = 1; c->overlap = 1;
+    c->convt_split = 0; c->gemm_path = 0; c->max_prefill_rows = 2048; c->cuda_graphs = 1; c->pdl = 1; c->overlap = 1;
 }
 
 int b200_engine_create(const b200_config* cfg, b200_engine** out) {
@@ -600,7 +638,7 @@ int b200_engine_create(const b200_config* cfg, b200_engine** out) {
         return B200_ESTATE;
     }
     auto* e = new b200_engine; e->cfg = *cfg;
-    if (e->cfg.max_prefill_rows <= 0) e->cfg.max_prefill_rows = 512;
+    if (e->cfg.max_prefill_rows <= 0) e->cfg.max_prefill_rows = 2048;
     if (e->cfg.max_voices < 1) e->cfg.max_voices = 1;
     PTTS_CUDA_CHECK(cudaSetDevice(cfg->device));
     {   // the FlowLM chain is the critical path of a frame: it gets the higher priority, the Mimi decode fills the gaps
@@ -897,25 +935,38 @@ int b200_begin_sentences(b200_engine* e, int n, const int32_t* slots, const int3
             rs.push_back(slot); rp.push_back(start + t); rt.push_back(id);
         }
     }
-    const float* bos = e->d_bos;
-    for (int i = 0; i < n; i++) {
-        const int slot = slots[i], v = voices[i];
-        const int nt = tok_off[i + 1] - tok_off[i];
-        const int start = e->voice_len[v];
-        if (start > 0) {
-            const long long bytes = (long long)start * D_MODEL * elt;
-            launch_k(false, copy_prefix_kernel, dim3(16, 2 * N_LAYERS), dim3(256), (size_t)(0), e->stream, (char*)e->kc, (char*)e->vc, e->kv_slot_stride * elt, e->kv_layer_stride * elt,
-                                                                               slot, e->cfg.max_slots + v, bytes);
+    if (n > 0) {
+        // per-sentence metadata in one upload: [slot | src voice slot | prefix rows | cur_len | max_gen | frames_after_eos] x n, then temps
+        e->ensure_pinned((size_t)n, (size_t)6 * n);
+        PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));       // pinned staging may still feed an earlier copy
+        int max_prefix = 0;
+        for (int i = 0; i < n; i++) {
+            const int slot = slots[i], v = voices[i];
+            const int nt = tok_off[i + 1] - tok_off[i];
+            const int start = e->voice_len[v];
+            // KV capacity guard (the reference has none: 1000 rows, no bounds check, src/pocket_tts.cpp:367): clamp the cap.
+            int mg = max_gen_len[i];
+            const int room = e->cfg.kv_capacity - (start + nt);
+            if (mg > room) mg = room;
+            e->pin_i[i] = slot; e->pin_i[n + i] = e->cfg.max_slots + v; e->pin_i[2 * n + i] = start; e->pin_i[3 * n + i] = start + nt;
+            e->pin_i[4 * n + i] = mg; e->pin_i[5 * n + i] = frames_after_eos[i];
+            e->pin_f[i] = temp[i];
+            e->h_cur_len[slot] = start + nt;
+            max_prefix = std::max(max_prefix, start);
         }
-        launch_k(false, reset_slot_kernel, dim3(1, e->shifts.n), dim3(256), (size_t)(0), e->stream, e->shifts, slot, e->e_prev, e->mimi_off);
-        // KV capacity guard (the reference has none: 1000 rows, no bounds check, src/pocket_tts.cpp:367): clamp the cap.
-        int mg = max_gen_len[i];
-        const int room = e->cfg.kv_capacity - (start + nt);
-        if (mg > room) mg = room;
-        launch_k(false, set_meta_kernel, dim3(1), dim3(32), (size_t)(0), e->stream, slot, start + nt, mg, frames_after_eos[i], temp[i], bos, e->cur_len, e->gen_step, e->eos_step,
-                                                 e->max_gen, e->fae, e->active, e->temp, e->lat_in_bf16, e->lat_f32);
-        e->h_cur_len[slot] = start + nt;
+        if ((size_t)n > e->begin_cap) {
+            e->begin_meta = e->dalloc<int>((size_t)6 * n, false); e->begin_temp = e->dalloc<float>((size_t)n, false); e->begin_cap = n;
+        }
+        PTTS_CUDA_CHECK(cudaMemcpyAsync(e->begin_meta, e->pin_i, (size_t)6 * n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        PTTS_CUDA_CHECK(cudaMemcpyAsync(e->begin_temp, e->pin_f, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        if (max_prefix > 0)
+            launch_k(false, begin_copy_prefix_kernel, dim3(8, 2 * N_LAYERS, n), dim3(256), (size_t)0, e->stream, n, (const int*)e->begin_meta, (char*)e->kc, (char*)e->vc,
+                     (long long)(e->kv_slot_stride * elt), (long long)(e->kv_layer_stride * elt), (long long)(D_MODEL * elt));
+        launch_k(false, begin_reset_kernel, dim3(n, e->shifts.n), dim3(256), (size_t)0, e->stream, n, (const int*)e->begin_meta, e->shifts, e->e_prev, e->mimi_off);
+        launch_k(false, begin_meta_kernel, dim3(n), dim3(32), (size_t)0, e->stream, n, (const int*)e->begin_meta, (const float*)e->begin_temp, (const float*)e->d_bos, e->cur_len,
+                 e->gen_step, e->eos_step, e->max_gen, e->fae, e->active, e->temp, e->lat_in_bf16, e->lat_f32);
         e->launches += 3;
+        PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));       // prefill_rows reuses the pinned staging
     }
     if (!rs.empty()) prefill_rows(e, rs, rp, &rt, nullptr);
     return B200_OK;
