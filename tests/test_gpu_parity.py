@@ -247,3 +247,26 @@ def test_batch64_tensor_core_path_matches_oracle(P, model_dir, orc, oracle_mod):
         # (max_prefill_rows) may see another split-K plan, i.e. another (equally valid) summation order, hence the tolerance for slot 63
         assert np.array_equal(gp[0], gp[1]) and np.array_equal(glat[0], glat[1])
         assert np.abs(glat[0] - glat[B - 1]).max() < LAT_MAXABS and snr_db(gp[0], gp[B - 1]) > SNR_MIN
+
+
+@pytest.mark.parametrize("opts", [dict(convt_split=1), dict(kv_f32=1), dict(overlap=0, cuda_graphs=0), dict(pdl=0), dict(pdl=2)],
+                         ids=["convt_split", "kv_f32_tc", "eager_single_stream", "no_pdl", "pdl_everywhere"])
+def test_engine_options_keep_parity(opts, P, model_dir, orc, oracle_mod):
+    """Every engine option runs the full pipeline within the stated tolerances (batch 16: tensor-core GEMMs everywhere)."""
+    B = 16
+    c = P.Context(model_dir, max_slots=B, kv_capacity=512, **opts)
+    eng = c.engine
+    st = c.stream("cosette", temp=0.7)
+    toks = c.tokenize(BENCH_SENTENCE)
+    eng.begin_sentences(list(range(B)), [st.voice] * B, [toks] * B, [oracle_mod.max_gen_len_for(BENCH_SENTENCE)] * B,
+                        [oracle_mod.frames_after_eos_guess(BENCH_SENTENCE)] * B, [0.7] * B)
+    os_ = orc.stream("cosette", kv_capacity=512)
+    os_.sentence_init(BENCH_SENTENCE)
+    rng = np.random.default_rng(5)
+    for i in range(5):
+        noise = (rng.standard_normal(32) * np.sqrt(0.7)).astype(np.float32)
+        ok, lat, pcm, e = os_.step(noise)
+        gp, prod, glat, geos = eng.step(0, B, np.stack([noise] * B))
+        assert ok and prod.all()
+        assert np.abs(glat[B - 1] - lat).max() < LAT_MAXABS and np.linalg.norm(glat[B - 1] - lat) / np.linalg.norm(lat) < LAT_REL, i
+        assert snr_db(pcm, gp[B - 1]) > SNR_MIN, i
