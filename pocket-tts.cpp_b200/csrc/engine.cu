@@ -405,11 +405,6 @@ struct b200_engine {
         seg_end(s_sea);
     }
 
-    void prepare_flow(int slot0, int n) {
-        launch_k(pdl_active, prepare_flow_kernel, dim3((n * 32 + 255) / 256), dim3(256), (size_t)(0), stream, slot0, n, (const int*)cur_len, (const float*)freq_flow, row_slot, row_pos, cs);
-        launches++;
-    }
-
     // One generation step for slots [slot0, slot0+n) (reference _stream_sentence_step, src/pocket_tts.cpp:446-492).
     // FlowLM step + head + stop rule + Mimi front end (everything that consumes / produces the latent hand-off), cut into N_LAYERS + 1
     // segments: segment l < 6 ends with the attention kernel of layer l, segment 6 is the rest. seg < 0 enqueues all of them.
@@ -563,7 +558,8 @@ __global__ void set_meta_kernel(int slot, int cur, int mg, int f, float t, const
     if (i < LDIM) { lat_f32[slot * LDIM + i] = bos[i]; lat_in_bf16[slot * LDIM + i] = __float2bfloat16_rn(bos[i]); }
 }
 
-// Batched sentence start (b200_begin_sentences): one launch each for all n sentences instead of three launches per sentence.
+// Batched sentence start (b200_begin_sentences; reference _stream_sentence_init src/pocket_tts.cpp:416-444, copy_states models/flow_lm.h:70-78,
+// init(mimi_states) models/mimi.h:71-75): one launch each for all n sentences instead of three launches per sentence.
 // meta = [slot | src voice slot | prefix rows | cur_len | max_gen | frames_after_eos] x n (ints), temps[n].
 __global__ void begin_meta_kernel(int n, const int* __restrict__ meta, const float* __restrict__ temps, const float* bos, int* cur_len, int* gen_step, int* eos_step,
                                   int* max_gen, int* fae, int* active, float* temp, __nv_bfloat16* lat_in_bf16, float* lat_f32) {
@@ -598,23 +594,6 @@ __global__ void begin_reset_kernel(int n, const int* __restrict__ meta, ShiftAll
         for (int i = threadIdx.x; i < M_DIM; i += blockDim.x) e_prev[(long long)slot * M_DIM + i] = 0.f;
         if (threadIdx.x == 0) mimi_off[slot] = 0;
     }
-}
-
-// copy_states (reference models/flow_lm.h:70-78): restore the voice-conditioned prefix rows [0, len) of every layer.
-__global__ void copy_prefix_kernel(char* kc, char* vc, long long slot_bytes, long long layer_bytes, int dst_slot, int src_slot, long long bytes) {
-    pdl_prologue();
-    char* base = (blockIdx.y & 1) ? vc : kc;
-    const int layer = blockIdx.y >> 1;
-    const uint4* src = reinterpret_cast<const uint4*>(base + layer * layer_bytes + src_slot * slot_bytes);
-    uint4* dst = reinterpret_cast<uint4*>(base + layer * layer_bytes + dst_slot * slot_bytes);
-    const long long n = bytes / 16;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
-}
-
-__global__ void copy_rows_f32_kernel(const float* src, float* dst, long long n) {
-    pdl_prologue();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[i];
 }
 
 }  // namespace
@@ -857,12 +836,12 @@ int b200_finalize_weights(b200_engine* e) {
     // Keep the shared-memory carve-out identical for every kernel of the step: mixed carve-outs force an SM reconfiguration
     // between consecutive launches, which shows up as microseconds of idle time on the ~100 small kernels of a frame.
     {
-        const void* ks[] = {(const void*)prepare_flow_kernel, (const void*)prepare_mimi_kernel, (const void*)rope_table_kernel, (const void*)gemm_ffma_kernel<__nv_bfloat16>, (const void*)gemm_ffma_kernel<__half>,
+        const void* ks[] = {(const void*)prepare_mimi_kernel, (const void*)rope_table_kernel, (const void*)gemm_ffma_kernel<__nv_bfloat16>, (const void*)gemm_ffma_kernel<__half>,
                             (const void*)gemv_small_kernel<__nv_bfloat16, 8>, (const void*)gemv_small_kernel<__half, 8>, (const void*)layernorm_kernel<D_MODEL>,
                             (const void*)layernorm_kernel<D_FLOW>, 
                             (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
-                            (const void*)attn_flow_split_kernel, (const void*)attn_flow_merge_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
-                            (const void*)step_logic_kernel, (const void*)step_front_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma_kernel, (const void*)attn_mimi_mma4_kernel, (const void*)cast_f16_kernel,
+                            (const void*)attn_flow_split_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
+                            (const void*)step_front_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma4_kernel,
                             (const void*)conv_n1_kernel, (const void*)shift_states_kernel};
         for (const void* k : ks) PTTS_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }

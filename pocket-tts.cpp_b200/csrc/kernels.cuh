@@ -18,18 +18,6 @@ __global__ void rope_table_kernel(const int* __restrict__ row_pos, const float* 
     cs[idx] = make_float2(cosf(rad), sinf(rad));
 }
 
-// Decode step, FlowLM side: one row per slot in [slot0, slot0+n): slot, position and the row's RoPE table in one launch.
-__global__ void prepare_flow_kernel(int slot0, int n, const int* __restrict__ cur_len, const float* __restrict__ freq,
-                                    int* __restrict__ row_slot, int* __restrict__ row_pos, float2* __restrict__ cs) {
-    pdl_prologue();
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * 32) return;
-    const int r = idx >> 5, i = idx & 31, pos = cur_len[slot0 + r];
-    if (i == 0) { row_slot[r] = slot0 + r; row_pos[r] = pos; }
-    const float rad = (float)pos * freq[i];
-    cs[idx] = make_float2(cosf(rad), sinf(rad));
-}
-
 // Decode step, Mimi side: 16 rows per slot (positions mimi_off .. mimi_off+15) and their RoPE table.
 __global__ void prepare_mimi_kernel(int slot0, int n, const int* __restrict__ mimi_off, const float* __restrict__ freq,
                                     int* __restrict__ mrow_slot, int* __restrict__ mrow_pos, float2* __restrict__ mcs) {
@@ -362,27 +350,6 @@ __global__ void __launch_bounds__(288, 2) attn_flow_split_kernel(const float* __
     }
 }
 
-__global__ void __launch_bounds__(256) attn_flow_merge_kernel(const float* __restrict__ ws_ml, const float* __restrict__ ws_acc, int splits,
-                                                              __nv_bfloat16* __restrict__ out) {
-    pdl_prologue();
-    const int row = blockIdx.x, t = threadIdx.x, h = t >> 4;
-    float M = -INFINITY;
-    for (int s = 0; s < splits; s++) M = fmaxf(M, ws_ml[((long long)row * splits + s) * 32 + h]);
-    float L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < splits; s++) {
-        const long long wo = (long long)row * splits + s;
-        const float ms = ws_ml[wo * 32 + h];
-        const float sc = (ms == -INFINITY) ? 0.f : expf(ms - M);
-        L = fmaf(ws_ml[wo * 32 + 16 + h], sc, L);
-        const float4 a = *reinterpret_cast<const float4*>(ws_acc + wo * D_MODEL + 4 * t);
-        o[0] = fmaf(a.x, sc, o[0]); o[1] = fmaf(a.y, sc, o[1]); o[2] = fmaf(a.z, sc, o[2]); o[3] = fmaf(a.w, sc, o[3]);
-    }
-    const float inv = 1.0f / L;
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0] * inv, o[1] * inv), p1 = __floats2bfloat162_rn(o[2] * inv, o[3] * inv);
-    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-    *reinterpret_cast<uint2*>(out + (long long)row * D_MODEL + 4 * t) = pk;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Mimi ring attention: 16 queries of one slot x all 250 ring slots, additive 0/-inf bias taken from the
 // reference's pattern (src/torch.h:168-221, called with the chunk's START offset, mimi_transformer.h:1198).
@@ -496,16 +463,14 @@ __global__ void __launch_bounds__(256) attn_mimi_kernel(const __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// Mimi ring attention on the warp-level tensor cores (mma.sync m16n8k16, bf16 x bf16 -> f32): the 16 queries of one
-// (slot, head) are exactly one M = 16 tile, so ONE WARP does a whole (slot, head): S = Q K^T as 32 key tiles of 8,
-// softmax, O = P V as 16 key steps x 8 output tiles. No shared memory and no ldmatrix: every global access is a 16-byte
-// vector load/store because the contraction index (and the output-dim index) may be permuted freely:
+// Mimi ring attention on the warp-level tensor cores (mma.sync m16n8k16, bf16 x bf16 -> f32): the 16 queries of one (slot, head) are
+// exactly one M = 16 tile: S = Q K^T as key tiles of 8, softmax, O = P V as key steps of 16 x 8 output tiles. No ldmatrix: every global
+// access is a 16-byte vector load/store because the contraction index (and the output-dim index) may be permuted freely:
 //   * QK^T: lane (g, t) loads K[key 8j+g][32p + 8t .. +7]; its 8 values are used as the k-slots of two k16 steps, and the
 //     Q fragments are loaded with the same permutation;
 //   * PV: output tile n holds dims {8c + n}, so lane (g, t) needs V[key][8g .. 8g+7] (one 16-byte load) for its four keys
 //     16s + {2t, 2t+1, 8+2t, 9+2t}; PRMT interleaves key pairs. The lane ends up owning O[q][16t .. 16t+15]: two 16-byte stores.
-// Two passes over K keep the reference's rounding point: pass 1 finds the exact row max and sum (online), pass 2 recomputes
-// the scores and rounds the NORMALISED probabilities to bf16 (ggml's bf16 mul_mat rounds its f32 operand), as attn_mimi_kernel.
+// The NORMALISED probabilities are rounded to bf16 before P V (ggml's bf16 mul_mat rounds its f32 operand), as in attn_mimi_kernel.
 // (tcgen05 cannot be used here: its minimum M is 64 and a CTA pair per 16-row problem would idle 3/4 of the datapath.)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -522,118 +487,11 @@ __device__ __forceinline__ MimiMaskRow mimi_mask_row(int offset, int j) {
 }
 __device__ __forceinline__ bool mimi_masked_fast(const MimiMaskRow& r, int c) { return c >= r.lo || (c > r.a && c <= r.b) || c >= M_CTX; }
 
-__global__ void __launch_bounds__(128) attn_mimi_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
-                                                            const __nv_bfloat16* __restrict__ vc, long long kv_slot_stride, int slot0, int n_slots,
-                                                            const int* __restrict__ mimi_off, int mask_mode, __nv_bfloat16* __restrict__ out) {
-    pdl_prologue();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int b = warp / M_HEADS, h = warp % M_HEADS;
-    if (b >= n_slots) return;
-    const int g = lane >> 2, t = lane & 3;
-    const int slot = slot0 + b;
-    const int offset = mimi_off[slot];
-    const __nv_bfloat16* K = kc + (long long)slot * kv_slot_stride + h * D_HEAD;
-    const __nv_bfloat16* V = vc + (long long)slot * kv_slot_stride + h * D_HEAD;
-    // Q fragments for the 4 (permuted) k16 steps: step 2p uses elements 0..3 of the 8-vector at dims 32p + 8t, step 2p+1 elements 4..7
-    uint32_t qa[4][4];
-#pragma unroll
-    for (int p = 0; p < 2; p++) {
-        const uint4 lo = *reinterpret_cast<const uint4*>(q + ((long long)b * M_T + g) * M_DIM + h * D_HEAD + 32 * p + 8 * t);
-        const uint4 hi = *reinterpret_cast<const uint4*>(q + ((long long)b * M_T + g + 8) * M_DIM + h * D_HEAD + 32 * p + 8 * t);
-        qa[2 * p][0] = lo.x; qa[2 * p][1] = hi.x; qa[2 * p][2] = lo.y; qa[2 * p][3] = hi.y;
-        qa[2 * p + 1][0] = lo.z; qa[2 * p + 1][1] = hi.z; qa[2 * p + 1][2] = lo.w; qa[2 * p + 1][3] = hi.w;
-    }
-    const MimiMaskRow mr0 = mimi_mask_row(offset, g), mr1 = mimi_mask_row(offset, g + 8);
-    auto score_tile = [&](int j, float (&sc)[4]) {
-        sc[0] = sc[1] = sc[2] = sc[3] = 0.f;
-        const int krow = min(8 * j + g, M_CTX - 1);                         // keys 250..255 do not exist: clamp the address, mask below
-        const __nv_bfloat16* kr = K + (long long)krow * M_DIM + 8 * t;
-#pragma unroll
-        for (int p = 0; p < 2; p++) {
-            const uint4 kv = *reinterpret_cast<const uint4*>(kr + 32 * p);
-            mma_bf16_16816(sc, qa[2 * p], kv.x, kv.y);
-            mma_bf16_16816(sc, qa[2 * p + 1], kv.z, kv.w);
-        }
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int c = 8 * j + 2 * t + e;
-            bool m0, m1;
-            if (mask_mode == 0) { m0 = mimi_masked_fast(mr0, c); m1 = mimi_masked_fast(mr1, c); }
-            else { m0 = c >= M_CTX || mimi_masked(offset, g, c, mask_mode); m1 = c >= M_CTX || mimi_masked(offset, g + 8, c, mask_mode); }
-            sc[e] = m0 ? -INFINITY : sc[e] * 0.125f;
-            sc[2 + e] = m1 ? -INFINITY : sc[2 + e] * 0.125f;
-        }
-    };
-    // ---- pass 1: exact row max and sum of exp (rows g and g+8), online over the 32 key tiles ----
-    float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    for (int j = 0; j < 32; j++) {
-        float sc[4];
-        score_tile(j, sc);
-        float t0 = fmaxf(sc[0], sc[1]), t1 = fmaxf(sc[2], sc[3]);
-        t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1)); t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
-        t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1)); t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
-        const float n0 = fmaxf(mx0, t0), n1 = fmaxf(mx1, t1);
-        float s0 = (n0 == -INFINITY) ? 0.f : expf(sc[0] - n0) + expf(sc[1] - n0);
-        float s1 = (n1 == -INFINITY) ? 0.f : expf(sc[2] - n1) + expf(sc[3] - n1);
-        s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-        l0 = (n0 == -INFINITY) ? 0.f : l0 * expf(mx0 - n0) + s0;
-        l1 = (n1 == -INFINITY) ? 0.f : l1 * expf(mx1 - n1) + s1;
-        mx0 = n0; mx1 = n1;
-    }
-    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-    // ---- pass 2: probabilities (bf16-rounded after normalisation) and O = P V ----
-    float o[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; n++) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
-    for (int s = 0; s < 16; s++) {
-        float sa[4], sb[4];
-        score_tile(2 * s, sa);
-        score_tile(2 * s + 1, sb);
-        uint32_t pa[4];
-        {
-            __nv_bfloat162 x;
-            x = __floats2bfloat162_rn(expf(sa[0] - mx0) * inv0, expf(sa[1] - mx0) * inv0); pa[0] = *reinterpret_cast<uint32_t*>(&x);
-            x = __floats2bfloat162_rn(expf(sa[2] - mx1) * inv1, expf(sa[3] - mx1) * inv1); pa[1] = *reinterpret_cast<uint32_t*>(&x);
-            x = __floats2bfloat162_rn(expf(sb[0] - mx0) * inv0, expf(sb[1] - mx0) * inv0); pa[2] = *reinterpret_cast<uint32_t*>(&x);
-            x = __floats2bfloat162_rn(expf(sb[2] - mx1) * inv1, expf(sb[3] - mx1) * inv1); pa[3] = *reinterpret_cast<uint32_t*>(&x);
-        }
-        // V rows of this lane's four keys (clamped: keys >= 250 carry probability 0), dims 8g..8g+7
-        const int k0 = 16 * s + 2 * t;
-        const uint4 v0 = *reinterpret_cast<const uint4*>(V + (long long)min(k0, M_CTX - 1) * M_DIM + 8 * g);
-        const uint4 v1 = *reinterpret_cast<const uint4*>(V + (long long)min(k0 + 1, M_CTX - 1) * M_DIM + 8 * g);
-        const uint4 v2 = *reinterpret_cast<const uint4*>(V + (long long)min(k0 + 8, M_CTX - 1) * M_DIM + 8 * g);
-        const uint4 v3 = *reinterpret_cast<const uint4*>(V + (long long)min(k0 + 9, M_CTX - 1) * M_DIM + 8 * g);
-        const uint32_t a0[4] = {v0.x, v0.y, v0.z, v0.w}, a1[4] = {v1.x, v1.y, v1.z, v1.w}, a2[4] = {v2.x, v2.y, v2.z, v2.w}, a3[4] = {v3.x, v3.y, v3.z, v3.w};
-#pragma unroll
-        for (int w = 0; w < 4; w++) {
-            // dims 8g + 2w (low halves) and 8g + 2w + 1 (high halves): pair (key k0, key k0+1) and (key k0+8, key k0+9)
-            const uint32_t b0_lo = __byte_perm(a0[w], a1[w], 0x5410), b1_lo = __byte_perm(a2[w], a3[w], 0x5410);
-            const uint32_t b0_hi = __byte_perm(a0[w], a1[w], 0x7632), b1_hi = __byte_perm(a2[w], a3[w], 0x7632);
-            mma_bf16_16816(o[2 * w], pa, b0_lo, b1_lo);
-            mma_bf16_16816(o[2 * w + 1], pa, b0_hi, b1_hi);
-        }
-    }
-    // o[n][e] = O[g][8(2t+e) + n], o[n][2+e] = O[g+8][...]: the lane owns dims 16t .. 16t+15 of rows g and g+8
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-        __nv_bfloat162 pk[8];
-#pragma unroll
-        for (int e = 0; e < 2; e++)
-#pragma unroll
-            for (int n = 0; n < 8; n += 2) pk[e * 4 + n / 2] = __floats2bfloat162_rn(o[n][2 * r + e], o[n + 1][2 * r + e]);
-        __nv_bfloat16* dst = out + ((long long)b * M_T + g + 8 * r) * M_DIM + h * D_HEAD + 16 * t;
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(&pk[0]);
-        *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<uint4*>(&pk[4]);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Mimi ring attention, four warps per (slot, head): warp w owns ring slots 64w .. 64w+63 (eight key tiles). Same fragment tricks as
-// attn_mimi_mma_kernel, but K is read ONCE: the warp's 16 x 64 scores stay in registers while the row max / sum are combined across
-// the four warps through shared memory, then P (normalised, rounded to bf16 like ggml's bf16 mul_mat operand) x V for the warp's own
-// keys and a fixed-order (deterministic) sum of the four partial outputs. 4x more warps in flight than the one-warp version, which
-// left ~14 warps per SM to hide HBM latency (74 us per layer at 256 slots for 131 MB of K/V).
+// Mimi ring attention, four warps per (slot, head): warp w owns ring slots 64w .. 64w+63 (eight key tiles). K is read ONCE: the warp's
+// 16 x 64 scores stay in registers while the row max / sum are combined across the four warps through shared memory, then P (normalised,
+// rounded to bf16) x V for the warp's own keys and a fixed-order (deterministic) sum of the four partial outputs. A one-warp-per-(slot,
+// head) version of the same fragments left ~14 warps per SM to hide HBM latency: 74 us per layer at 256 slots for 131 MB of K/V, vs 35 us.
 // ------------------------------------------------------------------------------------------------
 constexpr int AM4_LD = 68;                                   // padded row of the partial-output buffers (floats)
 
@@ -943,43 +801,6 @@ __global__ void __launch_bounds__(256) flow_in_kernel(int slot0, int n, const __
     *reinterpret_cast<uint2*>(n_bf + (long long)r * D_MODEL + i * 4) = *reinterpret_cast<uint2*>(yb);
 }
 
-// Stop rule + bookkeeping after the head (reference src/pocket_tts.cpp:457-467,487-489). Per slot:
-//   eos_step = first step with logit+4 > 0; stop when gen_step >= eos_step + frames_after_eos; hard cap max_gen_len.
-// produced[r] = 1 when this step emits a frame. Also hands the new latent to the next step (bf16 copy = the
-// A operand of input_linear) and advances the FlowLM position.
-__global__ void step_logic_kernel(int slot0, int n, const float* __restrict__ eos, const float* __restrict__ latent,
-                                  int* __restrict__ cur_len, int* __restrict__ gen_step, int* __restrict__ eos_step,
-                                  const int* __restrict__ max_gen, const int* __restrict__ fae, int* __restrict__ active,
-                                  __nv_bfloat16* __restrict__ lat_in_bf16, float* __restrict__ lat_f32, int* __restrict__ produced,
-                                  float* __restrict__ eos_out) {
-    pdl_prologue();
-    const int r = blockIdx.x, slot = slot0 + r, i = threadIdx.x;
-    if (r >= n) return;
-    __shared__ int emit;
-    if (i == 0) {
-        int e = 0;
-        if (active[slot]) {
-            const int g = gen_step[slot];
-            int es = eos_step[slot];
-            if (eos[r] > 0.f && es == -1) es = g;
-            eos_step[slot] = es;
-            cur_len[slot] += 1;                                   // increment_states (pocket_tts.cpp:96)
-            if (es != -1 && g >= es + fae[slot]) { gen_step[slot] = max_gen[slot]; active[slot] = 0; }
-            else {
-                e = 1; gen_step[slot] = g + 1;
-                if (g + 1 >= max_gen[slot]) active[slot] = 0;     // next receive would hit the cap (pocket_tts.cpp:450-453,495)
-            }
-        }
-        emit = e; produced[r] = e; if (eos_out) eos_out[r] = eos[r];
-    }
-    __syncthreads();
-    if (emit && i < LDIM) {
-        const float v = latent[r * LDIM + i];
-        lat_f32[slot * LDIM + i] = v;
-        lat_in_bf16[slot * LDIM + i] = __float2bfloat16_rn(v);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Mimi front end: z = latent*emb_std + emb_mean; e = Wq . f16(z) (1x1 conv, f16 operands; reference
 // src/pocket_tts.cpp:472-478, models/mimi.h:77-83); depthwise x16 upsampler on one step with carried state
@@ -1010,8 +831,10 @@ __global__ void __launch_bounds__(512) mimi_front_kernel(int slot0, const float*
     }
 }
 
-// step_logic_kernel + mimi_front_kernel in one launch (decode step): the stop rule of slot r, the latent hand-off to the next FlowLM
-// step, and the Mimi front end on the latent this step produced.
+// Stop rule + bookkeeping after the head (reference src/pocket_tts.cpp:457-467,487-489) and the Mimi front end in one launch. Per slot:
+//   eos_step = first step with logit+4 > 0; stop when gen_step >= eos_step + frames_after_eos; hard cap max_gen_len.
+// produced[r] = 1 when this step emits a frame. Hands the new latent to the next step (bf16 copy = the A operand of input_linear),
+// advances the FlowLM position, then runs mimi_front_kernel's math on the latent this step produced.
 __global__ void __launch_bounds__(512) step_front_kernel(int slot0, int n, const float* __restrict__ eos, const float* __restrict__ latent,
                                                          int* __restrict__ cur_len, int* __restrict__ gen_step, int* __restrict__ eos_step,
                                                          const int* __restrict__ max_gen, const int* __restrict__ fae, int* __restrict__ active,
@@ -1060,15 +883,6 @@ __global__ void __launch_bounds__(512) step_front_kernel(int slot0, int n, const
         const float y = __fadd_rn(__fmul_rn(e, wup_t[k * M_DIM + c]), __fmul_rn(ep, wup_t[(16 + k) * M_DIM + c]));
         xo[(long long)k * M_DIM] = y + bias;
     }
-}
-
-// f32 [rows][C] -> f16 copy into a conv input buffer (rows placed after the state rows).
-__global__ void cast_f16_kernel(const float* __restrict__ x, RowMap xmap, __half* __restrict__ out, RowMap omap, int rps, int R, int C) {
-    pdl_prologue();
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)R * C) return;
-    const int row = (int)(idx / C), col = (int)(idx % C);
-    out[omap.off(row, rps) + col] = __float2half_rn(x[xmap.off(row, rps) + col]);
 }
 
 // End-of-step upkeep for the streaming convs: every conv input buffer is [slot][S + T][C] with the S carried
