@@ -38,7 +38,8 @@ typedef struct b200_config {
     int gemm_path;        /* 0 = auto (tcgen05 for large row counts), 1 = CUDA-core only (validation path)          */
     int max_prefill_rows; /* rows per prefill chunk (0 = default 2048)                                              */
     int cuda_graphs;      /* 1 = replay the per-frame step as a CUDA graph (captured on second use of a shape)       */
-    int pdl;              /* 1 = programmatic dependent launch: each kernel's prologue overlaps its predecessor's tail  */
+    int pdl;              /* programmatic dependent launch (a kernel's prologue overlaps its predecessor's tail): 0 = off, 1 = for up to
+                             128 utterances per step (default), 2 = always                                                      */
     int overlap;          /* 1 = two-stream pipeline: the Mimi decode of frame t overlaps the FlowLM step of frame t+1   */
 } b200_config;
 

@@ -447,9 +447,9 @@ struct b200_engine {
     // kind 0 = full generation step (one stream), 1 = Mimi-only decode, 2 = FlowLM segment `part` -> mx2[par], 3 = Mimi chunk `part`
     // from mx2[par]. Runs on the CURRENT `stream` member (the pipeline swaps in stream_m for kind 3).
     void run_graphed(int kind, int slot0, int n, bool injected, int par = 0, int part = 0) {
-        // PDL overlaps each kernel's prologue with its predecessor's tail: a large win when the step is launch/latency bound
-        // (batch 1), neutral once kernels fill the machine and the step is replayed as a graph.
-        pdl_small = cfg.pdl >= 2 || (cfg.pdl == 1 && n <= 8);    // every kernel of the step
+        // PDL overlaps each kernel's prologue (barrier init, TMEM allocation, weight prefetch) with its predecessor's tail: a win while
+        // the step is launch/latency bound (measured +2..7 % at batch 16-128), a loss once the kernels fill the machine (-10 % at 256).
+        pdl_small = cfg.pdl >= 2 || (cfg.pdl == 1 && n <= 128);  // every kernel of the step
         pdl_chain = cfg.pdl >= 2;
         set_pdl(pdl_small);
         auto body = [&]() {
