@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128) attn_flow_kernel(const float* __restrict_
 // FlowLM attention, split-KV streaming version for the bf16 cache (the dominant kernel at large batch: pure KV stream).
 // One CTA per (KV split, query row), all 16 heads at once so that every cache row is read as one contiguous 2 KB line.
 // Warp 8 lane 0 is the producer: it streams groups of 8 consecutive K rows and V rows (16 KB each, contiguous in the
-// cache) into a 4-stage shared-memory ring with cp.async.bulk + mbarrier complete_tx. Consumer warp w owns key w of each
+// cache) into a 3-stage shared-memory ring (two CTAs per SM: 192 KB in flight per SM) with cp.async.bulk + mbarrier complete_tx. Consumer warp w owns key w of each
 // stage: lane l, chunk i reads the 16 bytes at i*512 + l*16 of the row = 8 dims of head 4i + l/8, so a row is four
 // conflict-free LDS.128 per lane; the dot products are finished with three shuffles inside each 8-lane group; softmax is
 // the online (running max / sum) form in fp32. Partial (m, l, acc) per split go to a workspace and attn_flow_merge_kernel
