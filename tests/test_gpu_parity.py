@@ -1,7 +1,7 @@
 """GPU parity tests (run on the B200 box: pytest -m gpu). Everything goes through the C ABI of libptts_b200.so.
 
 Tolerances (north_star: bit-exact ids / frame counts; latents max-abs + relative error; waveform SNR >= 40 dB):
-  * latents: max-abs <= 6e-2 (latent scale ~4), relative L2 <= 2e-2 per frame  — two *correct* implementations of this
+  * latents: max-abs <= 4e-2 (latent scale ~4), relative L2 <= 1.5e-2 per frame (measured worst case 2.5e-2 / 6.8e-3)  — two *correct* implementations of this
     bf16/f16 pipeline already differ by ~1.5e-2 max-abs through rounding flips (see tests/test_oracle.py)
   * waveform: SNR >= 40 dB per frame against the oracle under identical injected noise
 Free-running comparisons use injected noise (temp 0.7): with temp 0 and RANDOM weights the latent feedback loop is
@@ -18,7 +18,7 @@ from conftest import BENCH_SENTENCE, REPO, snr_db
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(REPO, "tests", "golden")
-LAT_MAXABS, LAT_REL, SNR_MIN = 6e-2, 2e-2, 40.0
+LAT_MAXABS, LAT_REL, SNR_MIN = 4e-2, 1.5e-2, 40.0
 
 
 @pytest.fixture(scope="module")
@@ -52,7 +52,7 @@ def test_prefill_kv_and_free_running_noise(which, ctx, ctx_f32kv, orc, oracle_mo
     assert os_.sentence_init(BENCH_SENTENCE) == toks
     n_pos = os_.current_end
     assert c.engine.slot_position(st.slot) == n_pos                     # voice-embedding indexing / positions bit-exact
-    tol = 3e-2 if which == "f32kv" else 6e-2                            # bf16 cache adds 2^-9 relative rounding
+    tol = 3e-2 if which == "f32kv" else 6e-2                            # KV entries (scale ~8): bf16 cache adds 2^-9 relative rounding
     for layer in (0, 3, 5):
         for kv in (0, 1):
             assert np.abs(c.engine.read_kv(st.slot, layer, kv, n_pos) - os_.kv(layer, kv)).max() < tol
