@@ -223,6 +223,16 @@ struct b200_engine {
     }
 
     // FlowLM transformer over R rows held in `h` (reference modules/transformer.h:253-278,363-374).
+    // Batch 1-2 decode: LayerNorm fused into the GEMV that consumes it (gemv_ln_kernel); x = f32 rows [R][L.in].
+    bool ln_in_gemv(int R) const { return R <= 2 && cfg.gemm_path == 0; }
+    void lin_ln(const float* x, const LnArgs& ln, const LinW& L, int R, Epi epi) {
+        if (!epi.bias) epi.bias = L.b;
+        const int blocks = (L.out / 2 + 7) / 8;
+        if (L.in == D_MODEL) launch_k(pdl_active, gemv_ln_kernel<D_MODEL>, dim3(blocks), dim3(256), (size_t)0, stream, x, ln, (const __nv_bfloat16*)L.w, R, L.out, epi);
+        else launch_k(pdl_active, gemv_ln_kernel<D_FLOW>, dim3(blocks), dim3(256), (size_t)0, stream, x, ln, (const __nv_bfloat16*)L.w, R, L.out, epi);
+        launches++;
+    }
+
     // ---- FlowLM transformer over R rows held in `h` (reference modules/transformer.h:253-278,363-374), in two pieces per layer so that the
     //      decode step can be cut into segments at the end of every attention kernel (run_step) ----
     // in_proj (+RoPE, KV append) and attention of layer l. Expects norm1 of layer l in n_bf.
@@ -232,7 +242,8 @@ struct b200_engine {
         e.kv_slot_stride = kv_slot_stride; e.q_out_f32 = q;
         if (cfg.kv_f32) { e.kcache = (float*)kc + l * kv_layer_stride; e.vcache = (float*)vc + l * kv_layer_stride; }
         else { e.kcache = (__nv_bfloat16*)kc + l * kv_layer_stride; e.vcache = (__nv_bfloat16*)vc + l * kv_layer_stride; }
-        lin(n_bf, L.in_proj, R, e);
+        if (l > 0 && ln_in_gemv(R)) { LnArgs a; a.w = L.n1w; a.b = L.n1b; a.eps = 1e-5f; lin_ln(h, a, L.in_proj, R, e); }   // layer 0: flow_in_kernel wrote n_bf
+        else lin(n_bf, L.in_proj, R, e);
         const int sg = seg_begin(0);
         const bool pdl_saved = pdl_active;
         set_pdl(pdl_small);                                  // the KV-streaming kernel fills the machine: no early dependents around it
@@ -266,15 +277,17 @@ struct b200_engine {
         auto& L = fl[l];
         Epi eo; eo.resid = h; eo.resid_map = rows(D_MODEL); eo.out = h; eo.out_map = rows(D_MODEL);
         LnFuse f2; f2.w = L.n2w; f2.b = L.n2b; f2.eps = 1e-5f; f2.out = n_bf;
-        if (!lin(att_bf, L.out_proj, R, eo, &f2)) {
+        const bool fuse = ln_in_gemv(R);
+        if (!lin(att_bf, L.out_proj, R, eo, &f2) && !fuse) {
             launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
         }
         Epi e1; e1.out2 = ff_bf; e1.out2_map = rows(D_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
-        lin(n_bf, L.lin1, R, e1);
+        if (fuse) { LnArgs a; a.w = L.n2w; a.b = L.n2b; a.eps = 1e-5f; lin_ln(h, a, L.lin1, R, e1); }
+        else lin(n_bf, L.lin1, R, e1);
         Epi e2; e2.resid = h; e2.resid_map = rows(D_MODEL); e2.out = h; e2.out_map = rows(D_MODEL);
         if (l + 1 < N_LAYERS) {
             LnFuse f1; f1.w = fl[l + 1].n1w; f1.b = fl[l + 1].n1b; f1.eps = 1e-5f; f1.out = n_bf;
-            if (!lin(ff_bf, L.lin2, R, e2, &f1)) {
+            if (!lin(ff_bf, L.lin2, R, e2, &f1) && !fuse) {    // fused: the next in_proj normalises h itself (flow_attn_part)
                 launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, fl[l + 1].n1w, fl[l + 1].n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
             }
         } else {
@@ -299,17 +312,25 @@ struct b200_engine {
         lin(sy_bf, ada_all, R, em);
         for (int r = 0; r < N_RES; r++) {
             const float* m = mod + r * 3 * D_FLOW;
-            launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3(R), dim3(D_FLOW / 4), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, rb[r].lnw, rb[r].lnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
             Epi e0; e0.out2 = h1_bf; e0.out2_map = rows(D_FLOW); e0.out2_type = OUT2_BF16; e0.act = ACT_SILU;
-            lin(hn_bf, rb[r].mlp0, R, e0);
+            if (ln_in_gemv(R)) { LnArgs a; a.w = rb[r].lnw; a.b = rb[r].lnb; a.eps = 1e-6f; a.shift = m; a.scale = m + D_FLOW; a.mod_ld = ada_all.out; lin_ln(xh, a, rb[r].mlp0, R, e0); }
+            else {
+                launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3(R), dim3(D_FLOW / 4), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, rb[r].lnw, rb[r].lnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
+                launches++;
+                lin(hn_bf, rb[r].mlp0, R, e0);
+            }
             Epi e2; e2.rowmul = m + 2 * D_FLOW; e2.rowmul_ld = ada_all.out; e2.resid = xh; e2.resid_map = rows(D_FLOW); e2.out = xh; e2.out_map = rows(D_FLOW);
             lin(h1_bf, rb[r].mlp2, R, e2);
         }
         const float* m = mod + N_RES * 3 * D_FLOW;
-        launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3(R), dim3(D_FLOW / 4), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, fnw, fnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
         Epi ef; ef.resid = noise_f32; ef.resid_map = rows(LDIM); ef.out = latent; ef.out_map = rows(LDIM);
-        lin(hn_bf, final_lin, R, ef);
-        launches += 2 + N_RES;
+        if (ln_in_gemv(R)) { LnArgs a; a.w = fnw; a.b = fnb; a.eps = 1e-6f; a.shift = m; a.scale = m + D_FLOW; a.mod_ld = ada_all.out; lin_ln(xh, a, final_lin, R, ef); }
+        else {
+            launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3(R), dim3(D_FLOW / 4), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, fnw, fnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
+            launches++;
+            lin(hn_bf, final_lin, R, ef);
+        }
+        launches += 1;
     }
 
     // Mimi front end (latent -> 16 transformer input rows, written to `xbuf`), reference models/mimi.h:77-83 + modules/conv.h:283-331.
@@ -836,7 +857,7 @@ int b200_finalize_weights(b200_engine* e) {
     // between consecutive launches, which shows up as microseconds of idle time on the ~100 small kernels of a frame.
     {
         const void* ks[] = {(const void*)prepare_mimi_kernel, (const void*)rope_table_kernel, (const void*)gemm_ffma_kernel<__nv_bfloat16>, (const void*)gemm_ffma_kernel<__half>,
-                            (const void*)gemv_small_kernel<__nv_bfloat16, 8>, (const void*)gemv_small_kernel<__half, 8>, (const void*)layernorm_kernel<D_MODEL>,
+                            (const void*)gemv_small_kernel<__nv_bfloat16, 8>, (const void*)gemv_small_kernel<__half, 8>, (const void*)gemv_ln_kernel<D_MODEL>, (const void*)gemv_ln_kernel<D_FLOW>, (const void*)layernorm_kernel<D_MODEL>,
                             (const void*)layernorm_kernel<D_FLOW>, 
                             (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
                             (const void*)attn_flow_split_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,

@@ -177,6 +177,82 @@ __global__ void __launch_bounds__(256) gemv_small_kernel(const T* __restrict__ A
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// GEMV with the LayerNorm that produces its input fused in (batch 1-2 decode): x is the f32 row, every CTA first normalises the
+// R <= 2 rows into shared memory (ggml_norm semantics like layernorm_kernel, optional affine, optional AdaLN modulate, result rounded
+// to bf16 exactly as the separate LN kernel stores it), then each warp computes two output columns. The redundant per-CTA LN costs
+// ~1 us of latency per launch and removes one launch (~4.7 us at this batch size) per LayerNorm: the step is launch bound there.
+// ------------------------------------------------------------------------------------------------
+struct LnArgs { const float* w = nullptr; const float* b = nullptr; float eps = 0.f; const float* shift = nullptr; const float* scale = nullptr; int mod_ld = 0; };
+
+template <int K>
+__global__ void __launch_bounds__(256) gemv_ln_kernel(const float* __restrict__ x, LnArgs ln, const __nv_bfloat16* __restrict__ W, int R, int N, Epi epi) {
+    pdl_prologue();
+    constexpr int PER = K / 256;                                 // elements per thread and row in the LN prologue
+    __shared__ float xs[2][K];
+    __shared__ float red[2][8];
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    for (int r = 0; r < R; r++) {
+        float v[PER]; float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; i++) { v[i] = x[(long long)r * K + tid * PER + i]; s += v[i]; }
+        s = warp_sum(s);
+        if (lane == 0) red[0][wid] = s;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) tot += red[0][w];
+        const float mean = tot / K;
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; i++) { v[i] -= mean; s2 += v[i] * v[i]; }
+        s2 = warp_sum(s2);
+        if (lane == 0) red[1][wid] = s2;
+        __syncthreads();
+        tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) tot += red[1][w];
+        const float rs = 1.0f / sqrtf(tot / K + ln.eps);
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int c = tid * PER + i;
+            float y = v[i] * rs;
+            if (ln.w) y *= ln.w[c];
+            if (ln.b) y += ln.b[c];
+            if (ln.scale) y = y * (ln.scale[(long long)r * ln.mod_ld + c] + 1.f) + ln.shift[(long long)r * ln.mod_ld + c];
+            xs[r][c] = __bfloat162float(__float2bfloat16_rn(y));
+        }
+        __syncthreads();
+    }
+    const int n0 = (blockIdx.x * 8 + wid) * 2;
+    if (n0 >= N) return;
+    const __nv_bfloat16* w0 = W + (long long)n0 * K;
+    const __nv_bfloat16* w1 = w0 + K;
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int k = lane * 8; k < K; k += 256) {
+        const uint4 wv0 = __ldg(reinterpret_cast<const uint4*>(w0 + k)), wv1 = __ldg(reinterpret_cast<const uint4*>(w1 + k));
+        const uint32_t a0[4] = {wv0.x, wv0.y, wv0.z, wv0.w}, a1[4] = {wv1.x, wv1.y, wv1.z, wv1.w};
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            if (r < R) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float xa = xs[r][k + 2 * j], xb = xs[r][k + 2 * j + 1];
+                    acc[r][0] = fmaf(xa, __uint_as_float(a0[j] << 16), acc[r][0]); acc[r][0] = fmaf(xb, __uint_as_float(a0[j] & 0xffff0000u), acc[r][0]);
+                    acc[r][1] = fmaf(xa, __uint_as_float(a1[j] << 16), acc[r][1]); acc[r][1] = fmaf(xb, __uint_as_float(a1[j] & 0xffff0000u), acc[r][1]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        if (r < R) {
+            const float v0 = warp_sum(acc[r][0]), v1 = warp_sum(acc[r][1]);
+            if (lane == 0) { const float v[2] = {v0, v1}; epi_apply<2>(epi, r, n0, v, N); }
+        }
+    }
+}
+
 // Final SEANet conv (64 -> 1 channel, k=3; reference seanet.h:208, defaults.h:113-118). Four lanes per output sample
 // (16 channels x 3 taps each, two shuffles to finish), eight consecutive samples per warp so every global load
 // instruction covers 1 KB of contiguous channel-last rows. f16 operands, fp32 accumulation like every other conv.
