@@ -538,8 +538,11 @@ struct b200_engine {
     }
 
     // One generation step for slots [slot0, slot0+n).
+    bool last_step_piped = false;        // the last run_step left its Mimi decode (and PCM copy, for b200_submit frames) to the Mimi stream
     void run_step(int slot0, int n, bool injected, long long tag = -1) {
+        last_step_piped = false;
         if (!cfg.overlap || !cfg.cuda_graphs || profiling) { join_mimi(); run_graphed(0, slot0, n, injected); return; }
+        last_step_piped = true;
         const int par = (int)(pipe_t & 1);
         struct CoresideScope { TcPlanCache* c; CoresideScope(TcPlanCache* c_) : c(c_) { c->coreside = c->coreside_allowed; } ~CoresideScope() { c->coreside = false; } } cs_scope(tc);
         PendingFrame prev = pending; pending.valid = false;
@@ -561,6 +564,10 @@ struct b200_engine {
         PTTS_CUDA_CHECK(cudaEventRecord(ev_main[par], stream));
         pending.valid = true; pending.slot0 = slot0; pending.n = n; pending.par = par; pending.tag = tag;
         pipe_t++;
+        // Small batches are launch-latency bound, not HBM bound: there is nothing to gain from placing the Mimi chunks behind the next
+        // step's attention kernels, and holding the frame back would add a whole FlowLM step to its latency. Decode it right away on
+        // the Mimi stream; it still overlaps the next FlowLM step (streaming API look-ahead, b200_submit).
+        if (n < 32) flush_pending();
     }
 
     void ensure_pinned(size_t nf, size_t ni) {
@@ -1052,7 +1059,7 @@ int b200_submit(b200_engine* e, int slot0, int n, const float* noise) {
     e->run_step(slot0, n, noise != nullptr, (long long)e->submit_t);
     PTTS_CUDA_CHECK(cudaMemcpyAsync(pd.produced, e->produced, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     PTTS_CUDA_CHECK(cudaEventRecord(pd.done_main, e->stream));
-    if (!e->pending.valid) {   // non-pipelined step (overlap off): the frame is already decoded on the main stream
+    if (!e->last_step_piped) {   // non-pipelined step (overlap off): the frame is already decoded on the main stream
         PTTS_CUDA_CHECK(cudaMemcpyAsync(pd.pcm, e->pcm + (size_t)slot0 * FRAME, (size_t)n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
         PTTS_CUDA_CHECK(cudaEventRecord(pd.done_mimi, e->stream));
     }   // otherwise the PCM copy is enqueued behind the frame's Mimi decode (finish_mimi_frame), by the next submit or by collect

@@ -76,6 +76,8 @@ struct ptts_context_t {
     SpmUnigram tokenizer;
     std::map<std::string, int> voices;      // resolved voice file -> engine voice id
     std::vector<bool> slot_used;
+    int n_streams = 0;
+    bool lookahead = true;                  // PTTS_B200_LOOKAHEAD=0: strictly one step per receive
 };
 
 struct ptts_stream_t {
@@ -84,6 +86,8 @@ struct ptts_stream_t {
     float temp = 0.7f;
     SentenceSplitter sproc;
     int frames_after_eos = 0, max_gen_len = 0, generation_step = 0;
+    int inflight = 0;                       // frames submitted to the engine but not collected yet (look-ahead pipeline)
+    std::vector<float> scratch;             // sink for a look-ahead frame that turned out to lie past the end of the sentence
 };
 
 static int upload_checkpoint(b200_engine* eng, const std::string& file) {
@@ -114,6 +118,7 @@ static ptts_context_t* init_with_config(const char* model_path, const b200_confi
     if (b200_finalize_weights(ctx->engine) != B200_OK) { fprintf(stderr, "error: failed to load weights %s\n", filename.c_str()); exit(1); }
     if (!ctx->tokenizer.load(ctx->model_path + "tokenizer.model")) { fprintf(stderr, "error: tokenizer not found %stokenizer.model\n", model_path); exit(1); }
     ctx->slot_used.assign(cfg.max_slots, false);
+    ctx->lookahead = env_int("PTTS_B200_LOOKAHEAD", 1) != 0 && cfg.overlap != 0;
     return ctx;
 }
 
@@ -160,26 +165,50 @@ ptts_stream_t* ptts_stream_from_safetensors(ptts_context_t* ctx, const char* voi
     int slot = -1;
     for (size_t i = 0; i < ctx->slot_used.size(); i++) if (!ctx->slot_used[i]) { slot = (int)i; break; }
     if (slot < 0) { fprintf(stderr, "error: no free stream slot (raise PTTS_B200_MAX_STREAMS)\n"); exit(1); }
-    ctx->slot_used[slot] = true;
+    ctx->slot_used[slot] = true; ctx->n_streams++;
     auto* s = new ptts_stream_t;
     s->ctx = ctx; s->slot = slot; s->voice = vid; s->temp = temp;
     ptts_stream_reset(s);
     return s;
 }
 
-void ptts_stream_reset(ptts_stream_t* s) { s->max_gen_len = 0; s->generation_step = 0; s->sproc.reset(); }   // reference :396-400
+static void stream_drain(ptts_stream_t* s);
+void ptts_stream_reset(ptts_stream_t* s) { stream_drain(s); s->max_gen_len = 0; s->generation_step = 0; s->sproc.reset(); }   // reference :396-400
 void ptts_stream_flush(ptts_stream_t* s) { s->sproc.flush(); }                                                  // reference :402-404
 void ptts_stream_send(ptts_stream_t* s, const char* chunk) {                                                   // reference :406-414
     if (chunk[0] == '\0') { ptts_stream_flush(s); return; }
     s->sproc.ingest(chunk);
 }
 
-static bool stream_step(ptts_stream_t* s, float* samples) {          // reference _stream_sentence_step :446-492
+// Collect and drop whatever this stream still has in flight (end of sentence, reset).
+static void stream_drain(ptts_stream_t* s) {
+    int32_t produced = 0;
+    if (s->inflight > 0 && s->scratch.size() < 1920) s->scratch.resize(1920);
+    while (s->inflight > 0) { b200_collect(s->ctx->engine, s->scratch.data(), &produced); s->inflight--; }
+}
+
+// reference _stream_sentence_step :446-492. With a single stream in the context the engine runs one frame AHEAD: the FlowLM step of
+// frame t+1 is submitted before frame t is collected, so it overlaps frame t's Mimi decode (b200_submit / b200_collect). At batch 1
+// both halves are launch-latency bound, so a frame costs max(FlowLM, Mimi) instead of their sum. A look-ahead step past the end of a
+// sentence is harmless: an inactive slot keeps its FlowLM state, and the Mimi state is reset by the next sentence start anyway.
+static bool stream_step(ptts_stream_t* s, float* samples) {
     if (s->generation_step >= s->max_gen_len) { fprintf(stderr, "warning: called with high gen step\n"); return false; }
     int32_t produced = 0;
-    b200_set_seed(s->ctx->engine, g_seed);
-    if (b200_step(s->ctx->engine, s->slot, 1, nullptr, samples, &produced, nullptr, nullptr) != B200_OK) { fprintf(stderr, "error: step failed\n"); exit(1); }
-    if (!produced) { s->generation_step = s->max_gen_len; return false; }
+    b200_engine* eng = s->ctx->engine;
+    b200_set_seed(eng, g_seed);
+    if (!s->ctx->lookahead || s->ctx->n_streams != 1) {               // several streams share the engine's in-order frame queue: stay synchronous
+        stream_drain(s);
+        if (b200_step(eng, s->slot, 1, nullptr, samples, &produced, nullptr, nullptr) != B200_OK) { fprintf(stderr, "error: step failed\n"); exit(1); }
+    } else {
+        if (s->inflight == 0) { if (b200_submit(eng, s->slot, 1, nullptr) != B200_OK) { fprintf(stderr, "error: step failed\n"); exit(1); } s->inflight++; }
+        if (s->generation_step + s->inflight < s->max_gen_len && s->inflight < 2) {
+            if (b200_submit(eng, s->slot, 1, nullptr) != B200_OK) { fprintf(stderr, "error: step failed\n"); exit(1); }
+            s->inflight++;
+        }
+        if (b200_collect(eng, samples, &produced) < 0) { fprintf(stderr, "error: step failed\n"); exit(1); }
+        s->inflight--;
+    }
+    if (!produced) { s->generation_step = s->max_gen_len; stream_drain(s); return false; }
     s->generation_step++;
     return true;
 }
@@ -196,6 +225,7 @@ bool ptts_stream_receive(ptts_stream_t* s, float* samples) {          // referen
         const int max_gen_len = (int)((words + 2.0f) * 12.5f);          // _stream_sentence_init :429-430
         std::vector<int> ids = s->ctx->tokenizer.encode(text);
         std::vector<int32_t> ids32(ids.begin(), ids.end());
+        stream_drain(s);
         const int rc = b200_begin_sentence(s->ctx->engine, s->slot, s->voice, ids32.data(), (int)ids32.size(), max_gen_len, fae, s->temp);
         if (rc != B200_OK) { fprintf(stderr, "error: sentence init failed (%d)\n", rc); exit(1); }
         s->frames_after_eos = fae; s->max_gen_len = max_gen_len; s->generation_step = 0;
