@@ -538,6 +538,7 @@ struct b200_engine {
     }
 
     // One generation step for slots [slot0, slot0+n).
+    int immediate_below = getenv("PTTS_B200_IMMEDIATE_BELOW") ? atoi(getenv("PTTS_B200_IMMEDIATE_BELOW")) : 32;   // tuning hook
     bool last_step_piped = false;        // the last run_step left its Mimi decode (and PCM copy, for b200_submit frames) to the Mimi stream
     void run_step(int slot0, int n, bool injected, long long tag = -1) {
         last_step_piped = false;
@@ -567,7 +568,7 @@ struct b200_engine {
         // Small batches are launch-latency bound, not HBM bound: there is nothing to gain from placing the Mimi chunks behind the next
         // step's attention kernels, and holding the frame back would add a whole FlowLM step to its latency. Decode it right away on
         // the Mimi stream; it still overlaps the next FlowLM step (streaming API look-ahead, b200_submit).
-        if (n < 32) flush_pending();
+        if (n < immediate_below) flush_pending();
     }
 
     void ensure_pinned(size_t nf, size_t ni) {
