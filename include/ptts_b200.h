@@ -80,8 +80,9 @@ B200_API int  b200_begin_sentences(b200_engine* e, int n, const int32_t* slots, 
  * Host<->device copies and one stream synchronise are inside the call. */
 B200_API int  b200_step(b200_engine* e, int slot0, int n, const float* noise, float* pcm, int32_t* produced,
                         float* latents, float* eos_logit);
-/* Device-resident variant: enqueue one step on the engine stream, no copies, no sync. Results stay in the
- * engine's device buffers (b200_device_ptr). */
+/* Device-resident variant: enqueue one step, no copies, no sync. Results stay in the engine's device buffers (b200_device_ptr).
+ * With cfg.overlap the step is pipelined over two streams (its Mimi decode may be enqueued together with the NEXT step, see
+ * DESIGN.md 4.1): call b200_join (stream-ordered) or b200_sync (host) before reading "pcm". */
 B200_API int  b200_step_enqueue(b200_engine* e, int slot0, int n, int use_injected_noise);
 /* Pipelined pair for throughput serving (up to three frames in flight): submit enqueues a frame and returns at once, collect blocks until the
    oldest submitted frame is complete and copies out its n x 1920 samples + produced flags; returns n (or a negative error).         */
