@@ -118,6 +118,8 @@ B200_API void* b200_stream(b200_engine* e);                        /* cudaStream
 B200_API void* b200_device_ptr(b200_engine* e, const char* name);  /* "pcm", "latent", "noise", "produced", "eos" */
 B200_API long long b200_launch_count(b200_engine* e);              /* kernels launched so far by this engine */
 B200_API int  b200_read_kv(b200_engine* e, int slot, int layer, int which, int n_pos, float* out); /* debug/parity */
+/* Host-only: tile width (32/64/128) and deterministic split-K factor the GEMM dispatcher would use (cost model of gemm_tc.cuh). */
+B200_API int  b200_debug_gemm_plan(int R, int N, int K, int num_sms, int want_ln, int* bn, int* splits);
 B200_API const char* b200_build_info(void);
 
 /* ---- extern "C" aliases of the reference's C++ API (include/pocket_tts/pocket_tts.h:18-42) ---- */

@@ -1261,6 +1261,15 @@ int b200_read_kv(b200_engine* e, int slot, int layer, int which, int n_pos, floa
     return B200_OK;
 }
 
+// Host-only: the tile width / split-K plan the tensor-core GEMM dispatcher picks for a [R x K] . [N x K]^T product of one slot
+// (no device needed; tests/test_cabi.py checks the invariants of the cost model).
+int b200_debug_gemm_plan(int R, int N, int K, int num_sms, int want_ln, int* bn, int* splits) {
+    if (R < 1 || N < 32 || N % 32 != 0 || K < 64 || K % 64 != 0 || num_sms < 1 || !bn || !splits) return B200_EINVAL;
+    const TcPlan p = tc_plan((R + 127) / 128, R, N, K, num_sms, want_ln != 0);
+    *bn = p.bn; *splits = p.splits;
+    return B200_OK;
+}
+
 const char* b200_build_info(void) { return "ptts_b200 sm_100a " __DATE__ " " __TIME__; }
 
 }  // extern "C"

@@ -45,3 +45,26 @@ def test_product_never_touches_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 src = open(os.path.join(root, f), errors="ignore").read()
                 assert "oracle" not in src.replace("no CPU fallback", ""), os.path.join(root, f)
+
+
+def test_gemm_planner_invariants(P):
+    """The tile/split-K cost model (host code, no GPU): valid tile widths, no empty splits, workspace bound, and the decode shapes of the
+    model never fall back to more partial planes than the reduction kernels were measured with."""
+    import ctypes
+    L = P.lib()
+    L.b200_debug_gemm_plan.restype = ctypes.c_int
+    L.b200_debug_gemm_plan.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_int)] * 2
+    bn, sp = ctypes.c_int(), ctypes.c_int()
+    shapes = [(1024, 3072), (1024, 1024), (1024, 4096), (4096, 1024), (512, 512), (1024, 512), (512, 10240), (512, 32), (512, 1536), (2048, 512), (3584, 512)]
+    for R in (3, 16, 64, 256, 512, 4096, 24576):
+        for K, N in shapes:
+            for ln in (0, 1):
+                assert L.b200_debug_gemm_plan(R, N, K, 148, ln, ctypes.byref(bn), ctypes.byref(sp)) == 0
+                assert bn.value in (32, 64, 128) and N % bn.value == 0
+                assert 1 <= sp.value <= 16
+                if sp.value > 1:
+                    kbps = -(-(K // 64) // sp.value)
+                    assert kbps >= 4 and sp.value * R * N <= 32 << 20          # >= 4 k-blocks per split, partial planes fit the workspace
+                if R > 512:
+                    assert sp.value == 1                                       # large-M GEMMs are never split
+    assert L.b200_debug_gemm_plan(0, 64, 64, 148, 0, ctypes.byref(bn), ctypes.byref(sp)) != 0
