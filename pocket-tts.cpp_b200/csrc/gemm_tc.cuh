@@ -427,10 +427,22 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
             mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
             tc_fence_after();
             const long long ws_off = (long long)split * p.ws_split_stride;
+            if (half * 32 >= BN) {                                 // BN = 32: the second warp of a lane group has no chunk, it only releases the buffer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * buf) : "memory");
+            }
 #pragma unroll 1
             for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 float v[32];
                 tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+                if (c0 + 64 >= BN) {
+                    // This warp's last chunk of the tile is now in registers: hand the accumulator buffer back to the MMA warp BEFORE the slow
+                    // global phase of the epilogue, so tile i+2's mainloop never waits for tile i's loads and stores.
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * buf) : "memory");
+                }
                 if constexpr (GEN) {
                     float4* sp = reinterpret_cast<float4*>(stg + lane * EPI_STG_LD);
 #pragma unroll
@@ -443,9 +455,6 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
                     if (live) epi_qkv32<CLS == -2>(epi, row, tile_n * BN + c0, v);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * buf) : "memory");
         }
     }
     tc_fence_before();
