@@ -1,5 +1,6 @@
 // engine.cu — device layer of the B200 Pocket-TTS engine: weights, per-utterance slots, ragged prefill and the
-// batched per-frame step (FlowLM backbone -> LSD flow head -> Mimi decoder -> 1920 PCM samples).
+// batched per-frame step (FlowLM backbone -> LSD flow head -> Mimi decoder -> 1920 PCM samples), replayed as CUDA
+// graphs on two streams (run_step: the Mimi decode of frame t overlaps the FlowLM step of frame t+1).
 // C ABI declared in include/ptts_b200.h. No CPU fallback: everything below runs on the device or aborts.
 #include "../../include/ptts_b200.h"
 #include "common.cuh"

@@ -2,9 +2,9 @@
 //   * operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a multi-stage shared-memory ring,
 //   * tcgen05.mma (kind::f16, bf16 or f16 inputs, fp32 accumulate) issued by ONE thread, accumulator in TMEM,
 //   * epilogue warps read TMEM with tcgen05.ld (32 lanes x 32 columns) and run the fused epilogue.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM lane groups
-// (warp & 3) * 32). One 128 x BN output tile per CTA; up to two CTAs per SM so one tile's epilogue overlaps the
-// other's loads/MMAs.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue (TMEM lane group (warp & 3) * 32, two
+// warps per lane group alternate 32-column chunks). Persistent over 128 x BN output tiles, accumulator double-buffered in TMEM and
+// released right after the last tcgen05.ld of a tile; up to two CTAs per SM. One kernel instantiation per (BN, epilogue class).
 //
 // A operand: channel-last activations [slot][rows][C]. A causal conv window (K = taps * C) is NOT materialised:
 // k-block kb = (tap, c0) is loaded at row offset +tap, so a conv is the same kernel as a linear (taps == 1).
