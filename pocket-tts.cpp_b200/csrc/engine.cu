@@ -468,6 +468,7 @@ struct b200_engine {
 
     // kind 0 = full generation step (one stream), 1 = Mimi-only decode, 2 = FlowLM segment `part` -> mx2[par], 3 = Mimi chunk `part`
     // from mx2[par]. Runs on the CURRENT `stream` member (the pipeline swaps in stream_m for kind 3).
+    static constexpr int ALL_PARTS = 15;     // `part` value meaning every segment / chunk in one graph
     void run_graphed(int kind, int slot0, int n, bool injected, int par = 0, int part = 0) {
         // PDL overlaps each kernel's prologue (barrier init, TMEM allocation, weight prefetch) with its predecessor's tail: a win while
         // the step is launch/latency bound (measured +2..7 % at batch 16-128), a loss once the kernels fill the machine (-10 % at 256).
@@ -477,8 +478,8 @@ struct b200_engine {
         auto body = [&]() {
             if (kind == 0) step_enqueue(slot0, n, injected);
             else if (kind == 1) { mimi_front(slot0, n, mx); mimi(slot0, n, mx); }
-            else if (kind == 2) flow_part(slot0, n, injected, mx2[par], part);
-            else mimi(slot0, n, mx2[par], part);
+            else if (kind == 2) flow_part(slot0, n, injected, mx2[par], part == ALL_PARTS ? -1 : part);
+            else mimi(slot0, n, mx2[par], part == ALL_PARTS ? -1 : part);
         };
         if (!cfg.cuda_graphs || profiling) { body(); return; }
         GraphEntry& g = graphs[std::make_tuple((kind * 2 + par) * 16 + part, slot0, n, injected ? 1 : 0)];
@@ -526,7 +527,8 @@ struct b200_engine {
         if (debug_skip_mimi) return;
         PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream_m, ev_main[f.par], 0));
         tc->coreside = tc->coreside_allowed;                  // same graphs (same launch shapes) as the interleaved form
-        for (int c = 0; c < N_MCHUNK; c++) mimi_chunk_on_side(f, c);
+        if (one_graph_per_stream(f.n)) mimi_chunk_on_side(f, ALL_PARTS);
+        else for (int c = 0; c < N_MCHUNK; c++) mimi_chunk_on_side(f, c);
         tc->coreside = false;
         finish_mimi_frame(f);
     }
@@ -540,6 +542,7 @@ struct b200_engine {
 
     // One generation step for slots [slot0, slot0+n).
     int immediate_below = getenv("PTTS_B200_IMMEDIATE_BELOW") ? atoi(getenv("PTTS_B200_IMMEDIATE_BELOW")) : 32;   // tuning hook
+    bool one_graph_per_stream(int n) const { return n >= 4 && n < immediate_below; }
     bool last_step_piped = false;        // the last run_step left its Mimi decode (and PCM copy, for b200_submit frames) to the Mimi stream
     void run_step(int slot0, int n, bool injected, long long tag = -1) {
         last_step_piped = false;
@@ -551,6 +554,17 @@ struct b200_engine {
         if (prev.valid && (prev.slot0 != slot0 || prev.n != n)) { pending = prev; flush_pending(); prev.valid = false; }   // different slot range: no interleave
         if (debug_skip_mimi) prev.valid = false;
         if (prev.valid) PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream_m, ev_main[prev.par], 0));
+        if (one_graph_per_stream(n)) {
+            // 4..31 utterances: one graph for the whole FlowLM part and one for the whole Mimi decode, enqueued immediately (measured:
+            // batch 8 0.545 -> 0.533 ms, batch 16 0.604 -> 0.577 ms; at batch 1-3 the 7 + 6 short graphs are faster, 0.40 vs 0.46 ms)
+            if (ev_mimi_valid[par]) PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_mimi[par], 0));
+            run_graphed(2, slot0, n, injected, par, ALL_PARTS);
+            PTTS_CUDA_CHECK(cudaEventRecord(ev_main[par], stream));
+            pending.valid = true; pending.slot0 = slot0; pending.n = n; pending.par = par; pending.tag = tag;
+            pipe_t++;
+            flush_pending();
+            return;
+        }
         for (int sg = 0; sg < N_SEG; sg++) {
             // only the last segment (step_front_kernel) writes the hand-off rows mx2[par]: wait there, not at the start of the step, for
             // frame t-2's Mimi decode (long finished in steady state; waiting up front would put its tail on the critical path)
