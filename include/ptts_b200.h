@@ -41,6 +41,10 @@ typedef struct b200_config {
     int pdl;              /* programmatic dependent launch (a kernel's prologue overlaps its predecessor's tail): 0 = off, 1 = for up to
                              128 utterances per step (default), 2 = always                                                      */
     int overlap;          /* 1 = two-stream pipeline: the Mimi decode of frame t overlaps the FlowLM step of frame t+1   */
+    int prefix_share;     /* 1 (default) = every utterance of a voice attends to ONE resident copy of the voice-conditioned KV prefix
+                             (cascade attention: prefix x all rows of the voice on tensor cores, private suffix streamed per row);
+                             0 = the reference's copy_states semantics (models/flow_lm.h:70-78): each sentence start copies the
+                             prefix into the slot's own cache. Results agree to rounding; tests run both. */
 } b200_config;
 
 B200_API void b200_default_config(b200_config* cfg);
@@ -98,7 +102,7 @@ B200_API int  b200_mimi_decode(b200_engine* e, int slot0, int n, const float* la
 B200_API int  b200_mimi_decode_enqueue(b200_engine* e, int slot0, int n);
 
 B200_API void b200_set_seed(b200_engine* e, uint64_t seed);
-B200_API int  b200_slot_position(b200_engine* e, int slot);        /* FlowLM current_end of a slot (host mirror) */
+B200_API int  b200_slot_position(b200_engine* e, int slot);        /* FlowLM current_end of a slot (synchronises the stream and reads the device counter) */
 /* Force every slot in the range to position `pos` with an active, never-ending sentence (bench: KV length control). */
 B200_API int  b200_debug_set_position(b200_engine* e, int slot0, int n, int pos, int max_gen_len);
 /* Unit-test hook for the GEMM family (tests/test_gpu_gemm.py): out[n_slots*T][N] = windows(A) . W^T (+bias); A is
@@ -115,9 +119,16 @@ B200_API int  b200_profile_read(b200_engine* e, float* out_ms, int* out_count);
 /* cudaProfilerStart (1) / cudaProfilerStop (0): lets `ncu --profile-from-start off` capture only a bracketed region. */
 B200_API void b200_profiler_range(int start);
 B200_API void* b200_stream(b200_engine* e);                        /* cudaStream_t the engine launches on */
-B200_API void* b200_device_ptr(b200_engine* e, const char* name);  /* "pcm", "latent", "noise", "produced", "eos" */
+B200_API void* b200_device_ptr(b200_engine* e, const char* name);  /* "pcm", "latent", "noise", "produced", "eos", "lat_f32", "noise_drawn" */
+B200_API int  b200_debug_read_f32(b200_engine* e, const char* name, long long offset, float* out, int n); /* synchronises, copies an f32 buffer out */
 B200_API long long b200_launch_count(b200_engine* e);              /* kernels launched so far by this engine */
 B200_API int  b200_read_kv(b200_engine* e, int slot, int layer, int which, int n_pos, float* out); /* debug/parity */
+/* Tap points for localising a parity failure (replaces GraphContext::debug, src/context.h:526-547; names follow the tests' CPU restatement):
+ * "flow.layer<l>" / "flow.attn<l>" [1024] (need b200_debug_taps(e, 1): steps then run eagerly on one stream), "mimi.upsample" [16*512],
+ * "mimi.transformer" [16*512], "seanet.conv0" [16*512], "seanet.convt2" [96*256], "seanet.res3" [96*256], "seanet.res6" [480*128],
+ * "seanet.res9" [1920*64] of `slot` after its last step. out == NULL returns the element count. */
+B200_API int  b200_debug_taps(b200_engine* e, int on);
+B200_API int  b200_debug_tap(b200_engine* e, const char* name, int slot, float* out, int max_elems);
 /* Host-only: tile width (32/64/128) and deterministic split-K factor the GEMM dispatcher would use (cost model of gemm_tc.cuh). */
 B200_API int  b200_debug_gemm_plan(int R, int N, int K, int num_sms, int want_ln, int* bn, int* splits);
 B200_API const char* b200_build_info(void);

@@ -52,6 +52,7 @@ def lib():
         L.oracle_mimi_bias_row.argtypes = [vp, ci, ci, fp]
         L.oracle_stream_create.restype = vp; L.oracle_stream_create.argtypes = [vp, fp, ci, ci]
         L.oracle_stream_destroy.argtypes = [vp]
+        L.oracle_stream_clone.restype = vp; L.oracle_stream_clone.argtypes = [vp]
         L.oracle_sentence_init.argtypes = [vp, ip, ci, ci, ci]
         L.oracle_step.restype = ci; L.oracle_step.argtypes = [vp, fp, fp, fp, fp]
         L.oracle_flowlm_rows.argtypes = [vp, fp, ci]
@@ -153,10 +154,17 @@ class Oracle:
 class OracleStream:
     """One utterance stream (reference ptts_stream_t, src/pocket_tts.cpp:333-394)."""
 
-    def __init__(self, oracle: Oracle, prompt: np.ndarray, kv_capacity: int):
+    def __init__(self, oracle: Oracle, prompt, kv_capacity: int, _handle=None):
         self.o = oracle
+        if _handle is not None:
+            self.h = _handle
+            return
         prompt = np.ascontiguousarray(prompt, np.float32)
         self.h = lib().oracle_stream_create(oracle.h, _fp(prompt), prompt.shape[0], kv_capacity)
+
+    def clone(self) -> "OracleStream":
+        """Same voice-conditioned state without repeating the voice prefill (deterministic, so identical to a fresh stream)."""
+        return OracleStream(self.o, None, 0, _handle=lib().oracle_stream_clone(self.h))
 
     def __del__(self):
         try:

@@ -641,6 +641,9 @@ oracle_stream* oracle_stream_create(oracle_ctx* c, const float* audio_prompt, in
     return s;
 }
 void oracle_stream_destroy(oracle_stream* s) { delete s; }
+// A second stream of the same voice without repeating the voice prefill (the reference would run get_state_for_audio_prompt again and
+// arrive at the same conditioned state: the prefill is deterministic). Test convenience for long prefixes.
+oracle_stream* oracle_stream_clone(const oracle_stream* s) { return new oracle_stream(*s); }
 
 // _stream_sentence_init (src/pocket_tts.cpp:416-444): restore conditioned KV, reset Mimi, text prefill.
 void oracle_sentence_init(oracle_stream* s, const int* tokens, int n_tokens, int max_gen_len, int frames_after_eos) {

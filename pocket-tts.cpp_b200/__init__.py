@@ -22,7 +22,8 @@ LDIM = 32
 class B200Config(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("max_slots", ctypes.c_int), ("max_voices", ctypes.c_int), ("kv_capacity", ctypes.c_int),
                 ("kv_f32", ctypes.c_int), ("mimi_mask_mode", ctypes.c_int), ("convt_split", ctypes.c_int), ("gemm_path", ctypes.c_int),
-                ("max_prefill_rows", ctypes.c_int), ("cuda_graphs", ctypes.c_int), ("pdl", ctypes.c_int), ("overlap", ctypes.c_int)]
+                ("max_prefill_rows", ctypes.c_int), ("cuda_graphs", ctypes.c_int), ("pdl", ctypes.c_int), ("overlap", ctypes.c_int),
+                ("prefix_share", ctypes.c_int)]
 
 
 _lib = None
@@ -77,6 +78,9 @@ def lib():
         "b200_launch_count": (ctypes.c_longlong, [vp]),
         "b200_read_kv": (ci, [vp, ci, ci, ci, ci, fp]),
         "b200_build_info": (cp, []),
+        "b200_debug_taps": (ci, [vp, ci]),
+        "b200_debug_tap": (ci, [vp, cp, ci, fp, ci]),
+        "b200_debug_read_f32": (ci, [vp, cp, ctypes.c_longlong, fp, ci]),
         "ptts_c_set_seed": (None, [ctypes.c_uint]),
         "ptts_c_get_seed": (ctypes.c_uint, []),
         "ptts_c_init": (vp, [cp]),
@@ -124,7 +128,7 @@ def _ip(a):
 def default_config(**kw) -> B200Config:
     cfg = B200Config()
     lib().b200_default_config(ctypes.byref(cfg))
-    for k in ("pdl", "cuda_graphs", "gemm_path", "kv_f32", "overlap"):          # environment overrides, like ptts_init (host_api.cpp)
+    for k in ("pdl", "cuda_graphs", "gemm_path", "kv_f32", "overlap", "prefix_share"):          # environment overrides, like ptts_init (host_api.cpp)
         v = os.environ.get("PTTS_B200_" + k.upper())
         if v not in (None, ""):
             setattr(cfg, k, int(v))
@@ -267,6 +271,24 @@ class Engine:
 
     def launch_count(self):
         return self.L.b200_launch_count(self.h)
+
+    def debug_taps(self, on=True):
+        assert self.L.b200_debug_taps(self.h, 1 if on else 0) == 0
+
+    def debug_tap(self, name, slot):
+        n = self.L.b200_debug_tap(self.h, name.encode(), slot, None, 0)
+        if n < 0:
+            raise RuntimeError(f"b200_debug_tap({name}) failed: {n}")
+        out = np.zeros(n, np.float32)
+        assert self.L.b200_debug_tap(self.h, name.encode(), slot, _fp(out), n) == n
+        return out
+
+    def debug_read(self, name, offset, n):
+        out = np.zeros(n, np.float32)
+        rc = self.L.b200_debug_read_f32(self.h, name.encode(), offset, _fp(out), n)
+        if rc != 0:
+            raise RuntimeError(f"b200_debug_read_f32({name}) failed: {rc}")
+        return out
 
     def read_kv(self, slot, layer, which, n_pos):
         out = np.zeros((n_pos, 1024), np.float32)

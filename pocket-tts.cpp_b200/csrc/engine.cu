@@ -53,8 +53,24 @@ struct b200_engine {
     long long launches = 0;
     uint64_t seed = 0; unsigned long long* d_seed = nullptr;
     // CUDA graphs of the per-frame step, keyed by (kind, slot0, n, injected); first use runs eagerly (warm-up), second captures
-    struct GraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; long long nlaunch = 0; };
-    std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; long long nlaunch = 0; unsigned long long last_use = 0; };
+    std::map<std::tuple<int, int, int, int, int>, GraphEntry> graphs;
+    // The cache is keyed by the batch range, so a server that varies (slot0, n) would otherwise grow it without bound: least-recently
+    // used entries are evicted beyond graph_cache_cap (26 graphs per range and noise mode; callers should use few distinct ranges).
+    size_t graph_cache_cap = getenv("PTTS_B200_GRAPH_CACHE") ? (size_t)atoi(getenv("PTTS_B200_GRAPH_CACHE")) : 512;
+    unsigned long long graph_clock = 0;
+    void evict_graphs() {
+        while (graphs.size() > graph_cache_cap) {
+            auto victim = graphs.end();
+            for (auto it = graphs.begin(); it != graphs.end(); ++it) if (victim == graphs.end() || it->second.last_use < victim->second.last_use) victim = it;
+            if (victim == graphs.end()) return;
+            if (victim->second.exec) {
+                // a graph launch still in flight keeps its resources alive (cudaGraphExecDestroy defers the release)
+                PTTS_CUDA_CHECK(cudaGraphExecDestroy(victim->second.exec));
+            }
+            graphs.erase(victim);
+        }
+    }
     int n_voices = 0;
     std::vector<int> voice_len;
     int total_slots = 0;       // max_slots + max_voices (voice prefixes live in the extra KV slots)
@@ -92,6 +108,19 @@ struct b200_engine {
     int *row_slot = nullptr, *row_pos = nullptr, *tok = nullptr; float2* cs = nullptr;
     float *af_ml = nullptr, *af_acc = nullptr;   // split-KV attention workspace [rows][splits][32] / [rows][splits][1024]
     int* af_cnt = nullptr;                       // per-row arrival counters of the in-kernel split merge (zero between launches)
+    // ---- shared voice prefix (cfg.prefix_share): per-slot {slot holding the prefix rows, number of prefix rows}; 0 rows = private cache ----
+    int *pfx_slot = nullptr, *pfx_len = nullptr; std::vector<int> h_pfx_slot, h_pfx_len;
+    unsigned long long pfx_version = 1;          // bumped whenever a slot's prefix assignment changes
+    // decode-side work list of attn_tile_kernel (prefix x rows of a voice), rebuilt when the stepped range or the assignment changes
+    AtItem* dec_items = nullptr; int* dec_meta = nullptr; int* dec_rows = nullptr; int dec_items_cap = 0;
+    int dec_key_slot0 = -1, dec_key_n = -1; unsigned long long dec_key_version = 0; int dec_grid_items = 0;
+    int tile_min_rows = getenv("PTTS_B200_TILE_MIN_ROWS") ? atoi(getenv("PTTS_B200_TILE_MIN_ROWS")) : 4;   // below: the streaming kernel reads the prefix itself
+    // attention context of the forward being enqueued (decode: the fixed scratch arrays; prefill: this call's staging)
+    struct AttnCtx { const int* row_slot = nullptr; const int* row_pos = nullptr; const float2* cs = nullptr;
+                     const AtItem* items = nullptr; const int* meta = nullptr; int n_items = 0; bool prefill = false; } actx;
+    // prefill staging on the device (grown on demand): [slot | pos | token] per row, tile items + meta per chunk, voice rows
+    int* pf_int = nullptr; size_t pf_int_cap = 0; AtItem* pf_items = nullptr; size_t pf_items_cap = 0; int* pf_meta = nullptr; size_t pf_meta_cap = 0;
+    float* pf_x = nullptr; size_t pf_x_cap = 0;
     __nv_bfloat16 *c_bf = nullptr, *sy_bf = nullptr, *hn_bf = nullptr, *h1_bf = nullptr;
     float *eos = nullptr, *ycond = nullptr, *mod = nullptr, *xh = nullptr, *noise_f32 = nullptr, *noise_inj = nullptr, *latent = nullptr;
     int* produced = nullptr; float* eos_out = nullptr;
@@ -105,6 +134,23 @@ struct b200_engine {
     ShiftAll shifts{};
     // pinned staging
     float* pin_f = nullptr; int* pin_i = nullptr; size_t pin_f_n = 0, pin_i_n = 0;
+    // ring of pinned staging buffers for ASYNCHRONOUS uploads (sentence start, prefill, work lists): a buffer is reused only after the
+    // event recorded behind its last copy has completed (normally long ago), so no entry point has to synchronise the stream
+    struct PinSlot { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; } pins[8];
+    int pin_next = 0; PinSlot* pin_cur = nullptr;
+    void* pin_acquire(size_t bytes) {
+        PinSlot& ps = pins[pin_next]; pin_next = (pin_next + 1) % 8;
+        if (!ps.ev) PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&ps.ev, cudaEventDisableTiming));
+        if (ps.used) PTTS_CUDA_CHECK(cudaEventSynchronize(ps.ev));
+        if (ps.cap < bytes) { if (ps.p) cudaFreeHost(ps.p); PTTS_CUDA_CHECK(cudaMallocHost(&ps.p, std::max<size_t>(bytes, 4096))); ps.cap = std::max<size_t>(bytes, 4096); }
+        pin_cur = &ps; return ps.p;
+    }
+    void pin_release(cudaStream_t st) { PTTS_CUDA_CHECK(cudaEventRecord(pin_cur->ev, st)); pin_cur->used = true; }
+    template <typename T> void grow(T*& ptr, size_t& cap, size_t need) {     // device scratch that only ever grows (old buffer stays in `allocs`)
+        if (need <= cap) return;
+        cap = std::max(need, cap * 2); ptr = dalloc<T>(cap, false);
+    }
+    bool begin_used = false;
     int* begin_meta = nullptr; float* begin_temp = nullptr; size_t begin_cap = 0;   // device copy of b200_begin_sentences' per-sentence metadata
     // b200_submit / b200_collect: up to three frames in flight, a ring of four pinned staging sets
     struct Pending { float* noise = nullptr; float* pcm = nullptr; int* produced = nullptr; size_t cap = 0; int slot0 = 0, n = 0; bool busy = false;
@@ -236,10 +282,86 @@ struct b200_engine {
 
     // ---- FlowLM transformer over R rows held in `h` (reference modules/transformer.h:253-278,363-374), in two pieces per layer so that the
     //      decode step can be cut into segments at the end of every attention kernel (run_step) ----
-    // in_proj (+RoPE, KV append) and attention of layer l. Expects norm1 of layer l in n_bf.
+    // ---- tap points (parity localisation; the reference's GraphContext::debug, src/context.h:526-547, printed tensor sums) ----
+    // b200_debug_taps(1): steps run eagerly on one stream and the FlowLM residual stream / attention output of every layer are copied
+    // aside; the Mimi-side taps are persistent buffers that can be read after any step (b200_debug_tap).
+    bool taps_on = false; float* tap_h = nullptr; __nv_bfloat16* tap_att = nullptr; int tap_slot0 = 0, tap_n = 0;
+    void tap_flow_layer(int l, int R) {
+        if (!taps_on || actx.prefill) return;
+        PTTS_CUDA_CHECK(cudaMemcpyAsync(tap_h + (size_t)l * cfg.max_slots * D_MODEL, h, (size_t)R * D_MODEL * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    }
+    void tap_flow_attn(int l, int R) {
+        if (!taps_on || actx.prefill) return;
+        PTTS_CUDA_CHECK(cudaMemcpyAsync(tap_att + (size_t)l * cfg.max_slots * D_MODEL, att_bf, (size_t)R * D_MODEL * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, stream));
+    }
+
+    // Decode rows of the range [slot0, slot0+n): row r = slot slot0+r. With a shared voice prefix, (re)builds the work list of
+    // attn_tile_kernel on the host when the range or the slot -> voice assignment changed: rows grouped by voice, 64-row tiles, the
+    // prefix cut into `splits` key ranges so that tiles x splits x 16 heads fill the machine about twice. Stream-ordered upload.
+    void prepare_decode(int slot0, int n) {
+        actx = AttnCtx{}; actx.row_slot = row_slot; actx.row_pos = row_pos; actx.cs = cs;
+        if (!cfg.prefix_share || cfg.kv_f32 || n < tile_min_rows) { dec_grid_items = 0; dec_key_n = -1; return; }
+        if (dec_key_slot0 == slot0 && dec_key_n == n && dec_key_version == pfx_version) return;
+        dec_key_slot0 = slot0; dec_key_n = n; dec_key_version = pfx_version;
+        std::map<std::pair<int, int>, std::vector<int>> groups;
+        for (int r = 0; r < n; r++) if (h_pfx_len[slot0 + r] > 0) groups[{h_pfx_slot[slot0 + r], h_pfx_len[slot0 + r]}].push_back(r);
+        int tiles = 0, max_p = 0;
+        for (auto& g : groups) { tiles += ((int)g.second.size() + AT_ROWS - 1) / AT_ROWS; max_p = std::max(max_p, g.first.second); }
+        if (tiles == 0) { dec_grid_items = 0; return; }
+        int splits = std::min(AF_PFX_SPLITS, std::max(1, (19 + tiles - 1) / tiles));
+        splits = std::max(1, std::min(splits, max_p / AT_KEYS));
+        std::vector<AtItem> items; std::vector<int> rows;
+        for (auto& g : groups) {
+            const int plen = g.first.second;
+            int chunk = (plen + splits - 1) / splits; chunk = (chunk + AT_KEYS - 1) / AT_KEYS * AT_KEYS;
+            for (size_t i0 = 0; i0 < g.second.size(); i0 += AT_ROWS) {
+                const int nr = (int)std::min<size_t>(AT_ROWS, g.second.size() - i0);
+                for (int sp = 0; sp < splits; sp++) {
+                    AtItem it{}; it.row0 = (int)(rows.size()); it.nrows = nr; it.a_slot = g.first.first; it.a_k0 = std::min(plen, sp * chunk); it.a_k1 = std::min(plen, (sp + 1) * chunk);
+                    it.b_slot = 0; it.b_k0 = 0; it.b_k1 = 0; it.out_split = AF_MAX_SPLITS + sp;
+                    items.push_back(it);
+                }
+                for (int i = 0; i < nr; i++) rows.push_back(g.second[i0 + i]);
+            }
+        }
+        if ((int)items.size() > dec_items_cap) { fprintf(stderr, "ptts_b200: internal error: %zu prefix tiles exceed the work-list capacity %d\n", items.size(), dec_items_cap); abort(); }
+        dec_grid_items = ((int)items.size() + 7) / 8 * 8;
+        const size_t bytes = 4 * sizeof(int) + rows.size() * sizeof(int) + items.size() * sizeof(AtItem);
+        char* pb = (char*)pin_acquire(bytes + 64);
+        int* meta = (int*)pb; meta[0] = (int)items.size(); meta[1] = splits; meta[2] = 0; meta[3] = 0;
+        int* prow = meta + 4; memcpy(prow, rows.data(), rows.size() * sizeof(int));
+        char* pit = (char*)(prow + rows.size()); memcpy(pit, items.data(), items.size() * sizeof(AtItem));
+        PTTS_CUDA_CHECK(cudaMemcpyAsync(dec_meta, meta, 4 * sizeof(int), cudaMemcpyHostToDevice, stream));
+        PTTS_CUDA_CHECK(cudaMemcpyAsync(dec_rows, prow, rows.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        PTTS_CUDA_CHECK(cudaMemcpyAsync(dec_items, pit, items.size() * sizeof(AtItem), cudaMemcpyHostToDevice, stream));
+        pin_release(stream);
+    }
+
+    // Number of KV splits of the streaming attention kernel for R rows. The CTA total should come close to whole waves of the resident
+    // CTAs (bf16: two 96 KB CTAs per SM) with at least ~2 CTAs per SM in flight (R = 256 rows streaming ~1.5k keys each: 3 splits =
+    // 5.19 waves, the last wave streams on 28 SMs; 4 splits = 6.92 waves, measured 1.557 -> 1.467 ms per step for the six launches).
+    // When the shared prefix is reduced by attn_tile_kernel the streamed part is only the utterance's own rows (a few hundred keys):
+    // two CTAs per SM are enough, more splits would only add per-CTA prologue/merge cost.
+    int af_splits(int R, bool short_stream) const {
+        if (af_splits_override > 0) return std::min(af_splits_override, AF_MAX_SPLITS);
+        const int sms = tc ? tc->num_sms : 148;
+        if (short_stream) return std::max(1, std::min(AF_MAX_SPLITS, (2 * sms + R - 1) / R));
+        int splits = 1; double best = -1.0;
+        for (int sp = 1; sp <= AF_MAX_SPLITS; sp++) {
+            const long long ctas = (long long)R * sp;
+            if (ctas < 2LL * sms && sp < AF_MAX_SPLITS) continue;
+            const double waves = (double)ctas / sms, eff = waves / std::ceil(waves);
+            if (eff > best + 1e-9) { best = eff; splits = sp; }
+            if (ctas >= 8LL * sms) break;
+        }
+        return splits;
+    }
+    bool use_prefix_tiles(int R) const { return cfg.prefix_share && !cfg.kv_f32 && !actx.prefill && R >= tile_min_rows && dec_grid_items > 0; }
+
+    // in_proj (+RoPE, KV append) and attention of layer l. Expects norm1 of layer l in n_bf; rows are described by `actx`.
     void flow_attn_part(int l, int R) {
         auto& L = fl[l];
-        Epi e; e.mode = EPI_FLOW_QKV; e.row_slot = row_slot; e.row_pos = row_pos; e.cs = cs; e.kv_f32 = cfg.kv_f32;
+        Epi e; e.mode = EPI_FLOW_QKV; e.row_slot = actx.row_slot; e.row_pos = actx.row_pos; e.cs = actx.cs; e.kv_f32 = cfg.kv_f32;
         e.kv_slot_stride = kv_slot_stride; e.q_out_f32 = q;
         if (cfg.kv_f32) { e.kcache = (float*)kc + l * kv_layer_stride; e.vcache = (float*)vc + l * kv_layer_stride; }
         else { e.kcache = (__nv_bfloat16*)kc + l * kv_layer_stride; e.vcache = (__nv_bfloat16*)vc + l * kv_layer_stride; }
@@ -248,29 +370,33 @@ struct b200_engine {
         const int sg = seg_begin(0);
         const bool pdl_saved = pdl_active;
         set_pdl(pdl_small);                                  // the KV-streaming kernel fills the machine: no early dependents around it
-        if (cfg.kv_f32) {
-            const size_t smem = (size_t)cfg.kv_capacity * sizeof(float);
-            launch_k(pdl_active, attn_flow_kernel<float>, dim3(R, N_HEADS), dim3(128), (size_t)(smem), stream, q, (const float*)e.kcache, (const float*)e.vcache, kv_slot_stride, row_slot, row_pos, att_bf);
+        if (actx.prefill && !cfg.kv_f32) {
+            // T > 1 rows with the causal mask (reference transformer.h:157-169): one tensor-core tile per 64 rows of a slot and head, K/V read
+            // once per tile instead of once per row
+            if (actx.n_items > 0)
+                launch_k(pdl_active, attn_tile_kernel<true>, dim3(actx.n_items, N_HEADS), dim3(128), (size_t)0, stream, (const float*)q, (const __nv_bfloat16*)e.kcache,
+                         (const __nv_bfloat16*)e.vcache, kv_slot_stride, actx.items, actx.meta, (const int*)nullptr, actx.row_pos, af_ml, af_acc, att_bf);
+            launches++;
         } else {
-            // KV splits: at least ~2 CTAs per SM, and among those the split count whose CTA total comes closest to whole waves of
-            // one 128 KB-smem CTA per SM (R = 256: 3 splits = 5.19 waves, the last wave streams on 28 SMs; 4 splits = 6.92 waves,
-            // measured 1.557 -> 1.467 ms per step for the six launches). The last split CTA of a row merges the row's partials.
-            const int sms = tc ? tc->num_sms : 148;
-            int splits = 1; double best = -1.0;
-            for (int sp = 1; sp <= AF_MAX_SPLITS; sp++) {
-                const long long ctas = (long long)R * sp;
-                if (ctas < 2LL * sms && sp < AF_MAX_SPLITS) continue;
-                const double waves = (double)ctas / sms, eff = waves / std::ceil(waves);
-                if (eff > best + 1e-9) { best = eff; splits = sp; }
-                if (ctas >= 8LL * sms) break;
+            const bool tiles = use_prefix_tiles(R);
+            AfKeys keys; keys.pfx_slot = pfx_slot; keys.pfx_len = pfx_len; keys.tiles_meta = tiles ? dec_meta : nullptr;
+            if (tiles) {   // shared voice prefix x all rows of the voice -> workspace partials (merged by the streaming kernel below)
+                launch_k(pdl_active, attn_tile_kernel<true>, dim3(dec_grid_items, N_HEADS), dim3(128), (size_t)0, stream, (const float*)q, (const __nv_bfloat16*)e.kcache,
+                         (const __nv_bfloat16*)e.vcache, kv_slot_stride, (const AtItem*)dec_items, (const int*)dec_meta, (const int*)dec_rows, actx.row_pos, af_ml, af_acc, att_bf);
+                launches++;
             }
-            if (af_splits_override > 0) splits = std::min(af_splits_override, AF_MAX_SPLITS);
-            launch_k(pdl_active, attn_flow_split_kernel, dim3(splits, R), dim3(288), (size_t)(AF_SMEM), stream, q, (const __nv_bfloat16*)e.kcache, (const __nv_bfloat16*)e.vcache, kv_slot_stride,
-                                                                              row_slot, row_pos, splits, af_ml, af_acc, att_bf, af_cnt);
+            const int splits = af_splits(R, tiles);
+            if (cfg.kv_f32)
+                launch_k(pdl_active, attn_flow_split_kernel<float>, dim3(splits, R), dim3(288), (size_t)(AfCfg<float>::SMEM), stream, (const float*)q, (const float*)e.kcache, (const float*)e.vcache,
+                         kv_slot_stride, actx.row_slot, actx.row_pos, keys, splits, af_ml, af_acc, att_bf, af_cnt);
+            else
+                launch_k(pdl_active, attn_flow_split_kernel<__nv_bfloat16>, dim3(splits, R), dim3(288), (size_t)(AfCfg<__nv_bfloat16>::SMEM), stream, (const float*)q, (const __nv_bfloat16*)e.kcache,
+                         (const __nv_bfloat16*)e.vcache, kv_slot_stride, actx.row_slot, actx.row_pos, keys, splits, af_ml, af_acc, att_bf, af_cnt);
+            launches++;
         }
-        launches++;
         set_pdl(pdl_saved);
         seg_end(sg);
+        tap_flow_attn(l, R);
     }
     // out_proj (+residual, norm2), linear1 (+GELU), linear2 (+residual) of layer l; leaves norm1 of layer l+1 in n_bf.
     void flow_chain_part(int l, int R) {
@@ -294,6 +420,7 @@ struct b200_engine {
         } else {
             lin(ff_bf, L.lin2, R, e2);
         }
+        tap_flow_layer(l, R);
     }
     void flow_forward(int R, bool ln1_done = false) {              // ln1_done: layer 0's norm1 already in n_bf (decode: flow_in_kernel)
         const int BIG = 1 << 30;
@@ -438,7 +565,7 @@ struct b200_engine {
             if (seg >= 0 && sg != seg) continue;
             if (sg == 0) {
                 launch_k(pdl_active, flow_in_kernel, dim3(n), dim3(256), (size_t)0, stream, slot0, n, (const __nv_bfloat16*)lat_in_bf16, (const __nv_bfloat16*)input_linear_t,
-                         (const float*)input_linear.b, (const float*)fl[0].n1w, (const float*)fl[0].n1b, h, n_bf, (const int*)cur_len, (const float*)freq_flow, row_slot, row_pos, cs);
+                         (const float*)input_linear.b, (const float*)fl[0].n1w, (const float*)fl[0].n1b, h, n_bf, (const int*)cur_len, (const int*)active, (const float*)freq_flow, row_slot, row_pos, cs);
                 launches++;
             } else {
                 flow_chain_part(sg - 1, n);
@@ -481,8 +608,11 @@ struct b200_engine {
             else if (kind == 2) flow_part(slot0, n, injected, mx2[par], part == ALL_PARTS ? -1 : part);
             else mimi(slot0, n, mx2[par], part == ALL_PARTS ? -1 : part);
         };
-        if (!cfg.cuda_graphs || profiling) { body(); return; }
-        GraphEntry& g = graphs[std::make_tuple((kind * 2 + par) * 16 + part, slot0, n, injected ? 1 : 0)];
+        if (!cfg.cuda_graphs || profiling || taps_on) { body(); return; }
+        const auto gkey = std::make_tuple((kind * 2 + par) * 16 + part, slot0, n, injected ? 1 : 0, (kind == 0 || kind == 2) ? dec_grid_items : 0);
+        if (!graphs.count(gkey)) { graphs[gkey].last_use = ++graph_clock; evict_graphs(); }
+        GraphEntry& g = graphs[gkey];
+        g.last_use = ++graph_clock;
         if (g.exec) { PTTS_CUDA_CHECK(cudaGraphLaunch(g.exec, stream)); launches += g.nlaunch; return; }
         if (g.seen++ == 0) { body(); return; }              // eager once: function attributes set, tensor maps encoded
         PTTS_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
@@ -533,8 +663,10 @@ struct b200_engine {
         finish_mimi_frame(f);
     }
     // Main stream waits for everything enqueued on the Mimi stream (before any non-pipelined use of Mimi state / PCM on the main stream).
+    cudaEvent_t ev_begin = nullptr, ev_reset = nullptr; bool reset_pending = false;   // sentence-start Mimi reset enqueued on the Mimi stream
     void join_mimi() {
         flush_pending();
+        if (reset_pending) { PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_reset, 0)); reset_pending = false; }
         if (!mimi_pending) return;
         if (ev_mimi_valid[last_mimi_par]) PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_mimi[last_mimi_par], 0));
         mimi_pending = false;
@@ -546,7 +678,9 @@ struct b200_engine {
     bool last_step_piped = false;        // the last run_step left its Mimi decode (and PCM copy, for b200_submit frames) to the Mimi stream
     void run_step(int slot0, int n, bool injected, long long tag = -1) {
         last_step_piped = false;
-        if (!cfg.overlap || !cfg.cuda_graphs || profiling) { join_mimi(); run_graphed(0, slot0, n, injected); return; }
+        prepare_decode(slot0, n);
+        tap_slot0 = slot0; tap_n = n;
+        if (!cfg.overlap || !cfg.cuda_graphs || profiling || taps_on) { join_mimi(); run_graphed(0, slot0, n, injected); return; }
         last_step_piped = true;
         const int par = (int)(pipe_t & 1);
         struct CoresideScope { TcPlanCache* c; CoresideScope(TcPlanCache* c_) : c(c_) { c->coreside = c->coreside_allowed; } ~CoresideScope() { c->coreside = false; } } cs_scope(tc);
@@ -604,14 +738,20 @@ __global__ void set_meta_kernel(int slot, int cur, int mg, int f, float t, const
 
 // Batched sentence start (b200_begin_sentences; reference _stream_sentence_init src/pocket_tts.cpp:416-444, copy_states models/flow_lm.h:70-78,
 // init(mimi_states) models/mimi.h:71-75): one launch each for all n sentences instead of three launches per sentence.
-// meta = [slot | src voice slot | prefix rows | cur_len | max_gen | frames_after_eos] x n (ints), temps[n].
+// meta = [slot | src voice slot | prefix rows | cur_len | max_gen | frames_after_eos | shared prefix rows (0 = private copy)] x n (ints), temps[n].
+// FlowLM-side state (main stream): stop-rule counters, BOS latent, upsampler carry, prefix assignment.
 __global__ void begin_meta_kernel(int n, const int* __restrict__ meta, const float* __restrict__ temps, const float* bos, int* cur_len, int* gen_step, int* eos_step,
-                                  int* max_gen, int* fae, int* active, float* temp, __nv_bfloat16* lat_in_bf16, float* lat_f32) {
+                                  int* max_gen, int* fae, int* active, float* temp, __nv_bfloat16* lat_in_bf16, float* lat_f32,
+                                  int* __restrict__ pfx_slot, int* __restrict__ pfx_len, float* __restrict__ e_prev) {
     const int j = blockIdx.x, i = threadIdx.x;
     if (j >= n) return;
     const int slot = meta[j], cur = meta[3 * n + j], mg = meta[4 * n + j], f = meta[5 * n + j];
-    if (i == 0) { cur_len[slot] = cur; gen_step[slot] = 0; eos_step[slot] = -1; max_gen[slot] = mg; fae[slot] = f; active[slot] = mg > 0 ? 1 : 0; temp[slot] = temps[j]; }
+    if (i == 0) {
+        cur_len[slot] = cur; gen_step[slot] = 0; eos_step[slot] = -1; max_gen[slot] = mg; fae[slot] = f; active[slot] = mg > 0 ? 1 : 0; temp[slot] = temps[j];
+        pfx_slot[slot] = meta[n + j]; pfx_len[slot] = meta[6 * n + j];
+    }
     if (i < LDIM) { lat_f32[slot * LDIM + i] = bos[i]; lat_in_bf16[slot * LDIM + i] = __float2bfloat16_rn(bos[i]); }
+    for (int c = i; c < M_DIM; c += blockDim.x) e_prev[(long long)slot * M_DIM + c] = 0.f;
 }
 __global__ void begin_copy_prefix_kernel(int n, const int* __restrict__ meta, char* kc, char* vc, long long slot_bytes, long long layer_bytes, long long row_bytes) {
     const int j = blockIdx.z;
@@ -629,15 +769,13 @@ __global__ void begin_copy_prefix_kernel(int n, const int* __restrict__ meta, ch
     }
     for (; i < n16; i += stride) dst[i] = src[i];
 }
-__global__ void begin_reset_kernel(int n, const int* __restrict__ meta, ShiftAll sa, float* __restrict__ e_prev, int* __restrict__ mimi_off) {
+// Mimi-side state (Mimi stream, behind every decode already enqueued there): carried conv rows, ring offset.
+__global__ void begin_reset_kernel(int n, const int* __restrict__ meta, ShiftAll sa, int* __restrict__ mimi_off) {
     const int slot = meta[blockIdx.x];
     const ShiftDesc d = sa.d[blockIdx.y];
     __half* base = d.buf + (long long)slot * d.slot_stride;
     for (int i = threadIdx.x; i < d.S * d.C; i += blockDim.x) base[i] = __float2half_rn(0.f);
-    if (blockIdx.y == 0) {
-        for (int i = threadIdx.x; i < M_DIM; i += blockDim.x) e_prev[(long long)slot * M_DIM + i] = 0.f;
-        if (threadIdx.x == 0) mimi_off[slot] = 0;
-    }
+    if (blockIdx.y == 0 && threadIdx.x == 0) mimi_off[slot] = 0;
 }
 
 }  // namespace
@@ -650,7 +788,7 @@ extern "C" {
 void b200_default_config(b200_config* c) {
     memset(c, 0, sizeof(*c));
     c->device = 0; c->max_slots = 1; c->max_voices = 8; c->kv_capacity = 2048; c->kv_f32 = 0; c->mimi_mask_mode = 0;
-    c->convt_split = 0; c->gemm_path = 0; c->max_prefill_rows = 2048; c->cuda_graphs = 1; c->pdl = 1; c->overlap = 1;
+    c->convt_split = 0; c->gemm_path = 0; c->max_prefill_rows = 2048; c->cuda_graphs = 1; c->pdl = 1; c->overlap = 1; c->prefix_share = 1;
 }
 
 int b200_engine_create(const b200_config* cfg, b200_engine** out) {
@@ -674,11 +812,14 @@ int b200_engine_create(const b200_config* cfg, b200_engine** out) {
             PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_mimi[i], cudaEventDisableTiming));
         }
         for (auto& ev : e->ev_seg) PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_begin, cudaEventDisableTiming));
+        PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_reset, cudaEventDisableTiming));
     }
     e->total_slots = cfg->max_slots + e->cfg.max_voices;
     e->max_rows = std::max(cfg->max_slots, e->cfg.max_prefill_rows);
     e->voice_len.assign(e->cfg.max_voices, 0);
     e->h_cur_len.assign(cfg->max_slots, 0);
+    e->h_pfx_slot.assign(e->total_slots, 0); e->h_pfx_len.assign(e->total_slots, 0);
     e->tc = tc_plan_cache_create();
     *out = e;
     return B200_OK;
@@ -697,6 +838,8 @@ void b200_engine_destroy(b200_engine* e) {
     }
     if (e->pin_f) cudaFreeHost(e->pin_f);
     if (e->pin_i) cudaFreeHost(e->pin_i);
+    for (auto& ps : e->pins) { if (ps.p) cudaFreeHost(ps.p); if (ps.ev) cudaEventDestroy(ps.ev); }
+    if (e->ev_begin) cudaEventDestroy(e->ev_begin); if (e->ev_reset) cudaEventDestroy(e->ev_reset);
     tc_plan_cache_destroy(e->tc);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(e->ev_main[i]); cudaEventDestroy(e->ev_mimi[i]); }
     for (auto& ev : e->ev_seg) cudaEventDestroy(ev);
@@ -846,7 +989,11 @@ int b200_finalize_weights(b200_engine* e) {
     e->h = e->dalloc<float>((size_t)MR * D_MODEL); e->q = e->dalloc<float>((size_t)MR * D_MODEL);
     e->n_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_MODEL); e->att_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_MODEL);
     e->ff_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_FF);
-    e->af_ml = e->dalloc<float>((size_t)MR * AF_MAX_SPLITS * 32); e->af_acc = e->dalloc<float>((size_t)MR * AF_MAX_SPLITS * D_MODEL); e->af_cnt = e->dalloc<int>(MR);
+    e->af_ml = e->dalloc<float>((size_t)MR * AF_WS_STRIDE * 32); e->af_acc = e->dalloc<float>((size_t)MR * AF_WS_STRIDE * D_MODEL); e->af_cnt = e->dalloc<int>(MR);
+    e->pfx_slot = e->dalloc<int>(TS); e->pfx_len = e->dalloc<int>(TS);
+    e->dec_items_cap = ((S + AT_ROWS - 1) / AT_ROWS + e->cfg.max_voices + 1) * AF_PFX_SPLITS + 8;
+    e->dec_items = e->dalloc<AtItem>(e->dec_items_cap); e->dec_meta = e->dalloc<int>(4); e->dec_rows = e->dalloc<int>(S);
+    e->tap_h = e->dalloc<float>((size_t)N_LAYERS * S * D_MODEL); e->tap_att = e->dalloc<__nv_bfloat16>((size_t)N_LAYERS * S * D_MODEL);
     e->row_slot = e->dalloc<int>(MR); e->row_pos = e->dalloc<int>(MR); e->tok = e->dalloc<int>(MR); e->cs = e->dalloc<float2>((size_t)MR * 32);
     e->c_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_MODEL); e->sy_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW);
     e->hn_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW); e->h1_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW);
@@ -883,45 +1030,84 @@ int b200_finalize_weights(b200_engine* e) {
                             (const void*)gemv_small_kernel<__nv_bfloat16, 8>, (const void*)gemv_small_kernel<__half, 8>, (const void*)gemv_ln_kernel<D_MODEL>, (const void*)gemv_ln_kernel<D_FLOW>, (const void*)layernorm_kernel<D_MODEL>,
                             (const void*)layernorm_kernel<D_FLOW>, 
                             (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
-                            (const void*)attn_flow_split_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
+                            (const void*)attn_flow_split_kernel<__nv_bfloat16>, (const void*)attn_flow_split_kernel<float>, (const void*)attn_tile_kernel<true>, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
                             (const void*)step_front_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma4_kernel,
                             (const void*)conv_n1_kernel, (const void*)shift_states_kernel};
         for (const void* k : ks) PTTS_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_mimi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM));
-    PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
-    if (cfg.kv_capacity * sizeof(float) > 48 * 1024) {
-        PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cfg.kv_capacity * sizeof(float))));
-        PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cfg.kv_capacity * sizeof(float))));
-    }
+    PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_split_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AfCfg<__nv_bfloat16>::SMEM));
+    PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_split_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AfCfg<float>::SMEM));
+    e->actx.row_slot = e->row_slot; e->actx.row_pos = e->row_pos; e->actx.cs = e->cs;
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     e->finalized = true;
     return B200_OK;
 }
 
-// ---- ragged FlowLM prefill of `R` rows already staged in pin_i = [slot | pos | token] and (for voice rows) h ----
+// ---- ragged FlowLM prefill (reference _run_flow_lm with T > 1, src/pocket_tts.cpp:40-98): rows = (slot, position, token | voice row), slot-major
+//      with ascending positions. Everything is staged once (pinned ring -> device) and enqueued without a host synchronisation; the rows are
+//      processed in chunks of max_prefill_rows (a later chunk of a sentence attends to the cache rows the earlier chunk appended). ----
 static void prefill_rows(b200_engine* e, const std::vector<int>& slots, const std::vector<int>& pos, const std::vector<int>* tokens, const float* x_host) {
-    const int total = (int)slots.size();
+    const int total = (int)slots.size(), MRp = e->cfg.max_prefill_rows;
+    if (total == 0) return;
+    const int nchunks = (total + MRp - 1) / MRp;
+    // tensor-core tile work list (bf16 cache): one item per run of <= 64 consecutive positions of one slot inside a chunk
+    std::vector<AtItem> items; std::vector<int> chunk_item0(nchunks + 1, 0);
+    if (!e->cfg.kv_f32) {
+        for (int c = 0; c < nchunks; c++) {
+            const int r0 = c * MRp, R = std::min(MRp, total - r0);
+            chunk_item0[c] = (int)items.size();
+            for (int i = 0; i < R;) {
+                int j = i + 1;
+                while (j < R && j - i < AT_ROWS && slots[r0 + j] == slots[r0 + i] && pos[r0 + j] == pos[r0 + j - 1] + 1) j++;
+                const int slot = slots[r0 + i], P = e->h_pfx_len[slot];
+                AtItem it{}; it.row0 = i; it.nrows = j - i; it.out_split = -1;
+                it.a_slot = e->h_pfx_slot[slot]; it.a_k0 = 0; it.a_k1 = P;                              // shared prefix rows (none: P = 0)
+                it.b_slot = slot; it.b_k0 = P; it.b_k1 = pos[r0 + j - 1] + 1;                            // own rows, causal
+                items.push_back(it);
+                i = j;
+            }
+        }
+        chunk_item0[nchunks] = (int)items.size();
+    }
+    e->grow(e->pf_int, e->pf_int_cap, (size_t)3 * total);
+    e->grow(e->pf_items, e->pf_items_cap, items.size() + 1);
+    e->grow(e->pf_meta, e->pf_meta_cap, (size_t)4 * nchunks);
+    if (x_host) e->grow(e->pf_x, e->pf_x_cap, (size_t)total * D_MODEL);
+    const size_t b_int = (size_t)3 * total * sizeof(int), b_meta = (size_t)4 * nchunks * sizeof(int), b_items = items.size() * sizeof(AtItem);
+    const size_t b_x = x_host ? (size_t)total * D_MODEL * sizeof(float) : 0;
+    char* pb = (char*)e->pin_acquire(b_int + b_meta + b_items + b_x + 256);
+    int* pi = (int*)pb;
+    for (int i = 0; i < total; i++) { pi[i] = slots[i]; pi[total + i] = pos[i]; pi[2 * total + i] = tokens ? (*tokens)[i] : 0; }
+    int* pm = pi + 3 * total;
+    for (int c = 0; c < nchunks; c++) { pm[4 * c] = chunk_item0[c + 1] - chunk_item0[c]; pm[4 * c + 1] = 0; pm[4 * c + 2] = 0; pm[4 * c + 3] = 0; }
+    char* pit = (char*)(pm + 4 * nchunks);
+    if (b_items) memcpy(pit, items.data(), b_items);
+    char* px = pit + ((b_items + 15) / 16) * 16;
+    if (x_host) memcpy(px, x_host, b_x);
+    PTTS_CUDA_CHECK(cudaMemcpyAsync(e->pf_int, pi, b_int, cudaMemcpyHostToDevice, e->stream));
+    PTTS_CUDA_CHECK(cudaMemcpyAsync(e->pf_meta, pm, b_meta, cudaMemcpyHostToDevice, e->stream));
+    if (b_items) PTTS_CUDA_CHECK(cudaMemcpyAsync(e->pf_items, pit, b_items, cudaMemcpyHostToDevice, e->stream));
+    if (x_host) PTTS_CUDA_CHECK(cudaMemcpyAsync(e->pf_x, px, b_x, cudaMemcpyHostToDevice, e->stream));
+    e->pin_release(e->stream);
     e->set_pdl(false);
-    for (int r0 = 0; r0 < total; r0 += e->cfg.max_prefill_rows) {
-        const int R = std::min(e->cfg.max_prefill_rows, total - r0);
-        e->ensure_pinned(x_host ? (size_t)R * D_MODEL : 1, (size_t)3 * R);
-        for (int i = 0; i < R; i++) { e->pin_i[i] = slots[r0 + i]; e->pin_i[R + i] = pos[r0 + i]; e->pin_i[2 * R + i] = tokens ? (*tokens)[r0 + i] : 0; }
-        PTTS_CUDA_CHECK(cudaMemcpyAsync(e->row_slot, e->pin_i, R * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-        PTTS_CUDA_CHECK(cudaMemcpyAsync(e->row_pos, e->pin_i + R, R * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    const b200_engine::AttnCtx saved = e->actx;
+    for (int c = 0; c < nchunks; c++) {
+        const int r0 = c * MRp, R = std::min(MRp, total - r0);
+        e->actx = b200_engine::AttnCtx{};
+        e->actx.row_slot = e->pf_int + r0; e->actx.row_pos = e->pf_int + total + r0; e->actx.cs = e->cs; e->actx.prefill = true;
+        e->actx.items = e->pf_items + chunk_item0[c]; e->actx.meta = e->pf_meta + 4 * c; e->actx.n_items = chunk_item0[c + 1] - chunk_item0[c];
         if (tokens) {
-            PTTS_CUDA_CHECK(cudaMemcpyAsync(e->tok, e->pin_i + 2 * R, R * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-            launch_k(false, embed_gather_kernel, dim3(R), dim3(256), (size_t)(0), e->stream, e->embed, e->tok, e->h, R);
+            launch_k(false, embed_gather_kernel, dim3(R), dim3(256), (size_t)(0), e->stream, e->embed, (const int*)(e->pf_int + 2 * total + r0), e->h, R);
             e->launches++;
         } else {
-            memcpy(e->pin_f, x_host + (size_t)r0 * D_MODEL, (size_t)R * D_MODEL * sizeof(float));
-            PTTS_CUDA_CHECK(cudaMemcpyAsync(e->h, e->pin_f, (size_t)R * D_MODEL * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+            PTTS_CUDA_CHECK(cudaMemcpyAsync(e->h, e->pf_x + (size_t)r0 * D_MODEL, (size_t)R * D_MODEL * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
         }
-        launch_k(false, rope_table_kernel, dim3((R * 32 + 255) / 256), dim3(256), (size_t)(0), e->stream, e->row_pos, e->freq_flow, e->cs, R);
+        launch_k(false, rope_table_kernel, dim3((R * 32 + 255) / 256), dim3(256), (size_t)(0), e->stream, e->actx.row_pos, e->freq_flow, e->cs, R);
         e->launches++;
         e->flow_forward(R);
-        PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));   // pinned staging is reused by the next chunk
     }
+    e->actx = saved;
 }
 
 int b200_voice_create(b200_engine* e, const float* audio_prompt, int T) {
@@ -942,54 +1128,67 @@ int b200_begin_sentences(b200_engine* e, int n, const int32_t* slots, const int3
                          const int32_t* tok_off, const int32_t* max_gen_len, const int32_t* frames_after_eos, const float* temp) {
     if (!e || !e->finalized || n < 0) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
-    e->join_mimi();                                           // the slot resets below touch Mimi state on the main stream
-    const size_t elt = e->cfg.kv_f32 ? 4 : 2;
     std::vector<int> rs, rp, rt;
     for (int i = 0; i < n; i++) {
         const int slot = slots[i], v = voices[i];
         if (slot < 0 || slot >= e->cfg.max_slots || v < 0 || v >= e->n_voices) return B200_EINVAL;
         const int nt = tok_off[i + 1] - tok_off[i];
         const int start = e->voice_len[v];
-        if (start + nt >= e->cfg.kv_capacity) return B200_ECAPACITY;
+        if (nt < 0 || start + nt >= e->cfg.kv_capacity) return B200_ECAPACITY;
         for (int t = 0; t < nt; t++) {
             const int id = tokens[tok_off[i] + t];
             if (id < 0 || id >= e->n_embed) return B200_EINVAL;
             rs.push_back(slot); rp.push_back(start + t); rt.push_back(id);
         }
     }
-    if (n > 0) {
-        // per-sentence metadata in one upload: [slot | src voice slot | prefix rows | cur_len | max_gen | frames_after_eos] x n, then temps
-        e->ensure_pinned((size_t)n, (size_t)6 * n);
-        PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));       // pinned staging may still feed an earlier copy
-        int max_prefix = 0;
-        for (int i = 0; i < n; i++) {
-            const int slot = slots[i], v = voices[i];
-            const int nt = tok_off[i + 1] - tok_off[i];
-            const int start = e->voice_len[v];
-            // KV capacity guard (the reference has none: 1000 rows, no bounds check, src/pocket_tts.cpp:367): clamp the cap.
-            int mg = max_gen_len[i];
-            const int room = e->cfg.kv_capacity - (start + nt);
-            if (mg > room) mg = room;
-            e->pin_i[i] = slot; e->pin_i[n + i] = e->cfg.max_slots + v; e->pin_i[2 * n + i] = start; e->pin_i[3 * n + i] = start + nt;
-            e->pin_i[4 * n + i] = mg; e->pin_i[5 * n + i] = frames_after_eos[i];
-            e->pin_f[i] = temp[i];
-            e->h_cur_len[slot] = start + nt;
-            max_prefix = std::max(max_prefix, start);
-        }
-        if ((size_t)n > e->begin_cap) {
-            e->begin_meta = e->dalloc<int>((size_t)6 * n, false); e->begin_temp = e->dalloc<float>((size_t)n, false); e->begin_cap = n;
-        }
-        PTTS_CUDA_CHECK(cudaMemcpyAsync(e->begin_meta, e->pin_i, (size_t)6 * n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-        PTTS_CUDA_CHECK(cudaMemcpyAsync(e->begin_temp, e->pin_f, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-        if (max_prefix > 0)
-            launch_k(false, begin_copy_prefix_kernel, dim3(8, 2 * N_LAYERS, n), dim3(256), (size_t)0, e->stream, n, (const int*)e->begin_meta, (char*)e->kc, (char*)e->vc,
-                     (long long)(e->kv_slot_stride * elt), (long long)(e->kv_layer_stride * elt), (long long)(D_MODEL * elt));
-        launch_k(false, begin_reset_kernel, dim3(n, e->shifts.n), dim3(256), (size_t)0, e->stream, n, (const int*)e->begin_meta, e->shifts, e->e_prev, e->mimi_off);
-        launch_k(false, begin_meta_kernel, dim3(n), dim3(32), (size_t)0, e->stream, n, (const int*)e->begin_meta, (const float*)e->begin_temp, (const float*)e->d_bos, e->cur_len,
-                 e->gen_step, e->eos_step, e->max_gen, e->fae, e->active, e->temp, e->lat_in_bf16, e->lat_f32);
-        e->launches += 3;
-        PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));       // prefill_rows reuses the pinned staging
+    if (n == 0) return B200_OK;
+    // A frame of these slots whose Mimi decode is still waiting for an interleaving partner must be decoded BEFORE the Mimi-state reset
+    // below (it belongs to the previous sentence). Nothing here waits on the host: uploads go through the pinned ring.
+    e->flush_pending();
+    // the previous call's Mimi-side reset reads the device copy of ITS metadata, which the upload below overwrites
+    if (e->begin_used) PTTS_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_reset, 0));
+    e->begin_used = true;
+    const size_t elt = e->cfg.kv_f32 ? 4 : 2;
+    // per-sentence metadata in one upload: [slot | src voice slot | prefix rows | cur_len | max_gen | frames_after_eos | shared rows] x n, then temps
+    int* pm = (int*)e->pin_acquire((size_t)8 * n * sizeof(int));
+    float* pt = (float*)(pm + 7 * n);
+    int max_copy = 0;
+    for (int i = 0; i < n; i++) {
+        const int slot = slots[i], v = voices[i];
+        const int nt = tok_off[i + 1] - tok_off[i];
+        const int start = e->voice_len[v];
+        // KV capacity guard (the reference has none: 1000 rows, no bounds check, src/pocket_tts.cpp:367): clamp the cap so that the last
+        // appended row is capacity-1; finished slots are dead rows on the device and never append (flow_in_kernel).
+        int mg = max_gen_len[i];
+        const int room = e->cfg.kv_capacity - (start + nt);
+        if (mg > room) mg = room;
+        const int shared = e->cfg.prefix_share ? start : 0;
+        pm[i] = slot; pm[n + i] = e->cfg.max_slots + v; pm[2 * n + i] = start; pm[3 * n + i] = start + nt;
+        pm[4 * n + i] = mg; pm[5 * n + i] = frames_after_eos[i]; pm[6 * n + i] = shared;
+        pt[i] = temp[i];
+        e->h_cur_len[slot] = start + nt;
+        if (e->h_pfx_slot[slot] != e->cfg.max_slots + v || e->h_pfx_len[slot] != shared) { e->h_pfx_slot[slot] = e->cfg.max_slots + v; e->h_pfx_len[slot] = shared; e->pfx_version++; }
+        if (!e->cfg.prefix_share) max_copy = std::max(max_copy, start);
     }
+    if ((size_t)n > e->begin_cap) {
+        e->begin_meta = e->dalloc<int>((size_t)7 * n, false); e->begin_temp = e->dalloc<float>((size_t)n, false); e->begin_cap = n;
+    }
+    PTTS_CUDA_CHECK(cudaMemcpyAsync(e->begin_meta, pm, (size_t)7 * n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    PTTS_CUDA_CHECK(cudaMemcpyAsync(e->begin_temp, pt, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    e->pin_release(e->stream);
+    if (max_copy > 0)   // reference semantics (prefix_share = 0): private copy of the voice-conditioned prefix, models/flow_lm.h:70-78
+        launch_k(false, begin_copy_prefix_kernel, dim3(8, 2 * N_LAYERS, n), dim3(256), (size_t)0, e->stream, n, (const int*)e->begin_meta, (char*)e->kc, (char*)e->vc,
+                 (long long)(e->kv_slot_stride * elt), (long long)(e->kv_layer_stride * elt), (long long)(D_MODEL * elt));
+    launch_k(false, begin_meta_kernel, dim3(n), dim3(128), (size_t)0, e->stream, n, (const int*)e->begin_meta, (const float*)e->begin_temp, (const float*)e->d_bos, e->cur_len,
+             e->gen_step, e->eos_step, e->max_gen, e->fae, e->active, e->temp, e->lat_in_bf16, e->lat_f32, e->pfx_slot, e->pfx_len, e->e_prev);
+    // Mimi-side reset on the Mimi stream: behind every Mimi decode already enqueued there, ahead of the new sentences' first decode. The
+    // main stream only waits for it when it touches Mimi state itself (join_mimi: synchronous b200_step, Mimi-only calls).
+    PTTS_CUDA_CHECK(cudaEventRecord(e->ev_begin, e->stream));
+    PTTS_CUDA_CHECK(cudaStreamWaitEvent(e->stream_m, e->ev_begin, 0));
+    launch_k(false, begin_reset_kernel, dim3(n, e->shifts.n), dim3(256), (size_t)0, e->stream_m, n, (const int*)e->begin_meta, e->shifts, e->mimi_off);
+    PTTS_CUDA_CHECK(cudaEventRecord(e->ev_reset, e->stream_m));
+    e->reset_pending = true;
+    e->launches += 3;
     if (!rs.empty()) prefill_rows(e, rs, rp, &rt, nullptr);
     return B200_OK;
 }
@@ -1037,6 +1236,8 @@ int b200_step(b200_engine* e, int slot0, int n, const float* noise, float* pcm, 
     // synchronous API: this frame's PCM is returned by this call, so there is nothing to overlap - replay the whole step as ONE graph
     // on the main stream (13 graph launches + events per frame would only add host latency, which is what batch-1 streaming feels)
     e->join_mimi();
+    e->prepare_decode(slot0, n);
+    e->tap_slot0 = slot0; e->tap_n = n;
     e->run_graphed(0, slot0, n, noise != nullptr);
     PTTS_CUDA_CHECK(cudaMemcpyAsync(p_pcm, e->pcm + (size_t)slot0 * FRAME, (size_t)n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     PTTS_CUDA_CHECK(cudaMemcpyAsync(e->pin_i, e->produced, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
@@ -1246,6 +1447,15 @@ void b200_profiler_range(int start) { if (start) cudaProfilerStart(); else cudaP
 
 void* b200_stream(b200_engine* e) { return e ? (void*)e->stream : nullptr; }
 
+// Debug read of a named f32 device buffer (see b200_device_ptr) after a full synchronisation: out[n] = buffer[offset .. offset+n).
+int b200_debug_read_f32(b200_engine* e, const char* name, long long offset, float* out, int n) {
+    float* p = (float*)b200_device_ptr(e, name);
+    if (!p || !out || n < 0 || offset < 0 || std::string(name) == "produced") return B200_EINVAL;
+    b200_sync(e);
+    PTTS_CUDA_CHECK(cudaMemcpy(out, p + offset, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
 void* b200_device_ptr(b200_engine* e, const char* name) {
     if (!e || !name) return nullptr;
     const std::string s = name;
@@ -1255,25 +1465,87 @@ void* b200_device_ptr(b200_engine* e, const char* name) {
     if (s == "produced") return e->produced;
     if (s == "eos") return e->eos_out;
     if (s == "lat_f32") return e->lat_f32;
+    if (s == "noise_drawn") return e->noise_f32;
     return nullptr;
 }
 
 long long b200_launch_count(b200_engine* e) { return e ? e->launches : 0; }
 
+// Logical cache rows [0, n_pos) of a slot: with a shared voice prefix the first rows come from the voice's resident copy.
 int b200_read_kv(b200_engine* e, int slot, int layer, int which, int n_pos, float* out) {
     if (!e || !e->finalized || slot < 0 || slot >= e->total_slots || layer < 0 || layer >= N_LAYERS || n_pos < 0 || n_pos > e->cfg.kv_capacity) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    const size_t n = (size_t)n_pos * D_MODEL;
-    const long long off = layer * e->kv_layer_stride + slot * e->kv_slot_stride;
-    if (e->cfg.kv_f32) {
-        PTTS_CUDA_CHECK(cudaMemcpy(out, (const float*)(which ? e->vc : e->kc) + off, n * 4, cudaMemcpyDeviceToHost));
-    } else {
-        std::vector<uint16_t> tmp(n);
-        PTTS_CUDA_CHECK(cudaMemcpy(tmp.data(), (const __nv_bfloat16*)(which ? e->vc : e->kc) + off, n * 2, cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < n; i++) { uint32_t u = (uint32_t)tmp[i] << 16; memcpy(&out[i], &u, 4); }
+    const int P = std::min(n_pos, e->h_pfx_len[slot]);
+    for (int part = 0; part < 2; part++) {
+        const int r0 = part == 0 ? 0 : P, r1 = part == 0 ? P : n_pos, src_slot = part == 0 ? e->h_pfx_slot[slot] : slot;
+        if (r1 <= r0) continue;
+        const size_t n = (size_t)(r1 - r0) * D_MODEL;
+        const long long off = layer * e->kv_layer_stride + src_slot * e->kv_slot_stride + (long long)r0 * D_MODEL;
+        float* dst = out + (size_t)r0 * D_MODEL;
+        if (e->cfg.kv_f32) {
+            PTTS_CUDA_CHECK(cudaMemcpy(dst, (const float*)(which ? e->vc : e->kc) + off, n * 4, cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<uint16_t> tmp(n);
+            PTTS_CUDA_CHECK(cudaMemcpy(tmp.data(), (const __nv_bfloat16*)(which ? e->vc : e->kc) + off, n * 2, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; i++) { uint32_t u = (uint32_t)tmp[i] << 16; memcpy(&dst[i], &u, 4); }
+        }
     }
     return B200_OK;
+}
+
+// Tap points for localising a parity failure (the reference's GraphContext::debug, src/context.h:526-547). Names are the ones the CPU
+// restatement under tests uses: "flow.layer<l>" = residual stream after FlowLM layer l [1024], "flow.attn<l>" = attention output of layer l [1024]
+// (both need b200_debug_taps(e, 1) before the step), "mimi.upsample" [16][512], "mimi.transformer" [16][512], "seanet.conv0" [16][512],
+// "seanet.convt2" [96][256], "seanet.res3" [96][256], "seanet.res6" [480][128], "seanet.res9" [1920][64] (state of the LAST step that
+// covered `slot`; low-precision buffers are widened to f32). Returns the element count, or a negative error.
+int b200_debug_taps(b200_engine* e, int on) {
+    if (!e || !e->finalized) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->join_mimi();
+    e->taps_on = on != 0;
+    return B200_OK;
+}
+int b200_debug_tap(b200_engine* e, const char* name, int slot, float* out, int max_elems) {
+    if (!e || !e->finalized || !name || slot < 0 || slot >= e->cfg.max_slots) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->join_mimi();
+    PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    const std::string s = name;
+    auto give_f32 = [&](const float* src, size_t n) -> int {
+        if (!out) return (int)n;
+        if ((size_t)max_elems < n) return B200_EINVAL;
+        PTTS_CUDA_CHECK(cudaMemcpy(out, src, n * sizeof(float), cudaMemcpyDeviceToHost));
+        return (int)n;
+    };
+    // rows [row0, row0 + rows) x the first `cols` of `ld` columns of a 16-bit buffer
+    auto give_16 = [&](const void* base, bool f16, long long slot_stride, int row0, int rows, int ld, int cols) -> int {
+        const size_t n = (size_t)rows * cols;
+        if (!out) return (int)n;
+        if ((size_t)max_elems < n) return B200_EINVAL;
+        std::vector<uint16_t> tmp((size_t)rows * ld);
+        PTTS_CUDA_CHECK(cudaMemcpy(tmp.data(), (const uint16_t*)base + (size_t)slot * slot_stride + (size_t)row0 * ld, tmp.size() * 2, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) {
+            const uint16_t u = tmp[(size_t)r * ld + c];
+            out[(size_t)r * cols + c] = f16 ? __half2float(*(const __half*)&u) : __bfloat162float(*(const __nv_bfloat16*)&u);
+        }
+        return (int)n;
+    };
+    if (s.rfind("flow.layer", 0) == 0 || s.rfind("flow.attn", 0) == 0) {
+        const bool att = s[5] == 'a';
+        const int l = atoi(s.c_str() + (att ? 9 : 10)), r = slot - e->tap_slot0;
+        if (l < 0 || l >= N_LAYERS || r < 0 || r >= e->tap_n) return B200_EINVAL;
+        if (att) return give_16(e->tap_att + (size_t)l * e->cfg.max_slots * D_MODEL, false, 0, r, 1, D_MODEL, D_MODEL);
+        return give_f32(e->tap_h + ((size_t)l * e->cfg.max_slots + r) * D_MODEL, D_MODEL);
+    }
+    if (s == "mimi.upsample") return give_f32(e->mx + (size_t)slot * M_T * M_DIM, (size_t)M_T * M_DIM);
+    if (s == "mimi.transformer") return give_16(e->buf0, true, 22LL * 512, 6, 16, 512, 512);
+    if (s == "seanet.conv0") return give_16(e->buf2, true, 17LL * e->C2, 1, 16, e->C2, 512);
+    if (s == "seanet.convt2") return give_f32(e->y3 + (size_t)slot * 96 * 256, (size_t)96 * 256);
+    if (s == "seanet.res3") return give_16(e->buf5, true, 97LL * e->C5, 1, 96, e->C5, 256);
+    if (s == "seanet.res6") return give_16(e->buf8, true, 481LL * e->C8, 1, 480, e->C8, 128);
+    if (s == "seanet.res9") return give_16(e->buf11, true, 1922LL * 64, 2, 1920, 64, 64);
+    return B200_ENOTFOUND;
 }
 
 // Host-only: the tile width / split-K plan the tensor-core GEMM dispatcher picks for a [R x K] . [N x K]^T product of one slot

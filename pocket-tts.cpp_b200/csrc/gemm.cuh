@@ -52,6 +52,7 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int row, int col0, const
     const int D = mimi ? M_DIM : D_MODEL;
     const int slot = e.row_slot[row];
     const int pos = e.row_pos[row];
+    if (slot < 0) return;                 // dead row (finished utterance): nothing is appended or handed on
 #pragma unroll
     for (int p = 0; p < NV; p += 2) {
         const int col = col0 + p;

@@ -28,10 +28,30 @@ public:
         if (fread(&n, 8, 1, f) != 1 || n == 0 || n > (1ull << 30)) { fclose(f); return false; }
         std::string js(n, '\0');
         if (fread(&js[0], 1, n, f) != n) { fclose(f); return false; }
-        fclose(f);
         data_base = 8 + (int64_t)n;
+        int64_t data_size = -1;
+        if (fseek(f, 0, SEEK_END) == 0) data_size = (int64_t)ftell(f) - data_base;
+        fclose(f);
         pos_ = 0; s_ = &js;
-        return parse_header();
+        if (!parse_header() || data_size < 0) return false;
+        // Reject malformed / truncated files up front: every consumer sizes its copies from the shape product
+        // (the reference trusts the file, src/safetensor.cpp; a user-supplied voice file must not cause an over-read).
+        for (auto& kv : entries) {
+            const StEntry& e = kv.second;
+            const int64_t esz = dtype_size(e.dtype);
+            int64_t count = 1;
+            for (int64_t d : e.shape) { if (d < 0 || (d > 0 && count > (int64_t)1 << 40)) return false; count *= d; }
+            if (e.begin < 0 || e.end < e.begin || e.end > data_size) return false;
+            if (esz > 0 && e.end - e.begin != count * esz) return false;
+        }
+        return true;
+    }
+    static int64_t dtype_size(const std::string& d) {
+        if (d == "F32" || d == "I32" || d == "U32") return 4;
+        if (d == "BF16" || d == "F16" || d == "I16" || d == "U16") return 2;
+        if (d == "F64" || d == "I64" || d == "U64") return 8;
+        if (d == "I8" || d == "U8" || d == "BOOL" || d == "F8_E4M3" || d == "F8_E5M2") return 1;
+        return 0;   // unknown dtype: size unchecked, the loader skips it anyway
     }
 
     // Reads one tensor's raw bytes (file dtype).

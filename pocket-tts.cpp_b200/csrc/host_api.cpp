@@ -78,6 +78,7 @@ struct ptts_context_t {
     std::vector<bool> slot_used;
     int n_streams = 0;
     bool lookahead = true;                  // PTTS_B200_LOOKAHEAD=0: strictly one step per receive
+    unsigned int seed_pushed = 0; bool seed_valid = false;   // last seed handed to the engine (ptts_set_seed is process-global)
 };
 
 struct ptts_stream_t {
@@ -134,6 +135,7 @@ ptts_context_t* ptts_init(ggml_backend*, ggml_backend*, const char* model_path) 
     cfg.cuda_graphs = env_int("PTTS_B200_CUDA_GRAPHS", 1);
     cfg.pdl = env_int("PTTS_B200_PDL", 1);
     cfg.overlap = env_int("PTTS_B200_OVERLAP", 1);
+    cfg.prefix_share = env_int("PTTS_B200_PREFIX_SHARE", 1);
     return init_with_config(model_path, cfg);
 }
 
@@ -154,6 +156,7 @@ ptts_stream_t* ptts_stream_from_safetensors(ptts_context_t* ctx, const char* voi
         std::vector<uint8_t> raw;
         if (e == st.entries.end() || !st.read(e->second, raw)) { fprintf(stderr, "error: failed to open voice %s\n", voice.c_str()); exit(1); }
         size_t n = 1; for (auto d : e->second.shape) n *= (size_t)d;
+        if (n == 0 || n % 1024 != 0) { fprintf(stderr, "error: voice %s: audio_prompt has %zu elements, not a multiple of 1024\n", voice.c_str(), n); exit(1); }
         std::vector<float> prompt(n);
         if (e->second.dtype == "F32") memcpy(prompt.data(), raw.data(), n * 4);
         else if (e->second.dtype == "BF16") { const uint16_t* s = (const uint16_t*)raw.data(); for (size_t i = 0; i < n; i++) { uint32_t u = (uint32_t)s[i] << 16; memcpy(&prompt[i], &u, 4); } }
@@ -195,10 +198,16 @@ static bool stream_step(ptts_stream_t* s, float* samples) {
     if (s->generation_step >= s->max_gen_len) { fprintf(stderr, "warning: called with high gen step\n"); return false; }
     int32_t produced = 0;
     b200_engine* eng = s->ctx->engine;
-    b200_set_seed(eng, g_seed);
+    if (s->ctx->seed_pushed != g_seed || !s->ctx->seed_valid) { b200_set_seed(eng, g_seed); s->ctx->seed_pushed = g_seed; s->ctx->seed_valid = true; }
     if (!s->ctx->lookahead || s->ctx->n_streams != 1) {               // several streams share the engine's in-order frame queue: stay synchronous
-        stream_drain(s);
-        if (b200_step(eng, s->slot, 1, nullptr, samples, &produced, nullptr, nullptr) != B200_OK) { fprintf(stderr, "error: step failed\n"); exit(1); }
+        if (s->inflight > 0) {
+            // This stream submitted look-ahead frames while it was alone in the context and a second stream has appeared since. The engine
+            // has already advanced the slot for those frames (gen_step, latent feedback), so they ARE the next frames of this stream:
+            // hand them out in order instead of dropping them (only a stream that was alone can own in-flight frames, so the engine's
+            // in-order queue holds nothing else).
+            if (b200_collect(eng, samples, &produced) < 0) { fprintf(stderr, "error: step failed\n"); exit(1); }
+            s->inflight--;
+        } else if (b200_step(eng, s->slot, 1, nullptr, samples, &produced, nullptr, nullptr) != B200_OK) { fprintf(stderr, "error: step failed\n"); exit(1); }
     } else {
         if (s->inflight == 0) { if (b200_submit(eng, s->slot, 1, nullptr) != B200_OK) { fprintf(stderr, "error: step failed\n"); exit(1); } s->inflight++; }
         if (s->generation_step + s->inflight < s->max_gen_len && s->inflight < 2) {

@@ -90,86 +90,29 @@ __global__ void __launch_bounds__(C / 4) layernorm_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// FlowLM attention, one query row against its slot's cache rows [0, pos] (reference
-// modules/transformer.h:157-199, src/torch.h:128-150: scale 1/8, causal by construction, softmax with f32
-// probabilities, f32 PV). One CTA per (row, head). Baseline implementation; see attn_flow_split_kernel.
+// FlowLM attention (reference modules/transformer.h:157-199, src/torch.h:128-150: scale 1/8, causal, softmax with f32
+// probabilities, f32 PV). Two kernels share the work:
+//   * attn_flow_split_kernel<KV>  — split-KV STREAMING kernel, one query row per CTA: the per-utterance part of the cache
+//                                    (HBM bound; bf16 or the reference's f32 cache type);
+//   * attn_tile_kernel            — tensor-core (mma.sync) flash tile: 64 query rows x one head against a key range that
+//                                    MANY rows have in common (the shared voice prefix in decode) or that the rows of one
+//                                    slot need under the causal mask (prefill, transformer.h:157-169).
+// Both produce either the normalised bf16 output or a partial (max, sum, unnormalised acc) per (row, head) in a workspace
+// [row][AF_WS_STRIDE entries]; the last streaming CTA of a row merges all partials of that row in a fixed order.
+// Rows whose row_slot is negative are DEAD (finished utterances still inside the stepped slot range): nothing is read,
+// appended or written for them.
 // ------------------------------------------------------------------------------------------------
-template <typename KV>
-__global__ void __launch_bounds__(128) attn_flow_kernel(const float* __restrict__ q, const KV* __restrict__ kc, const KV* __restrict__ vc,
-                                                        long long kv_slot_stride, const int* __restrict__ row_slot,
-                                                        const int* __restrict__ row_pos, __nv_bfloat16* __restrict__ out) {
-    pdl_prologue();
-    extern __shared__ float sc[];                 // [len] scores
-    __shared__ float qs[D_HEAD];
-    __shared__ float red[4];
-    __shared__ float pv[4][D_HEAD];
-    const int row = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int len = row_pos[row] + 1;
-    const KV* K = kc + (long long)row_slot[row] * kv_slot_stride + h * D_HEAD;
-    const KV* V = vc + (long long)row_slot[row] * kv_slot_stride + h * D_HEAD;
-    if (tid < D_HEAD) qs[tid] = q[(long long)row * D_MODEL + h * D_HEAD + tid];
-    __syncthreads();
-    float mx = -INFINITY;
-    for (int j = tid; j < len; j += 128) {
-        const KV* kr = K + (long long)j * D_MODEL;
-        float acc = 0.f;
-#pragma unroll
-        for (int d = 0; d < D_HEAD; d += 8) {
-            if constexpr (sizeof(KV) == 2) {
-                const uint4 kv = *reinterpret_cast<const uint4*>(kr + d);
-                const __nv_bfloat16* ke = reinterpret_cast<const __nv_bfloat16*>(&kv);
-#pragma unroll
-                for (int t = 0; t < 8; t++) acc = fmaf(__bfloat162float(ke[t]), qs[d + t], acc);
-            } else {
-                const float4 k0 = *reinterpret_cast<const float4*>(kr + d), k1 = *reinterpret_cast<const float4*>(kr + d + 4);
-                acc = fmaf(k0.x, qs[d], acc); acc = fmaf(k0.y, qs[d + 1], acc); acc = fmaf(k0.z, qs[d + 2], acc); acc = fmaf(k0.w, qs[d + 3], acc);
-                acc = fmaf(k1.x, qs[d + 4], acc); acc = fmaf(k1.y, qs[d + 5], acc); acc = fmaf(k1.z, qs[d + 6], acc); acc = fmaf(k1.w, qs[d + 7], acc);
-            }
-        }
-        acc *= 0.125f;
-        sc[j] = acc;
-        mx = fmaxf(mx, acc);
-    }
-    mx = warp_max(mx);
-    if (lane == 0) red[wid] = mx;
-    __syncthreads();
-    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-    __syncthreads();
-    float sum = 0.f;
-    for (int j = tid; j < len; j += 128) { const float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
-    sum = warp_sum(sum);
-    if (lane == 0) red[wid] = sum;
-    __syncthreads();
-    const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
-    float a0 = 0.f, a1 = 0.f;
-    for (int j = wid; j < len; j += 4) {
-        const float p = sc[j] * inv;
-        const KV* vr = V + (long long)j * D_MODEL + 2 * lane;
-        a0 = fmaf(p, to_f32<KV>(vr[0]), a0);
-        a1 = fmaf(p, to_f32<KV>(vr[1]), a1);
-    }
-    pv[wid][2 * lane] = a0; pv[wid][2 * lane + 1] = a1;
-    __syncthreads();
-    if (tid < D_HEAD) {
-        const float o = pv[0][tid] + pv[1][tid] + pv[2][tid] + pv[3][tid];
-        out[(long long)row * D_MODEL + h * D_HEAD + tid] = __float2bfloat16_rn(o);
-    }
-}
+constexpr int AF_STAGES = 3, AF_KEYS = 8;
+constexpr int AF_MAX_SPLITS = 16, AF_PFX_SPLITS = 8, AF_WS_STRIDE = AF_MAX_SPLITS + AF_PFX_SPLITS;
 
-// ------------------------------------------------------------------------------------------------
-// FlowLM attention, split-KV streaming version for the bf16 cache (the dominant kernel at large batch: pure KV stream).
-// One CTA per (KV split, query row), all 16 heads at once so that every cache row is read as one contiguous 2 KB line.
-// Warp 8 lane 0 is the producer: it streams groups of 8 consecutive K rows and V rows (16 KB each, contiguous in the
-// cache) into a 3-stage shared-memory ring (two CTAs per SM: 192 KB in flight per SM) with cp.async.bulk + mbarrier complete_tx. Consumer warp w owns key w of each
-// stage: lane l, chunk i reads the 16 bytes at i*512 + l*16 of the row = 8 dims of head 4i + l/8, so a row is four
-// conflict-free LDS.128 per lane; the dot products are finished with three shuffles inside each 8-lane group; softmax is
-// the online (running max / sum) form in fp32. Partial (m, l, acc) per split go to a workspace and attn_flow_merge_kernel
-// combines them (for one split the normalised bf16 output is written directly).
-// Same math as attn_flow_kernel (reference modules/transformer.h:157-199, src/torch.h:128-150).
-// ------------------------------------------------------------------------------------------------
-constexpr int AF_STAGES = 3, AF_KEYS = 8, AF_ROW_BYTES = D_MODEL * 2, AF_STAGE_BYTES = 2 * AF_KEYS * AF_ROW_BYTES;   // 32 KB
-constexpr int AF_SMEM = AF_STAGES * AF_STAGE_BYTES + 128;
-constexpr int AF_MAX_SPLITS = 16;
+template <typename KV> struct AfCfg {
+    static constexpr int ROW_BYTES = D_MODEL * (int)sizeof(KV);          // one cache row, all 16 heads: 2 KB (bf16) / 4 KB (f32)
+    static constexpr int STAGE_BYTES = 2 * AF_KEYS * ROW_BYTES;          // 8 K rows + 8 V rows: 32 KB / 64 KB
+    static constexpr int SMEM = AF_STAGES * STAGE_BYTES + 128;
+    static constexpr int NCH = ROW_BYTES / 512;                          // 16-byte chunks per lane and row: 4 / 8
+    static constexpr int EPC = 16 / (int)sizeof(KV);                     // elements per chunk: 8 / 4
+    static constexpr int LPH = D_HEAD / EPC;                             // lanes sharing a head: 8 / 16
+};
 
 __device__ __forceinline__ uint32_t af_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void af_mbar_wait(uint32_t bar, uint32_t parity) {
@@ -179,23 +122,47 @@ __device__ __forceinline__ void af_mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // hardware sleep until the phase flips
     } while (!ok);
 }
+__device__ __forceinline__ void af_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
 
-__global__ void __launch_bounds__(288, 2) attn_flow_split_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
-                                                                 const __nv_bfloat16* __restrict__ vc, long long kv_slot_stride,
-                                                                 const int* __restrict__ row_slot, const int* __restrict__ row_pos, int splits,
-                                                                 float* __restrict__ ws_ml, float* __restrict__ ws_acc,
-                                                                 __nv_bfloat16* __restrict__ out, int* __restrict__ merge_cnt) {
+// Per-launch description of the keys a row attends to.
+//   pfx_slot / pfx_len (per SLOT, may be null): keys [0, P) of the row live in ANOTHER slot's cache (the voice prefix shared by every
+//   utterance of that voice, reference copy_states models/flow_lm.h:70-78 made a private copy instead); keys [P, pos] are the slot's own.
+//   tiles_meta (may be null): {item count, prefix splits} of an attn_tile_kernel launch that ALREADY reduced keys [0, P) of every row with
+//   P > 0 into workspace entries [AF_MAX_SPLITS, AF_MAX_SPLITS + prefix splits); this kernel then streams only [P, pos] and merges both.
+struct AfKeys { const int* pfx_slot; const int* pfx_len; const int* tiles_meta; };
+
+// One CTA per (KV split, query row), all 16 heads at once so that every cache row is read as one contiguous 2/4 KB line. Warp 8 lane 0
+// is the producer: it streams groups of 8 consecutive K rows and V rows into a 3-stage shared-memory ring with cp.async.bulk + mbarrier
+// complete_tx (bf16: two CTAs per SM = 192 KB in flight per SM; f32: one CTA of 192 KB). Consumer warp w owns key w of each stage: lane l,
+// chunk i reads the 16 bytes at i*512 + l*16 of the row, so a row is NCH conflict-free LDS.128 per lane; the dot products are finished
+// with shuffles inside each LPH-lane group; softmax is the online (running max / sum) form in fp32.
+template <typename KV>
+__global__ void __launch_bounds__(288, sizeof(KV) == 2 ? 2 : 1)
+attn_flow_split_kernel(const float* __restrict__ q, const KV* __restrict__ kc, const KV* __restrict__ vc, long long kv_slot_stride,
+                       const int* __restrict__ row_slot, const int* __restrict__ row_pos, const AfKeys keys, int splits,
+                       float* __restrict__ ws_ml, float* __restrict__ ws_acc, __nv_bfloat16* __restrict__ out, int* __restrict__ merge_cnt) {
+    using C = AfCfg<KV>;
     pdl_prologue();
     extern __shared__ __align__(128) uint8_t af_smem[];
     const int row = blockIdx.y, split = blockIdx.x;
+    const int slot = row_slot[row];
+    if (slot < 0) return;                                          // dead row: uniform for the whole CTA, before any barrier
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int len = row_pos[row] + 1;
-    int chunk = (len + splits - 1) / splits; chunk = (chunk + AF_KEYS - 1) / AF_KEYS * AF_KEYS;
-    const int j_begin = split * chunk, j_end = min(len, j_begin + chunk);
-    const int n_keys = max(0, j_end - j_begin);
+    int P = 0, pslot = slot, n_extra = 0;
+    if (keys.pfx_len) { P = min(keys.pfx_len[slot], len); pslot = keys.pfx_slot[slot]; }
+    if (keys.tiles_meta && P > 0) n_extra = keys.tiles_meta[1];
+    const int nA = n_extra > 0 ? 0 : P;                            // prefix keys streamed by this kernel
+    const int ntot = nA + (len - P);                               // concatenated key space [A | B]
+    int chunk = (ntot + splits - 1) / splits; chunk = (chunk + AF_KEYS - 1) / AF_KEYS * AF_KEYS;
+    const int c_begin = split * chunk, c_end = min(ntot, c_begin + chunk);
+    const int n_keys = max(0, c_end - c_begin);
     const int n_stages_total = (n_keys + AF_KEYS - 1) / AF_KEYS;
     const uint32_t sbase = af_smem_u32(af_smem);
-    const uint32_t bars = sbase + AF_STAGES * AF_STAGE_BYTES;      // full[4] | empty[4]
+    const uint32_t bars = sbase + AF_STAGES * C::STAGE_BYTES;      // full[3] | empty[3]
     if (threadIdx.x == 0) {
         for (int s = 0; s < AF_STAGES; s++) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8 * s), "r"(1));
@@ -205,147 +172,375 @@ __global__ void __launch_bounds__(288, 2) attn_flow_split_kernel(const float* __
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    const long long slot_off = (long long)row_slot[row] * kv_slot_stride;
 
     if (warp == 8) {
         if (lane == 0) {
-            // the KV stream is read exactly once per step: mark it evict-first so that it does not push the Mimi stream's operands
-            // (re-read by many tiles) and the next GEMM's prefetched weights out of L2
+            // the per-utterance KV stream is read exactly once per step: mark it evict-first so that it does not push the Mimi stream's
+            // operands (re-read by many tiles), the shared prefix and the next GEMM's prefetched weights out of L2
             uint64_t pol;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-            const char* kg = reinterpret_cast<const char*>(kc + slot_off + (long long)j_begin * D_MODEL);
-            const char* vg = reinterpret_cast<const char*>(vc + slot_off + (long long)j_begin * D_MODEL);
+            const char* kA = reinterpret_cast<const char*>(kc + (long long)pslot * kv_slot_stride);
+            const char* vA = reinterpret_cast<const char*>(vc + (long long)pslot * kv_slot_stride);
+            const char* kB = reinterpret_cast<const char*>(kc + (long long)slot * kv_slot_stride);
+            const char* vB = reinterpret_cast<const char*>(vc + (long long)slot * kv_slot_stride);
             for (int it = 0; it < n_stages_total; it++) {
                 const int s = it % AF_STAGES; const uint32_t ph = (it / AF_STAGES) & 1;
                 af_mbar_wait(bars + 8 * (AF_STAGES + s), ph ^ 1);
-                const int nk = min(AF_KEYS, n_keys - it * AF_KEYS);
-                const uint32_t bytes = (uint32_t)nk * AF_ROW_BYTES;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8 * s), "r"(2 * bytes) : "memory");
-                const uint32_t dst = sbase + s * AF_STAGE_BYTES;
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                             ::"r"(dst), "l"(kg + (long long)it * AF_KEYS * AF_ROW_BYTES), "r"(bytes), "r"(bars + 8 * s), "l"(pol) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                             ::"r"(dst + AF_KEYS * AF_ROW_BYTES), "l"(vg + (long long)it * AF_KEYS * AF_ROW_BYTES), "r"(bytes), "r"(bars + 8 * s), "l"(pol) : "memory");
+                const int c0 = c_begin + it * AF_KEYS;
+                const int nk = min(AF_KEYS, c_end - c0);
+                const int na = max(0, min(nk, nA - c0));           // rows of this stage that come from the shared prefix
+                const int nb = nk - na;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8 * s), "r"(2u * (uint32_t)nk * C::ROW_BYTES) : "memory");
+                const uint32_t dk = sbase + s * C::STAGE_BYTES, dv = dk + AF_KEYS * C::ROW_BYTES;
+                if (na > 0) {
+                    af_bulk_load(dk, kA + (long long)c0 * C::ROW_BYTES, (uint32_t)na * C::ROW_BYTES, bars + 8 * s, pol);
+                    af_bulk_load(dv, vA + (long long)c0 * C::ROW_BYTES, (uint32_t)na * C::ROW_BYTES, bars + 8 * s, pol);
+                }
+                if (nb > 0) {
+                    const long long rb = (long long)(P + max(0, c0 - nA)) * C::ROW_BYTES;      // own rows start at position P
+                    af_bulk_load(dk + na * C::ROW_BYTES, kB + rb, (uint32_t)nb * C::ROW_BYTES, bars + 8 * s, pol);
+                    af_bulk_load(dv + na * C::ROW_BYTES, vB + rb, (uint32_t)nb * C::ROW_BYTES, bars + 8 * s, pol);
+                }
             }
         }
-    } else {
-        // ---- consumers: lane owns dims d(i,e) = i*256 + lane*8 + e of head 4i + lane/8 ----
-        float qr[4][8];
+        return;                                                    // the producer warp takes no part in the merge below (named barrier 1)
+    }
+    // ---- consumers: lane owns elements i * (512 / sizeof(KV)) + lane * EPC + e of the row, i.e. of head (that index) / 64 ----
+    float qr[C::NCH][C::EPC];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const float* qp = q + (long long)row * D_MODEL + i * 256 + lane * 8;
-            const float4 a = *reinterpret_cast<const float4*>(qp), b = *reinterpret_cast<const float4*>(qp + 4);
-            qr[i][0] = a.x * 0.125f; qr[i][1] = a.y * 0.125f; qr[i][2] = a.z * 0.125f; qr[i][3] = a.w * 0.125f;
-            qr[i][4] = b.x * 0.125f; qr[i][5] = b.y * 0.125f; qr[i][6] = b.z * 0.125f; qr[i][7] = b.w * 0.125f;
+    for (int i = 0; i < C::NCH; i++) {
+        const float* qp = q + (long long)row * D_MODEL + i * (512 / (int)sizeof(KV)) + lane * C::EPC;
+#pragma unroll
+        for (int e = 0; e < C::EPC; e += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(qp + e);
+            qr[i][e] = a.x * 0.125f; qr[i][e + 1] = a.y * 0.125f; qr[i][e + 2] = a.z * 0.125f; qr[i][e + 3] = a.w * 0.125f;
         }
-        float m[4], l[4], acc[4][8];
+    }
+    float m[C::NCH], l[C::NCH], acc[C::NCH][C::EPC];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { m[i] = -INFINITY; l[i] = 0.f;
+    for (int i = 0; i < C::NCH; i++) { m[i] = -INFINITY; l[i] = 0.f;
 #pragma unroll
-            for (int e = 0; e < 8; e++) acc[i][e] = 0.f; }
-        for (int it = 0; it < n_stages_total; it++) {
-            const int s = it % AF_STAGES; const uint32_t ph = (it / AF_STAGES) & 1;
-            af_mbar_wait(bars + 8 * s, ph);
-            const int nk = min(AF_KEYS, n_keys - it * AF_KEYS);
-            if (warp < nk) {
-                const uint8_t* kr = af_smem + s * AF_STAGE_BYTES + warp * AF_ROW_BYTES + lane * 16;
-                const uint8_t* vr = kr + AF_KEYS * AF_ROW_BYTES;
-                float sc[4];
+        for (int e = 0; e < C::EPC; e++) acc[i][e] = 0.f; }
+    for (int it = 0; it < n_stages_total; it++) {
+        const int s = it % AF_STAGES; const uint32_t ph = (it / AF_STAGES) & 1;
+        af_mbar_wait(bars + 8 * s, ph);
+        const int nk = min(AF_KEYS, n_keys - it * AF_KEYS);
+        if (warp < nk) {
+            const uint8_t* kr = af_smem + s * C::STAGE_BYTES + warp * C::ROW_BYTES + lane * 16;
+            const uint8_t* vr = kr + AF_KEYS * C::ROW_BYTES;
+            float sc[C::NCH];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint4 kv = *reinterpret_cast<const uint4*>(kr + i * 512);
+            for (int i = 0; i < C::NCH; i++) {
+                const uint4 kv = *reinterpret_cast<const uint4*>(kr + i * 512);
+                float a = 0.f;
+                if constexpr (sizeof(KV) == 2) {
                     const uint32_t w[4] = {kv.x, kv.y, kv.z, kv.w};
-                    float a = 0.f;
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
                         a = fmaf(__uint_as_float(w[t] << 16), qr[i][2 * t], a);
                         a = fmaf(__uint_as_float(w[t] & 0xffff0000u), qr[i][2 * t + 1], a);
                     }
-                    a += __shfl_xor_sync(0xffffffffu, a, 4);
-                    a += __shfl_xor_sync(0xffffffffu, a, 2);
-                    a += __shfl_xor_sync(0xffffffffu, a, 1);
-                    sc[i] = a;
+                } else {
+                    a = fmaf(__uint_as_float(kv.x), qr[i][0], a); a = fmaf(__uint_as_float(kv.y), qr[i][1], a);
+                    a = fmaf(__uint_as_float(kv.z), qr[i][2], a); a = fmaf(__uint_as_float(kv.w), qr[i][3], a);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float mn = fmaxf(m[i], sc[i]);
-                    const float corr = expf(m[i] - mn), p = expf(sc[i] - mn);
-                    m[i] = mn; l[i] = l[i] * corr + p;
-                    const uint4 vv = *reinterpret_cast<const uint4*>(vr + i * 512);
+                for (int o = C::LPH / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                sc[i] = a;
+            }
+#pragma unroll
+            for (int i = 0; i < C::NCH; i++) {
+                const float mn = fmaxf(m[i], sc[i]);
+                const float corr = expf(m[i] - mn), p = expf(sc[i] - mn);
+                m[i] = mn; l[i] = l[i] * corr + p;
+                const uint4 vv = *reinterpret_cast<const uint4*>(vr + i * 512);
+                if constexpr (sizeof(KV) == 2) {
                     const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
                         acc[i][2 * t] = fmaf(acc[i][2 * t], corr, p * __uint_as_float(w[t] << 16));
                         acc[i][2 * t + 1] = fmaf(acc[i][2 * t + 1], corr, p * __uint_as_float(w[t] & 0xffff0000u));
                     }
+                } else {
+                    acc[i][0] = fmaf(acc[i][0], corr, p * __uint_as_float(vv.x)); acc[i][1] = fmaf(acc[i][1], corr, p * __uint_as_float(vv.y));
+                    acc[i][2] = fmaf(acc[i][2], corr, p * __uint_as_float(vv.z)); acc[i][3] = fmaf(acc[i][3], corr, p * __uint_as_float(vv.w));
                 }
             }
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * (AF_STAGES + s)) : "memory");
         }
-        // ---- cross-warp merge through shared memory (ring is drained: every stage was consumed by all 8 warps) ----
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        float* sm_m = reinterpret_cast<float*>(af_smem);               // [8][16]
-        float* sm_l = sm_m + 8 * 16;                                   // [8][16]
-        float* sm_a = sm_l + 8 * 16;                                   // [8][1024]
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * (AF_STAGES + s)) : "memory");
+    }
+    // ---- cross-warp merge through shared memory (ring is drained: every stage was consumed by all 8 warps) ----
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float* sm_m = reinterpret_cast<float*>(af_smem);               // [8][16]
+    float* sm_l = sm_m + 8 * 16;                                   // [8][16]
+    float* sm_a = sm_l + 8 * 16;                                   // [8][1024]
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if ((lane & 7) == 0) { sm_m[warp * 16 + 4 * i + (lane >> 3)] = m[i]; sm_l[warp * 16 + 4 * i + (lane >> 3)] = l[i]; }
-            float* ap = sm_a + warp * D_MODEL + i * 256 + lane * 8;
-            *reinterpret_cast<float4*>(ap) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            *reinterpret_cast<float4*>(ap + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    for (int i = 0; i < C::NCH; i++) {
+        const int e0 = i * (512 / (int)sizeof(KV)) + lane * C::EPC;  // first element this lane owns in chunk i
+        if ((lane % C::LPH) == 0) { sm_m[warp * 16 + (e0 >> 6)] = m[i]; sm_l[warp * 16 + (e0 >> 6)] = l[i]; }
+        float* ap = sm_a + warp * D_MODEL + e0;
+#pragma unroll
+        for (int e = 0; e < C::EPC; e += 4) *reinterpret_cast<float4*>(ap + e) = make_float4(acc[i][e], acc[i][e + 1], acc[i][e + 2], acc[i][e + 3]);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int t = threadIdx.x;                                     // 0..255: dims 4t..4t+3, head t/16
+    const int h = t >> 4;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; w++) M = fmaxf(M, sm_m[w * 16 + h]);
+    float L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const float mw = sm_m[w * 16 + h];
+        const float sc = (mw == -INFINITY) ? 0.f : expf(mw - M);
+        L = fmaf(sm_l[w * 16 + h], sc, L);
+        const float4 a = *reinterpret_cast<const float4*>(sm_a + w * D_MODEL + 4 * t);
+        o[0] = fmaf(a.x, sc, o[0]); o[1] = fmaf(a.y, sc, o[1]); o[2] = fmaf(a.z, sc, o[2]); o[3] = fmaf(a.w, sc, o[3]);
+    }
+    if (splits == 1 && n_extra == 0) {
+        const float inv = 1.0f / L;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0] * inv, o[1] * inv), p1 = __floats2bfloat162_rn(o[2] * inv, o[3] * inv);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(out + (long long)row * D_MODEL + 4 * t) = pk;
+        return;
+    }
+    const long long wrow = (long long)row * AF_WS_STRIDE;
+    if ((t & 15) == 0) { ws_ml[(wrow + split) * 32 + h] = M; ws_ml[(wrow + split) * 32 + 16 + h] = L; }
+    *reinterpret_cast<float4*>(ws_acc + (wrow + split) * D_MODEL + 4 * t) = make_float4(o[0], o[1], o[2], o[3]);
+    // The LAST split CTA of a row to finish merges all of the row's partials (fixed entry order: deterministic) and writes the bf16
+    // output, which removes the separate merge launch from every layer. Release/acquire through the per-row counter. The prefix
+    // partials (entries AF_MAX_SPLITS..) were written by an EARLIER kernel of the same stream, hence are already visible.
+    __threadfence();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    int* flag = reinterpret_cast<int*>(af_smem);
+    if (t == 0) { const int prev = atomicAdd(merge_cnt + row, 1); *flag = (prev == splits - 1); if (prev == splits - 1) merge_cnt[row] = 0; }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (!*flag) return;
+    __threadfence();
+    const int n_ent = splits + n_extra;
+    float Mm = -INFINITY;
+    for (int e = 0; e < n_ent; e++) { const int sp = e < splits ? e : AF_MAX_SPLITS + (e - splits); Mm = fmaxf(Mm, __ldcg(ws_ml + (wrow + sp) * 32 + h)); }
+    float Lm = 0.f, om[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int e = 0; e < n_ent; e++) {
+        const long long w2 = wrow + (e < splits ? e : AF_MAX_SPLITS + (e - splits));
+        const float ms = __ldcg(ws_ml + w2 * 32 + h);
+        const float sc = (ms == -INFINITY) ? 0.f : expf(ms - Mm);
+        Lm = fmaf(__ldcg(ws_ml + w2 * 32 + 16 + h), sc, Lm);
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(ws_acc + w2 * D_MODEL + 4 * t));
+        om[0] = fmaf(a.x, sc, om[0]); om[1] = fmaf(a.y, sc, om[1]); om[2] = fmaf(a.z, sc, om[2]); om[3] = fmaf(a.w, sc, om[3]);
+    }
+    const float inv = 1.0f / Lm;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(om[0] * inv, om[1] * inv), p1 = __floats2bfloat162_rn(om[2] * inv, om[3] * inv);
+    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(out + (long long)row * D_MODEL + 4 * t) = pk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core attention tile (bf16 cache): one CTA = 64 query rows x ONE head x a list of key blocks, flash style (online softmax,
+// S = Q K^T and O += P V on mma.sync m16n8k16 bf16 -> f32; warp w owns query rows 16w .. 16w+15).
+//   decode, shared voice prefix: the query rows are all utterances of one voice (row_list), the keys a split of that voice's prefix:
+//     every prefix row is read once per 64 utterances (from L2) instead of once per utterance (from HBM). Output = partial.
+//   prefill: the query rows are consecutive positions of one slot, keys = [shared prefix | own rows up to the row's position]
+//     (causal mask key <= shift + query, transformer.h:157-169). Output = normalised bf16 rows.
+// Precision: the reference computes attention in f32 on an f32 cache. K/V are bf16 here (cfg.kv_f32 = 0); q and the probabilities
+// would lose another 8 bits as single bf16 MMA operands, so both are fed as hi + lo bf16 pairs (two MMAs each, ~16 mantissa bits):
+// the tile kernel then agrees with the f32-FMA streaming kernel to ~1e-5 relative (tests/test_gpu_attention.py).
+// No ldmatrix: the contraction index (QK^T) and the output-dim index (PV) are permuted so that every shared-memory access is a
+// conflict-free LDS.128 (same fragment scheme as attn_mimi_mma4_kernel below):
+//   * QK^T: lane (g, t) loads K[key 8j+g][32p + 8t .. +7]; its 8 values are the k-slots of two k16 steps, Q fragments use the same order;
+//   * PV: output tile n holds dims {8c + n}: lane (g, t) loads V[key][8g .. 8g+7] for its four keys 16s + {2t, 2t+1, 8+2t, 9+2t};
+//     PRMT interleaves key pairs. The lane ends up owning O[row][16t .. 16t+15].
+// Shared memory: K and V blocks of 64 keys x 64 dims (8 KB each), double buffered with cp.async; the 16-byte chunk c of key row r is
+// stored at chunk c ^ ((r & 1) << 2) for K and c ^ (((r >> 1) & 3) << 1) for V (both access patterns above hit 32 distinct banks).
+// ------------------------------------------------------------------------------------------------
+struct AtItem {
+    int row0, nrows;               // query rows: row_list[row0 + i] (or row0 + i when row_list is null), i < nrows <= 64
+    int a_slot, a_k0, a_k1;        // segment A: keys [a_k0, a_k1) of slot a_slot, visible to every row (shared prefix)
+    int b_slot, b_k0, b_k1;        // segment B: keys [b_k0, b_k1) of slot b_slot, key k visible to a row iff k <= row_pos[row]
+    int out_split;                 // >= 0: partial -> workspace entry out_split of each row; < 0: normalised bf16 -> out
+    int pad0, pad1, pad2;
+};
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void at_split2(float x, float y, uint32_t& hi, uint32_t& lo) {      // (x, y) -> bf16x2 hi, bf16x2 lo
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+constexpr int AT_ROWS = 64, AT_KEYS = 64, AT_TILE_BYTES = AT_KEYS * D_HEAD * 2;   // 8 KB
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kc, const __nv_bfloat16* __restrict__ vc,
+                                                        long long kv_slot_stride, const AtItem* __restrict__ items, const int* __restrict__ meta,
+                                                        const int* __restrict__ row_list, const int* __restrict__ row_pos,
+                                                        float* __restrict__ ws_ml, float* __restrict__ ws_acc, __nv_bfloat16* __restrict__ out) {
+    pdl_prologue();
+    __shared__ __align__(128) uint8_t sKV[2][2][AT_TILE_BYTES];    // [buffer][K | V]
+    if ((int)blockIdx.x >= meta[0]) return;
+    const AtItem it = items[blockIdx.x];
+    const int h = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int i0 = 16 * warp + g, i1 = i0 + 8;
+    const int r0 = i0 < it.nrows ? (row_list ? row_list[it.row0 + i0] : it.row0 + i0) : -1;
+    const int r1 = i1 < it.nrows ? (row_list ? row_list[it.row0 + i1] : it.row0 + i1) : -1;
+    const int rp0 = r0 >= 0 ? row_pos[r0] : -1, rp1 = r1 >= 0 ? row_pos[r1] : -1;
+    // ---- Q fragments (scaled by 1/8, hi + lo) ----
+    uint32_t qh[4][4], ql[4][4];
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        float x0[8], x1[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) { x0[e] = 0.f; x1[e] = 0.f; }
+        if (r0 >= 0) {
+            const float4 a = *reinterpret_cast<const float4*>(q + (long long)r0 * D_MODEL + h * D_HEAD + 32 * p + 8 * t), b = *reinterpret_cast<const float4*>(q + (long long)r0 * D_MODEL + h * D_HEAD + 32 * p + 8 * t + 4);
+            x0[0] = a.x; x0[1] = a.y; x0[2] = a.z; x0[3] = a.w; x0[4] = b.x; x0[5] = b.y; x0[6] = b.z; x0[7] = b.w;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int t = threadIdx.x;                                     // 0..255: dims 4t..4t+3, head t/16
-        const int h = t >> 4;
-        float M = -INFINITY;
-#pragma unroll
-        for (int w = 0; w < 8; w++) M = fmaxf(M, sm_m[w * 16 + h]);
-        float L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int w = 0; w < 8; w++) {
-            const float mw = sm_m[w * 16 + h];
-            const float sc = (mw == -INFINITY) ? 0.f : expf(mw - M);
-            L = fmaf(sm_l[w * 16 + h], sc, L);
-            const float4 a = *reinterpret_cast<const float4*>(sm_a + w * D_MODEL + 4 * t);
-            o[0] = fmaf(a.x, sc, o[0]); o[1] = fmaf(a.y, sc, o[1]); o[2] = fmaf(a.z, sc, o[2]); o[3] = fmaf(a.w, sc, o[3]);
+        if (r1 >= 0) {
+            const float4 a = *reinterpret_cast<const float4*>(q + (long long)r1 * D_MODEL + h * D_HEAD + 32 * p + 8 * t), b = *reinterpret_cast<const float4*>(q + (long long)r1 * D_MODEL + h * D_HEAD + 32 * p + 8 * t + 4);
+            x1[0] = a.x; x1[1] = a.y; x1[2] = a.z; x1[3] = a.w; x1[4] = b.x; x1[5] = b.y; x1[6] = b.z; x1[7] = b.w;
         }
-        if (splits == 1) {
-            const float inv = 1.0f / L;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0] * inv, o[1] * inv), p1 = __floats2bfloat162_rn(o[2] * inv, o[3] * inv);
-            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(out + (long long)row * D_MODEL + 4 * t) = pk;
+#pragma unroll
+        for (int e = 0; e < 8; e++) { x0[e] *= 0.125f; x1[e] *= 0.125f; }
+        // k16 step 2p: slots (2t, 2t+1) = values 0,1 and (2t+8, 2t+9) = values 2,3; step 2p+1: values 4,5 and 6,7
+        at_split2(x0[0], x0[1], qh[2 * p][0], ql[2 * p][0]); at_split2(x1[0], x1[1], qh[2 * p][1], ql[2 * p][1]);
+        at_split2(x0[2], x0[3], qh[2 * p][2], ql[2 * p][2]); at_split2(x1[2], x1[3], qh[2 * p][3], ql[2 * p][3]);
+        at_split2(x0[4], x0[5], qh[2 * p + 1][0], ql[2 * p + 1][0]); at_split2(x1[4], x1[5], qh[2 * p + 1][1], ql[2 * p + 1][1]);
+        at_split2(x0[6], x0[7], qh[2 * p + 1][2], ql[2 * p + 1][2]); at_split2(x1[6], x1[7], qh[2 * p + 1][3], ql[2 * p + 1][3]);
+    }
+    const int nblkA = (max(0, it.a_k1 - it.a_k0) + AT_KEYS - 1) / AT_KEYS, nblkB = (max(0, it.b_k1 - it.b_k0) + AT_KEYS - 1) / AT_KEYS;
+    const int nblk = nblkA + nblkB;
+    const uint32_t s_base = af_smem_u32(&sKV[0][0][0]);
+    auto load_block = [&](int bi, int buf) {
+        const bool segB = bi >= nblkA;
+        const int k0 = segB ? it.b_k0 + (bi - nblkA) * AT_KEYS : it.a_k0 + bi * AT_KEYS;
+        const int kend = segB ? it.b_k1 : it.a_k1;
+        const long long sbase = (long long)(segB ? it.b_slot : it.a_slot) * kv_slot_stride + h * D_HEAD;
+#pragma unroll
+        for (int c = threadIdx.x; c < AT_KEYS * 8; c += 128) {
+            const int key = c >> 3, ch = c & 7, kk = k0 + key;
+            const uint32_t nbytes = kk < kend ? 16u : 0u;          // out-of-range rows are zero-filled
+            const long long off = sbase + (long long)min(kk, kend - 1) * D_MODEL + ch * 8;
+            const uint32_t dK = s_base + (uint32_t)(buf * 2) * AT_TILE_BYTES + key * 128 + ((ch ^ ((key & 1) << 2)) << 4);
+            const uint32_t dV = s_base + (uint32_t)(buf * 2 + 1) * AT_TILE_BYTES + key * 128 + ((ch ^ (((key >> 1) & 3) << 1)) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dK), "l"(kc + off), "r"(nbytes) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dV), "l"(vc + off), "r"(nbytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; n++) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+    if (nblk > 0) load_block(0, 0);
+    for (int bi = 0; bi < nblk; bi++) {
+        const int buf = bi & 1;
+        if (bi + 1 < nblk) { load_block(bi + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const bool segB = bi >= nblkA;
+        const int k0 = segB ? it.b_k0 + (bi - nblkA) * AT_KEYS : it.a_k0 + bi * AT_KEYS;
+        const int kend = segB ? it.b_k1 : it.a_k1;
+        const int lim0 = segB ? min(kend - 1, rp0) : kend - 1, lim1 = segB ? min(kend - 1, rp1) : kend - 1;   // last visible key per row
+        const uint8_t* sK = &sKV[buf][0][0];
+        const uint8_t* sV = &sKV[buf][1][0];
+        // ---- S = Q K^T for 64 keys (8 tiles of 8) ----
+        float S[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int key = 8 * j + g;
+            const uint4 ka = *reinterpret_cast<const uint4*>(sK + key * 128 + ((t ^ ((key & 1) << 2)) << 4));
+            const uint4 kb = *reinterpret_cast<const uint4*>(sK + key * 128 + (((4 + t) ^ ((key & 1) << 2)) << 4));
+            float (&sc)[4] = S[j];
+            sc[0] = sc[1] = sc[2] = sc[3] = 0.f;
+            mma_bf16_16816(sc, qh[0], ka.x, ka.y); mma_bf16_16816(sc, qh[1], ka.z, ka.w);
+            mma_bf16_16816(sc, qh[2], kb.x, kb.y); mma_bf16_16816(sc, qh[3], kb.z, kb.w);
+            if (PRECISE) {
+                mma_bf16_16816(sc, ql[0], ka.x, ka.y); mma_bf16_16816(sc, ql[1], ka.z, ka.w);
+                mma_bf16_16816(sc, ql[2], kb.x, kb.y); mma_bf16_16816(sc, ql[3], kb.z, kb.w);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int kk = k0 + 8 * j + 2 * t + e;
+                if (kk > lim0) sc[e] = -INFINITY;
+                if (kk > lim1) sc[2 + e] = -INFINITY;
+            }
+        }
+        // ---- online softmax (rows g and g+8; the four lanes of a quad share a row) ----
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { mx0 = fmaxf(mx0, fmaxf(S[j][0], S[j][1])); mx1 = fmaxf(mx1, fmaxf(S[j][2], S[j][3])); }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float mu0 = mn0 == -INFINITY ? 0.f : mn0, mu1 = mn1 == -INFINITY ? 0.f : mn1;    // nothing visible yet: exp(-inf - 0) = 0
+        const float c0 = expf(m0 - mu0), c1 = expf(m1 - mu1);
+        m0 = mn0; m1 = mn1; l0 *= c0; l1 *= c1;
+#pragma unroll
+        for (int n = 0; n < 8; n++) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            S[j][0] = expf(S[j][0] - mu0); S[j][1] = expf(S[j][1] - mu0); S[j][2] = expf(S[j][2] - mu1); S[j][3] = expf(S[j][3] - mu1);
+            l0 += S[j][0] + S[j][1]; l1 += S[j][2] + S[j][3];
+        }
+        // ---- O += P V (4 key steps of 16) ----
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+            uint32_t ph[4], pl[4];
+            at_split2(S[2 * s4][0], S[2 * s4][1], ph[0], pl[0]); at_split2(S[2 * s4][2], S[2 * s4][3], ph[1], pl[1]);
+            at_split2(S[2 * s4 + 1][0], S[2 * s4 + 1][1], ph[2], pl[2]); at_split2(S[2 * s4 + 1][2], S[2 * s4 + 1][3], ph[3], pl[3]);
+            const int ka = 16 * s4 + 2 * t;
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int key = ka + (u & 1) + 8 * (u >> 1);
+                v[u] = *reinterpret_cast<const uint4*>(sV + key * 128 + ((g ^ (((key >> 1) & 3) << 1)) << 4));
+            }
+            const uint32_t a0[4] = {v[0].x, v[0].y, v[0].z, v[0].w}, a1[4] = {v[1].x, v[1].y, v[1].z, v[1].w};
+            const uint32_t a2[4] = {v[2].x, v[2].y, v[2].z, v[2].w}, a3[4] = {v[3].x, v[3].y, v[3].z, v[3].w};
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const uint32_t b0_lo = __byte_perm(a0[w], a1[w], 0x5410), b1_lo = __byte_perm(a2[w], a3[w], 0x5410);
+                const uint32_t b0_hi = __byte_perm(a0[w], a1[w], 0x7632), b1_hi = __byte_perm(a2[w], a3[w], 0x7632);
+                mma_bf16_16816(o[2 * w], ph, b0_lo, b1_lo);
+                mma_bf16_16816(o[2 * w + 1], ph, b0_hi, b1_hi);
+                if (PRECISE) { mma_bf16_16816(o[2 * w], pl, b0_lo, b1_lo); mma_bf16_16816(o[2 * w + 1], pl, b0_hi, b1_hi); }
+            }
+        }
+        __syncthreads();                                           // this buffer is refilled two iterations from now
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    // o[n][e] = O[row g][16t + 8e + n], o[n][2+e] = O[row g+8][...]: the lane owns dims 16t .. 16t+15 of its two rows
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const int r = rr ? r1 : r0;
+        if (r < 0) continue;
+        const float mr = rr ? m1 : m0, lr = rr ? l1 : l0;
+        if (it.out_split >= 0) {
+            const long long w = (long long)r * AF_WS_STRIDE + it.out_split;
+            if (t == 0) { ws_ml[w * 32 + h] = mr; ws_ml[w * 32 + 16 + h] = lr; }
+            float* dst = ws_acc + w * D_MODEL + h * D_HEAD + 16 * t;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                *reinterpret_cast<float4*>(dst + 8 * e) = make_float4(o[0][2 * rr + e], o[1][2 * rr + e], o[2][2 * rr + e], o[3][2 * rr + e]);
+                *reinterpret_cast<float4*>(dst + 8 * e + 4) = make_float4(o[4][2 * rr + e], o[5][2 * rr + e], o[6][2 * rr + e], o[7][2 * rr + e]);
+            }
         } else {
-            const long long wo = (long long)row * splits + split;
-            if ((t & 15) == 0) { ws_ml[wo * 32 + h] = M; ws_ml[wo * 32 + 16 + h] = L; }
-            *reinterpret_cast<float4*>(ws_acc + wo * D_MODEL + 4 * t) = make_float4(o[0], o[1], o[2], o[3]);
-            if (merge_cnt) {
-                // The LAST split CTA of a row to finish merges all of the row's partials (fixed split order: deterministic) and writes the
-                // bf16 output, which removes the separate merge launch from every layer. Release/acquire through the per-row counter.
-                __threadfence();
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                int* flag = reinterpret_cast<int*>(af_smem);
-                if (t == 0) { const int prev = atomicAdd(merge_cnt + row, 1); *flag = (prev == splits - 1); if (prev == splits - 1) merge_cnt[row] = 0; }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (*flag) {
-                    __threadfence();
-                    float Mm = -INFINITY;
-                    for (int sp = 0; sp < splits; sp++) Mm = fmaxf(Mm, __ldcg(ws_ml + ((long long)row * splits + sp) * 32 + h));
-                    float Lm = 0.f, om[4] = {0.f, 0.f, 0.f, 0.f};
-                    for (int sp = 0; sp < splits; sp++) {
-                        const long long w2 = (long long)row * splits + sp;
-                        const float ms = __ldcg(ws_ml + w2 * 32 + h);
-                        const float sc = (ms == -INFINITY) ? 0.f : expf(ms - Mm);
-                        Lm = fmaf(__ldcg(ws_ml + w2 * 32 + 16 + h), sc, Lm);
-                        const float4 a = __ldcg(reinterpret_cast<const float4*>(ws_acc + w2 * D_MODEL + 4 * t));
-                        om[0] = fmaf(a.x, sc, om[0]); om[1] = fmaf(a.y, sc, om[1]); om[2] = fmaf(a.z, sc, om[2]); om[3] = fmaf(a.w, sc, om[3]);
-                    }
-                    const float inv = 1.0f / Lm;
-                    __nv_bfloat162 p0 = __floats2bfloat162_rn(om[0] * inv, om[1] * inv), p1 = __floats2bfloat162_rn(om[2] * inv, om[3] * inv);
-                    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                    *reinterpret_cast<uint2*>(out + (long long)row * D_MODEL + 4 * t) = pk;
-                }
-            }
+            const float inv = lr > 0.f ? 1.0f / lr : 0.f;
+            __nv_bfloat162 pk[8];
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+#pragma unroll
+                for (int n = 0; n < 8; n += 2) pk[e * 4 + n / 2] = __floats2bfloat162_rn(o[n][2 * rr + e] * inv, o[n + 1][2 * rr + e] * inv);
+            __nv_bfloat16* dst = out + (long long)r * D_MODEL + h * D_HEAD + 16 * t;
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(&pk[0]);
+            *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<uint4*>(&pk[4]);
         }
     }
 }
@@ -473,10 +668,6 @@ __global__ void __launch_bounds__(256) attn_mimi_kernel(const __nv_bfloat16* __r
 // The NORMALISED probabilities are rounded to bf16 before P V (ggml's bf16 mul_mat rounds its f32 operand), as in attn_mimi_kernel.
 // (tcgen05 cannot be used here: its minimum M is 64 and a CTA pair per 16-row problem would idle 3/4 of the datapath.)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 struct MimiMaskRow { int lo; int a, b; };      // masked iff c >= lo || (a < c && c <= b) || c >= 250   (reference pattern, row j)
 __device__ __forceinline__ MimiMaskRow mimi_mask_row(int offset, int j) {
@@ -753,7 +944,7 @@ __global__ void __launch_bounds__(128) noise_inproj_kernel(int slot0, int n, con
 __global__ void __launch_bounds__(256) flow_in_kernel(int slot0, int n, const __nv_bfloat16* __restrict__ lat_in, const __nv_bfloat16* __restrict__ w_in_t,
                                                       const float* __restrict__ b_in, const float* __restrict__ lnw, const float* __restrict__ lnb,
                                                       float* __restrict__ h, __nv_bfloat16* __restrict__ n_bf,
-                                                      const int* __restrict__ cur_len, const float* __restrict__ freq,
+                                                      const int* __restrict__ cur_len, const int* __restrict__ active, const float* __restrict__ freq,
                                                       int* __restrict__ row_slot, int* __restrict__ row_pos, float2* __restrict__ cs) {
     pdl_prologue();
     __shared__ float xs[LDIM];
@@ -763,7 +954,9 @@ __global__ void __launch_bounds__(256) flow_in_kernel(int slot0, int n, const __
     if (i < LDIM) xs[i] = __bfloat162float(lat_in[(long long)(slot0 + r) * LDIM + i]);
     if (warp == 1) {                                           // row bookkeeping for the QKV epilogues: slot, position, RoPE table
         const int pos = cur_len[slot0 + r];
-        if (lane == 0) { row_slot[r] = slot0 + r; row_pos[r] = pos; }
+        // a finished utterance inside the stepped range is a DEAD row (row_slot < 0): no KV append (its position may already equal the
+        // cache capacity), no attention; the rest of the step computes on finite garbage that nothing consumes
+        if (lane == 0) { row_slot[r] = active[slot0 + r] ? slot0 + r : -1; row_pos[r] = pos; }
         const float rad = (float)pos * freq[lane];
         cs[r * 32 + lane] = make_float2(cosf(rad), sinf(rad));
     }
