@@ -74,6 +74,16 @@ B200_API int  b200_begin_sentence(b200_engine* e, int slot, int voice, const int
 B200_API int  b200_begin_sentences(b200_engine* e, int n, const int32_t* slots, const int32_t* voices,
                                    const int32_t* tokens, const int32_t* tok_off, const int32_t* max_gen_len,
                                    const int32_t* frames_after_eos, const float* temp);
+/* Same, plus rng_stream[n]: the id that keys the device noise generator for each sentence (default = the slot). A scheduler passes the
+ * sentence's global index so that its audio does not depend on the slot or GPU it lands on. Nothing in this call waits on the host:
+ * uploads are staged through a pinned ring, the prefill is enqueued behind the steps already submitted (reference
+ * _stream_sentence_init is synchronous, src/pocket_tts.cpp:416-444). max_gen_len is clamped to the remaining KV capacity. */
+B200_API int  b200_begin_sentences_ex(b200_engine* e, int n, const int32_t* slots, const int32_t* voices, const int32_t* tokens,
+                                      const int32_t* tok_off, const int32_t* max_gen_len, const int32_t* frames_after_eos,
+                                      const float* temp, const uint32_t* rng_stream);
+B200_API int  b200_voice_len(b200_engine* e, int voice);           /* prefix rows of a resident voice */
+B200_API int  b200_kv_capacity(b200_engine* e);
+B200_API int  b200_max_slots(b200_engine* e);
 
 /* Replaces _stream_sentence_step (src/pocket_tts.cpp:446-492) for the dense slot range [slot0, slot0+n):
  * FlowLM step -> EOS/stop rule -> LSD head -> Mimi -> 1920 samples per slot.
@@ -151,11 +161,37 @@ B200_API void ptts_c_stream_flush(ptts_stream_t* s);
 B200_API void ptts_c_stream_send(ptts_stream_t* s, const char* chunk);
 B200_API int ptts_c_stream_receive(ptts_stream_t* s, float* samples);
 B200_API b200_engine* ptts_c_engine(ptts_context_t* ctx);
+B200_API void ptts_c_destroy(ptts_context_t* ctx);   /* frees the engine and the context (the reference API never frees, src/pocket_tts.cpp:313) */
 /* Text front end, exposed for bit-exactness tests (conditioners/text.h:21-27,81-94). */
 B200_API int ptts_c_tokenize(ptts_context_t* ctx, const char* text, int32_t* ids, int max_ids);
 B200_API int ptts_c_count_words(const char* text);
 /* Pending sentences of a stream after send/flush (conditioners/text.h:207-251); returns count, copies the i-th. */
 B200_API int ptts_c_stream_pending(ptts_stream_t* s, int index, char* buf, int buflen);
+
+/* ---- continuous batching: the batched extension of the streaming API. The reference rolls one stream to its next
+ * sentence inside ptts_stream_receive (src/pocket_tts.cpp:494-519); here sentences of many utterances share the engine's slots and a
+ * finished slot is refilled while the others keep generating. Utterance audio = its sentences' frames in order. ---- */
+typedef struct ptts_batch_t ptts_batch_t;
+typedef struct ptts_batch_stats { long long steps, frames, slot_steps, sentences, refills; double wall_ms; } ptts_batch_stats;
+B200_API ptts_batch_t* ptts_c_batch_create(ptts_context_t* ctx, int n_slots /* 0 = all engine slots */);
+B200_API void ptts_c_batch_destroy(ptts_batch_t* b);
+/* refill policy: start queued sentences once refill_min slots are free or refill_every steps passed; stepped range rounded up to
+ * range_quantum slots; keep_pcm 0 = count frames only. Values <= 0 (keep_pcm < 0) keep the default. */
+B200_API int  ptts_c_batch_configure(ptts_batch_t* b, int refill_min, int refill_every, int range_quantum, int keep_pcm);
+B200_API int  ptts_c_batch_add(ptts_batch_t* b, const char* voice, const char* text, float temp);   /* -> utterance id */
+B200_API int  ptts_c_batch_add_tokens(ptts_batch_t* b, int voice_id, const int32_t* ids, int n_ids, int max_gen_len, int frames_after_eos,
+                                      float temp, uint32_t rng_stream /* 0 = job index + 1 */);
+B200_API long long ptts_c_batch_run(ptts_batch_t* b);                  /* runs every queued sentence to completion; frames produced */
+B200_API int  ptts_c_batch_frames(ptts_batch_t* b, int utt);
+B200_API int  ptts_c_batch_read(ptts_batch_t* b, int utt, float* pcm, int max_frames);   /* [frames][1920] */
+B200_API void ptts_c_batch_stats(ptts_batch_t* b, ptts_batch_stats* out);
+/* The same scheduler over caller-supplied engine calls (CPU tests drive it with a mock engine). */
+typedef int (*ptts_batch_begin_fn)(void* user, int n, const int32_t* slots, const int32_t* voices, const int32_t* tokens, const int32_t* tok_off,
+                                   const int32_t* max_gen_len, const int32_t* frames_after_eos, const float* temp, const uint32_t* rng_stream);
+typedef int (*ptts_batch_submit_fn)(void* user, int slot0, int n);
+typedef int (*ptts_batch_collect_fn)(void* user, float* pcm, int32_t* produced);
+B200_API ptts_batch_t* ptts_c_batch_create_with_ops(void* user, ptts_batch_begin_fn begin, ptts_batch_submit_fn submit, ptts_batch_collect_fn collect,
+                                                    int n_slots, int frame_size);
 
 /* Host-only text front end (no GPU needed): tokenizer + sentence splitter objects. */
 typedef struct ptts_text_t ptts_text_t;

@@ -26,6 +26,16 @@ class B200Config(ctypes.Structure):
                 ("prefix_share", ctypes.c_int)]
 
 
+class BatchStats(ctypes.Structure):
+    _fields_ = [("steps", ctypes.c_longlong), ("frames", ctypes.c_longlong), ("slot_steps", ctypes.c_longlong), ("sentences", ctypes.c_longlong),
+                ("refills", ctypes.c_longlong), ("wall_ms", ctypes.c_double)]
+
+
+_I32P, _F32P, _U32P = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint32)
+BATCH_BEGIN_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, _I32P, _I32P, _I32P, _I32P, _I32P, _I32P, _F32P, _U32P)
+BATCH_SUBMIT_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int)
+BATCH_COLLECT_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, _F32P, _I32P)
+
 _lib = None
 
 
@@ -93,11 +103,26 @@ def lib():
         "ptts_c_stream_send": (None, [vp, cp]),
         "ptts_c_stream_receive": (ci, [vp, fp]),
         "ptts_c_engine": (vp, [vp]),
+        "ptts_c_destroy": (None, [vp]),
         "ptts_c_voice": (ci, [vp]),
         "ptts_c_slot": (ci, [vp]),
         "ptts_c_tokenize": (ci, [vp, cp, ip, ci]),
         "ptts_c_count_words": (ci, [cp]),
         "ptts_c_stream_pending": (ci, [vp, ci, cp, ci]),
+        "b200_begin_sentences_ex": (ci, [vp, ci, ip, ip, ip, ip, ip, ip, fp, ctypes.POINTER(ctypes.c_uint32)]),
+        "b200_voice_len": (ci, [vp, ci]),
+        "b200_kv_capacity": (ci, [vp]),
+        "b200_max_slots": (ci, [vp]),
+        "ptts_c_batch_create": (vp, [vp, ci]),
+        "ptts_c_batch_destroy": (None, [vp]),
+        "ptts_c_batch_configure": (ci, [vp, ci, ci, ci, ci]),
+        "ptts_c_batch_add": (ci, [vp, cp, cp, cf]),
+        "ptts_c_batch_add_tokens": (ci, [vp, ci, ip, ci, ci, ci, cf, ctypes.c_uint32]),
+        "ptts_c_batch_run": (ctypes.c_longlong, [vp]),
+        "ptts_c_batch_frames": (ci, [vp, ci]),
+        "ptts_c_batch_read": (ci, [vp, ci, fp, ci]),
+        "ptts_c_batch_stats": (None, [vp, ctypes.POINTER(BatchStats)]),
+        "ptts_c_batch_create_with_ops": (vp, [vp, BATCH_BEGIN_FN, BATCH_SUBMIT_FN, BATCH_COLLECT_FN, ci, ci]),
         "ptts_c_text_create": (vp, [cp]),
         "ptts_c_text_destroy": (None, [vp]),
         "ptts_c_text_encode": (ci, [vp, cp, ip, ci]),
@@ -159,14 +184,18 @@ class Engine:
         if rc != 0:
             raise RuntimeError(f"b200_begin_sentence failed: {rc}")
 
-    def begin_sentences(self, slots, voices, token_lists, max_gen_len, frames_after_eos, temps):
+    def begin_sentences(self, slots, voices, token_lists, max_gen_len, frames_after_eos, temps, rng_streams=None):
         n = len(slots)
         off = np.zeros(n + 1, np.int32)
         off[1:] = np.cumsum([len(t) for t in token_lists])
         toks = np.ascontiguousarray(np.concatenate([np.asarray(t, np.int32) for t in token_lists]) if n else np.zeros(0, np.int32), np.int32)
         a = [np.ascontiguousarray(x, np.int32) for x in (slots, voices, max_gen_len, frames_after_eos)]
         tp = np.ascontiguousarray(temps, np.float32)
-        rc = self.L.b200_begin_sentences(self.h, n, _ip(a[0]), _ip(a[1]), _ip(toks), _ip(off), _ip(a[2]), _ip(a[3]), _fp(tp))
+        if rng_streams is not None:
+            rs = np.ascontiguousarray(rng_streams, np.uint32)
+            rc = self.L.b200_begin_sentences_ex(self.h, n, _ip(a[0]), _ip(a[1]), _ip(toks), _ip(off), _ip(a[2]), _ip(a[3]), _fp(tp), rs.ctypes.data_as(_U32P))
+        else:
+            rc = self.L.b200_begin_sentences(self.h, n, _ip(a[0]), _ip(a[1]), _ip(toks), _ip(off), _ip(a[2]), _ip(a[3]), _fp(tp))
         if rc != 0:
             raise RuntimeError(f"b200_begin_sentences failed: {rc}")
 
@@ -311,6 +340,12 @@ class Context:
             raise RuntimeError("ptts_init failed")
         self.engine = Engine(L.ptts_c_engine(self.h))
 
+    def close(self):
+        """Frees the engine (device memory) and the context. Streams / batches of this context must not be used afterwards."""
+        if self.h:
+            lib().ptts_c_destroy(self.h)
+            self.h = None; self.engine = None
+
     @property
     def sample_rate(self):
         return lib().ptts_c_get_sample_rate(self.h)
@@ -326,6 +361,66 @@ class Context:
 
     def stream(self, voice="cosette", temp=0.7) -> "Stream":
         return Stream(self, voice, temp)
+
+
+class Batch:
+    """Continuous batching over the engine's slots (ptts_c_batch_*): queue utterances, run() generates all of them, finished slots are
+    refilled with queued sentences. With `ops` = (begin, submit, collect) Python callables the scheduler runs over a mock engine (CPU tests)."""
+
+    def __init__(self, ctx: "Context" = None, n_slots: int = 0, ops=None, frame_size: int = FRAME):
+        L = lib()
+        self.frame_size = frame_size
+        if ops is not None:
+            self._cbs = (BATCH_BEGIN_FN(ops[0]), BATCH_SUBMIT_FN(ops[1]), BATCH_COLLECT_FN(ops[2]))   # keep the thunks alive
+            self.h = L.ptts_c_batch_create_with_ops(None, self._cbs[0], self._cbs[1], self._cbs[2], n_slots, frame_size)
+        else:
+            self.h = L.ptts_c_batch_create(ctx.h, n_slots)
+        if not self.h:
+            raise RuntimeError("ptts_c_batch_create failed")
+
+    def configure(self, refill_min=0, refill_every=0, range_quantum=0, keep_pcm=-1):
+        assert lib().ptts_c_batch_configure(self.h, refill_min, refill_every, range_quantum, keep_pcm) == 0
+
+    def add(self, voice: str, text: str, temp: float = 0.7) -> int:
+        u = lib().ptts_c_batch_add(self.h, voice.encode(), text.encode(), float(temp))
+        if u < 0:
+            raise RuntimeError(f"ptts_c_batch_add failed: {u}")
+        return u
+
+    def add_tokens(self, voice_id, ids, max_gen_len, frames_after_eos, temp=0.7, rng_stream=0) -> int:
+        a = np.ascontiguousarray(ids, np.int32)
+        u = lib().ptts_c_batch_add_tokens(self.h, voice_id, _ip(a), len(a), max_gen_len, frames_after_eos, float(temp), rng_stream)
+        if u < 0:
+            raise RuntimeError(f"ptts_c_batch_add_tokens failed: {u}")
+        return u
+
+    def run(self) -> int:
+        n = lib().ptts_c_batch_run(self.h)
+        if n < 0:
+            raise RuntimeError(f"ptts_c_batch_run failed: {n}")
+        return n
+
+    def frames(self, utt) -> int:
+        return lib().ptts_c_batch_frames(self.h, utt)
+
+    def read(self, utt) -> np.ndarray:
+        n = self.frames(utt)
+        out = np.zeros((max(n, 1), self.frame_size), np.float32)
+        got = lib().ptts_c_batch_read(self.h, utt, _fp(out), n)
+        return out[:got]
+
+    def stats(self) -> dict:
+        st = BatchStats()
+        lib().ptts_c_batch_stats(self.h, ctypes.byref(st))
+        d = {k: getattr(st, k) for k, _ in BatchStats._fields_}
+        d["idle_slot_fraction"] = 1.0 - d["frames"] / d["slot_steps"] if d["slot_steps"] else 0.0
+        return d
+
+    def __del__(self):
+        try:
+            lib().ptts_c_batch_destroy(self.h)
+        except Exception:
+            pass
 
 
 class Stream:

@@ -98,7 +98,7 @@ struct b200_engine {
     __nv_bfloat16 *mkc = nullptr, *mvc = nullptr;      // Mimi ring [layer][max_slots][250][512]
     long long mkv_slot_stride = 0, mkv_layer_stride = 0;
     int *cur_len = nullptr, *mimi_off = nullptr, *gen_step = nullptr, *eos_step = nullptr, *max_gen = nullptr, *fae = nullptr, *active = nullptr;
-    float* temp = nullptr;
+    float* temp = nullptr; unsigned int* rng_id = nullptr;   // per-slot sampling temperature, RNG stream id of the sentence in the slot
     __nv_bfloat16* lat_in_bf16 = nullptr; float* lat_f32 = nullptr;   // [slot][32] backbone input / last latent
     float* e_prev = nullptr;                                          // upsampler state [slot][512]
     std::vector<int> h_cur_len;                                       // host mirror of cur_len
@@ -285,7 +285,7 @@ struct b200_engine {
     // ---- tap points (parity localisation; the reference's GraphContext::debug, src/context.h:526-547, printed tensor sums) ----
     // b200_debug_taps(1): steps run eagerly on one stream and the FlowLM residual stream / attention output of every layer are copied
     // aside; the Mimi-side taps are persistent buffers that can be read after any step (b200_debug_tap).
-    bool taps_on = false; float* tap_h = nullptr; __nv_bfloat16* tap_att = nullptr; int tap_slot0 = 0, tap_n = 0;
+    bool taps_on = false; float* tap_h = nullptr; __nv_bfloat16* tap_att = nullptr; float* tap_up = nullptr; int tap_slot0 = 0, tap_n = 0;
     void tap_flow_layer(int l, int R) {
         if (!taps_on || actx.prefill) return;
         PTTS_CUDA_CHECK(cudaMemcpyAsync(tap_h + (size_t)l * cfg.max_slots * D_MODEL, h, (size_t)R * D_MODEL * sizeof(float), cudaMemcpyDeviceToDevice, stream));
@@ -576,7 +576,7 @@ struct b200_engine {
         seg_end(s_flow);
         const int s_head = seg_begin(2);
         launch_k(pdl_active, noise_inproj_kernel, dim3(n), dim3(128), (size_t)(0), stream, slot0, n, (const float*)(injected ? noise_inj : nullptr), (const unsigned long long*)d_seed,
-                 (const float*)temp, (const int*)gen_step, noise_f32, (const __nv_bfloat16*)input_proj_t, (const float*)input_proj.b, xh);
+                 (const float*)temp, (const int*)gen_step, (const unsigned int*)rng_id, noise_f32, (const __nv_bfloat16*)input_proj_t, (const float*)input_proj.b, xh);
         flow_head(n);
         launches += 1;
         seg_end(s_head);
@@ -589,6 +589,8 @@ struct b200_engine {
     void step_enqueue(int slot0, int n, bool injected) {       // single-stream form (eager / profiling)
         const int s_all = seg_begin(5);
         flow_part(slot0, n, injected, mx);
+        if (taps_on)   // the Mimi transformer updates its input rows in place: keep the upsampler output aside
+            PTTS_CUDA_CHECK(cudaMemcpyAsync(tap_up + (size_t)slot0 * M_T * M_DIM, mx + (size_t)slot0 * M_T * M_DIM, (size_t)n * M_T * M_DIM * sizeof(float), cudaMemcpyDeviceToDevice, stream));
         mimi(slot0, n, mx);
         seg_end(s_all);
     }
@@ -738,17 +740,17 @@ __global__ void set_meta_kernel(int slot, int cur, int mg, int f, float t, const
 
 // Batched sentence start (b200_begin_sentences; reference _stream_sentence_init src/pocket_tts.cpp:416-444, copy_states models/flow_lm.h:70-78,
 // init(mimi_states) models/mimi.h:71-75): one launch each for all n sentences instead of three launches per sentence.
-// meta = [slot | src voice slot | prefix rows | cur_len | max_gen | frames_after_eos | shared prefix rows (0 = private copy)] x n (ints), temps[n].
+// meta = [slot | src voice slot | prefix rows | cur_len | max_gen | frames_after_eos | shared prefix rows (0 = private copy) | RNG stream id] x n (ints), temps[n].
 // FlowLM-side state (main stream): stop-rule counters, BOS latent, upsampler carry, prefix assignment.
 __global__ void begin_meta_kernel(int n, const int* __restrict__ meta, const float* __restrict__ temps, const float* bos, int* cur_len, int* gen_step, int* eos_step,
                                   int* max_gen, int* fae, int* active, float* temp, __nv_bfloat16* lat_in_bf16, float* lat_f32,
-                                  int* __restrict__ pfx_slot, int* __restrict__ pfx_len, float* __restrict__ e_prev) {
+                                  int* __restrict__ pfx_slot, int* __restrict__ pfx_len, float* __restrict__ e_prev, unsigned int* __restrict__ rng_id) {
     const int j = blockIdx.x, i = threadIdx.x;
     if (j >= n) return;
     const int slot = meta[j], cur = meta[3 * n + j], mg = meta[4 * n + j], f = meta[5 * n + j];
     if (i == 0) {
         cur_len[slot] = cur; gen_step[slot] = 0; eos_step[slot] = -1; max_gen[slot] = mg; fae[slot] = f; active[slot] = mg > 0 ? 1 : 0; temp[slot] = temps[j];
-        pfx_slot[slot] = meta[n + j]; pfx_len[slot] = meta[6 * n + j];
+        pfx_slot[slot] = meta[n + j]; pfx_len[slot] = meta[6 * n + j]; rng_id[slot] = (unsigned int)meta[7 * n + j];
     }
     if (i < LDIM) { lat_f32[slot * LDIM + i] = bos[i]; lat_in_bf16[slot * LDIM + i] = __float2bfloat16_rn(bos[i]); }
     for (int c = i; c < M_DIM; c += blockDim.x) e_prev[(long long)slot * M_DIM + c] = 0.f;
@@ -984,6 +986,7 @@ int b200_finalize_weights(b200_engine* e) {
     e->mkc = e->dalloc<__nv_bfloat16>((size_t)e->mkv_layer_stride * M_LAYERS); e->mvc = e->dalloc<__nv_bfloat16>((size_t)e->mkv_layer_stride * M_LAYERS);
     e->cur_len = e->dalloc<int>(TS); e->mimi_off = e->dalloc<int>(S); e->gen_step = e->dalloc<int>(S); e->eos_step = e->dalloc<int>(S);
     e->max_gen = e->dalloc<int>(S); e->fae = e->dalloc<int>(S); e->active = e->dalloc<int>(S); e->temp = e->dalloc<float>(S);
+    { std::vector<unsigned int> ids(S); for (int i = 0; i < S; i++) ids[i] = (unsigned int)i; e->rng_id = e->upload(ids); }
     e->lat_in_bf16 = e->dalloc<__nv_bfloat16>((size_t)S * LDIM); e->lat_f32 = e->dalloc<float>((size_t)S * LDIM);
     e->e_prev = e->dalloc<float>((size_t)S * M_DIM);
     e->h = e->dalloc<float>((size_t)MR * D_MODEL); e->q = e->dalloc<float>((size_t)MR * D_MODEL);
@@ -993,6 +996,7 @@ int b200_finalize_weights(b200_engine* e) {
     e->pfx_slot = e->dalloc<int>(TS); e->pfx_len = e->dalloc<int>(TS);
     e->dec_items_cap = ((S + AT_ROWS - 1) / AT_ROWS + e->cfg.max_voices + 1) * AF_PFX_SPLITS + 8;
     e->dec_items = e->dalloc<AtItem>(e->dec_items_cap); e->dec_meta = e->dalloc<int>(4); e->dec_rows = e->dalloc<int>(S);
+    e->tap_up = e->dalloc<float>((size_t)S * M_T * M_DIM);
     e->tap_h = e->dalloc<float>((size_t)N_LAYERS * S * D_MODEL); e->tap_att = e->dalloc<__nv_bfloat16>((size_t)N_LAYERS * S * D_MODEL);
     e->row_slot = e->dalloc<int>(MR); e->row_pos = e->dalloc<int>(MR); e->tok = e->dalloc<int>(MR); e->cs = e->dalloc<float2>((size_t)MR * 32);
     e->c_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_MODEL); e->sy_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW);
@@ -1126,6 +1130,11 @@ int b200_voice_create(b200_engine* e, const float* audio_prompt, int T) {
 
 int b200_begin_sentences(b200_engine* e, int n, const int32_t* slots, const int32_t* voices, const int32_t* tokens,
                          const int32_t* tok_off, const int32_t* max_gen_len, const int32_t* frames_after_eos, const float* temp) {
+    return b200_begin_sentences_ex(e, n, slots, voices, tokens, tok_off, max_gen_len, frames_after_eos, temp, nullptr);
+}
+
+int b200_begin_sentences_ex(b200_engine* e, int n, const int32_t* slots, const int32_t* voices, const int32_t* tokens, const int32_t* tok_off,
+                            const int32_t* max_gen_len, const int32_t* frames_after_eos, const float* temp, const uint32_t* rng_stream) {
     if (!e || !e->finalized || n < 0) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     std::vector<int> rs, rp, rt;
@@ -1150,8 +1159,8 @@ int b200_begin_sentences(b200_engine* e, int n, const int32_t* slots, const int3
     e->begin_used = true;
     const size_t elt = e->cfg.kv_f32 ? 4 : 2;
     // per-sentence metadata in one upload: [slot | src voice slot | prefix rows | cur_len | max_gen | frames_after_eos | shared rows] x n, then temps
-    int* pm = (int*)e->pin_acquire((size_t)8 * n * sizeof(int));
-    float* pt = (float*)(pm + 7 * n);
+    int* pm = (int*)e->pin_acquire((size_t)9 * n * sizeof(int));
+    float* pt = (float*)(pm + 8 * n);
     int max_copy = 0;
     for (int i = 0; i < n; i++) {
         const int slot = slots[i], v = voices[i];
@@ -1164,23 +1173,23 @@ int b200_begin_sentences(b200_engine* e, int n, const int32_t* slots, const int3
         if (mg > room) mg = room;
         const int shared = e->cfg.prefix_share ? start : 0;
         pm[i] = slot; pm[n + i] = e->cfg.max_slots + v; pm[2 * n + i] = start; pm[3 * n + i] = start + nt;
-        pm[4 * n + i] = mg; pm[5 * n + i] = frames_after_eos[i]; pm[6 * n + i] = shared;
+        pm[4 * n + i] = mg; pm[5 * n + i] = frames_after_eos[i]; pm[6 * n + i] = shared; pm[7 * n + i] = (int)(rng_stream ? rng_stream[i] : (uint32_t)slot);
         pt[i] = temp[i];
         e->h_cur_len[slot] = start + nt;
         if (e->h_pfx_slot[slot] != e->cfg.max_slots + v || e->h_pfx_len[slot] != shared) { e->h_pfx_slot[slot] = e->cfg.max_slots + v; e->h_pfx_len[slot] = shared; e->pfx_version++; }
         if (!e->cfg.prefix_share) max_copy = std::max(max_copy, start);
     }
     if ((size_t)n > e->begin_cap) {
-        e->begin_meta = e->dalloc<int>((size_t)7 * n, false); e->begin_temp = e->dalloc<float>((size_t)n, false); e->begin_cap = n;
+        e->begin_meta = e->dalloc<int>((size_t)8 * n, false); e->begin_temp = e->dalloc<float>((size_t)n, false); e->begin_cap = n;
     }
-    PTTS_CUDA_CHECK(cudaMemcpyAsync(e->begin_meta, pm, (size_t)7 * n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    PTTS_CUDA_CHECK(cudaMemcpyAsync(e->begin_meta, pm, (size_t)8 * n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     PTTS_CUDA_CHECK(cudaMemcpyAsync(e->begin_temp, pt, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     e->pin_release(e->stream);
     if (max_copy > 0)   // reference semantics (prefix_share = 0): private copy of the voice-conditioned prefix, models/flow_lm.h:70-78
         launch_k(false, begin_copy_prefix_kernel, dim3(8, 2 * N_LAYERS, n), dim3(256), (size_t)0, e->stream, n, (const int*)e->begin_meta, (char*)e->kc, (char*)e->vc,
                  (long long)(e->kv_slot_stride * elt), (long long)(e->kv_layer_stride * elt), (long long)(D_MODEL * elt));
     launch_k(false, begin_meta_kernel, dim3(n), dim3(128), (size_t)0, e->stream, n, (const int*)e->begin_meta, (const float*)e->begin_temp, (const float*)e->d_bos, e->cur_len,
-             e->gen_step, e->eos_step, e->max_gen, e->fae, e->active, e->temp, e->lat_in_bf16, e->lat_f32, e->pfx_slot, e->pfx_len, e->e_prev);
+             e->gen_step, e->eos_step, e->max_gen, e->fae, e->active, e->temp, e->lat_in_bf16, e->lat_f32, e->pfx_slot, e->pfx_len, e->e_prev, e->rng_id);
     // Mimi-side reset on the Mimi stream: behind every Mimi decode already enqueued there, ahead of the new sentences' first decode. The
     // main stream only waits for it when it touches Mimi state itself (join_mimi: synchronous b200_step, Mimi-only calls).
     PTTS_CUDA_CHECK(cudaEventRecord(e->ev_begin, e->stream));
@@ -1192,6 +1201,10 @@ int b200_begin_sentences(b200_engine* e, int n, const int32_t* slots, const int3
     if (!rs.empty()) prefill_rows(e, rs, rp, &rt, nullptr);
     return B200_OK;
 }
+
+int b200_voice_len(b200_engine* e, int voice) { return (!e || voice < 0 || voice >= e->n_voices) ? B200_EINVAL : e->voice_len[voice]; }
+int b200_kv_capacity(b200_engine* e) { return e ? e->cfg.kv_capacity : B200_EINVAL; }
+int b200_max_slots(b200_engine* e) { return e ? e->cfg.max_slots : B200_EINVAL; }
 
 int b200_begin_sentence(b200_engine* e, int slot, int voice, const int32_t* tokens, int n_tokens, int max_gen_len, int frames_after_eos, float temp) {
     const int32_t off[2] = {0, n_tokens};
@@ -1538,7 +1551,7 @@ int b200_debug_tap(b200_engine* e, const char* name, int slot, float* out, int m
         if (att) return give_16(e->tap_att + (size_t)l * e->cfg.max_slots * D_MODEL, false, 0, r, 1, D_MODEL, D_MODEL);
         return give_f32(e->tap_h + ((size_t)l * e->cfg.max_slots + r) * D_MODEL, D_MODEL);
     }
-    if (s == "mimi.upsample") return give_f32(e->mx + (size_t)slot * M_T * M_DIM, (size_t)M_T * M_DIM);
+    if (s == "mimi.upsample") return give_f32(e->tap_up + (size_t)slot * M_T * M_DIM, (size_t)M_T * M_DIM);   // needs b200_debug_taps(e, 1)
     if (s == "mimi.transformer") return give_16(e->buf0, true, 22LL * 512, 6, 16, 512, 512);
     if (s == "seanet.conv0") return give_16(e->buf2, true, 17LL * e->C2, 1, 16, e->C2, 512);
     if (s == "seanet.convt2") return give_f32(e->y3 + (size_t)slot * 96 * 256, (size_t)96 * 256);

@@ -6,6 +6,7 @@
 #include "../../include/ptts_b200.h"
 #include "host/safetensors.hpp"
 #include "host/spm_unigram.hpp"
+#include "host/batch_scheduler.hpp"
 
 #include <cctype>
 #include <cstdlib>
@@ -142,8 +143,8 @@ ptts_context_t* ptts_init(ggml_backend*, ggml_backend*, const char* model_path) 
 int ptts_get_sample_rate(ptts_context_t*) { return 24000; }   // reference :324-326
 int ptts_get_frame_size(ptts_context_t*) { return 1920; }     // reference :328-330
 
-// reference src/pocket_tts.cpp:351-394 (+ get_state_for_audio_prompt :100-124)
-ptts_stream_t* ptts_stream_from_safetensors(ptts_context_t* ctx, const char* voice_c_str, float temp) {
+// Voice name or path -> engine voice id; the first use loads the file and prefills the prefix (reference src/pocket_tts.cpp:356-359,100-124).
+static int resolve_voice(ptts_context_t* ctx, const char* voice_c_str) {
     std::string voice = voice_c_str;
     for (const char* v : kVoices) if (voice == v) { voice = ctx->model_path + "embeddings/" + v + ".safetensors"; break; }
     int vid;
@@ -165,6 +166,12 @@ ptts_stream_t* ptts_stream_from_safetensors(ptts_context_t* ctx, const char* voi
         if (vid < 0) { fprintf(stderr, "error: failed to prefill voice %s (%d)\n", voice.c_str(), vid); exit(1); }
         ctx->voices[voice] = vid;
     }
+    return vid;
+}
+
+// reference src/pocket_tts.cpp:351-394 (+ get_state_for_audio_prompt :100-124)
+ptts_stream_t* ptts_stream_from_safetensors(ptts_context_t* ctx, const char* voice_c_str, float temp) {
+    const int vid = resolve_voice(ctx, voice_c_str);
     int slot = -1;
     for (size_t i = 0; i < ctx->slot_used.size(); i++) if (!ctx->slot_used[i]) { slot = (int)i; break; }
     if (slot < 0) { fprintf(stderr, "error: no free stream slot (raise PTTS_B200_MAX_STREAMS)\n"); exit(1); }
@@ -261,6 +268,9 @@ void ptts_c_stream_flush(ptts_stream_t* s) { ptts_stream_flush(s); }
 void ptts_c_stream_send(ptts_stream_t* s, const char* chunk) { ptts_stream_send(s, chunk); }
 int ptts_c_stream_receive(ptts_stream_t* s, float* samples) { return ptts_stream_receive(s, samples) ? 1 : 0; }
 b200_engine* ptts_c_engine(ptts_context_t* c) { return c ? c->engine : nullptr; }
+// The reference API has no destroy functions (contexts live for the process, src/pocket_tts.cpp:313,381); long-running hosts and
+// tests that create several engines need one. Streams of the context must not be used afterwards.
+void ptts_c_destroy(ptts_context_t* c) { if (c) { b200_engine_destroy(c->engine); delete c; } }
 int ptts_c_tokenize(ptts_context_t* c, const char* text, int32_t* ids, int max_ids) {
     std::vector<int> v = c->tokenizer.encode(text);
     for (int i = 0; i < (int)v.size() && i < max_ids; i++) ids[i] = v[i];
@@ -275,6 +285,107 @@ int ptts_c_stream_pending(ptts_stream_t* s, int index, char* buf, int buflen) {
         memcpy(buf, t.data(), m); buf[m] = 0;
     }
     return n;
+}
+
+// ---- continuous batching (host/batch_scheduler.hpp): many utterances over the engine's slots, finished slots refilled ----
+struct ptts_batch_t {
+    ptts_context_t* ctx = nullptr;                // null for a scheduler driven through caller-supplied ops (tests)
+    BatchScheduler* sched = nullptr;
+    std::vector<std::vector<int>> utt_jobs;       // utterance -> its sentences' job ids, in order
+};
+static int batch_begin_engine(void* u, int n, const int32_t* sl, const int32_t* vo, const int32_t* toks, const int32_t* off, const int32_t* mg,
+                              const int32_t* fae, const float* tp, const uint32_t* rs) {
+    return b200_begin_sentences_ex((b200_engine*)u, n, sl, vo, toks, off, mg, fae, tp, rs);
+}
+static int batch_submit_engine(void* u, int slot0, int n) { return b200_submit((b200_engine*)u, slot0, n, nullptr); }
+static int batch_collect_engine(void* u, float* pcm, int32_t* produced) { return b200_collect((b200_engine*)u, pcm, produced); }
+
+ptts_batch_t* ptts_c_batch_create(ptts_context_t* ctx, int n_slots) {
+    if (!ctx) return nullptr;
+    const int max_slots = b200_max_slots(ctx->engine);
+    if (n_slots <= 0 || n_slots > max_slots) n_slots = max_slots;
+    for (bool used : ctx->slot_used) if (used) { fprintf(stderr, "error: ptts_c_batch_create needs a context without open streams (slots are shared)\n"); return nullptr; }
+    auto* b = new ptts_batch_t; b->ctx = ctx;
+    BatchOps ops; ops.user = ctx->engine; ops.begin = batch_begin_engine; ops.submit = batch_submit_engine; ops.collect = batch_collect_engine;
+    b->sched = new BatchScheduler(ops, n_slots);
+    if (ctx->seed_pushed != g_seed || !ctx->seed_valid) { b200_set_seed(ctx->engine, g_seed); ctx->seed_pushed = g_seed; ctx->seed_valid = true; }
+    return b;
+}
+ptts_batch_t* ptts_c_batch_create_with_ops(void* user, ptts_batch_begin_fn begin, ptts_batch_submit_fn submit, ptts_batch_collect_fn collect, int n_slots, int frame_size) {
+    if (!begin || !submit || !collect || n_slots < 1 || frame_size < 1) return nullptr;
+    auto* b = new ptts_batch_t;
+    BatchOps ops; ops.user = user; ops.begin = begin; ops.submit = submit; ops.collect = collect;
+    b->sched = new BatchScheduler(ops, n_slots, frame_size);
+    return b;
+}
+void ptts_c_batch_destroy(ptts_batch_t* b) { if (b) { delete b->sched; delete b; } }
+int ptts_c_batch_configure(ptts_batch_t* b, int refill_min, int refill_every, int range_quantum, int keep_pcm) {
+    if (!b) return B200_EINVAL;
+    if (refill_min > 0) b->sched->refill_min = refill_min;
+    if (refill_every > 0) b->sched->refill_every = refill_every;
+    if (range_quantum > 0) b->sched->range_quantum = range_quantum;
+    if (keep_pcm >= 0) b->sched->keep_pcm = keep_pcm != 0;
+    return B200_OK;
+}
+// One utterance = text in the reference's streaming sense: split into sentences (str_processor, conditioners/text.h:181-251), each
+// sentence is one job with the reference's cap and frames_after_eos (src/pocket_tts.cpp:429-430,504-506).
+int ptts_c_batch_add(ptts_batch_t* b, const char* voice, const char* text, float temp) {
+    if (!b || !b->ctx || !voice || !text) return B200_EINVAL;
+    const int vid = resolve_voice(b->ctx, voice);
+    auto& rv = b->sched->room_of_voice;
+    if ((int)rv.size() <= vid) rv.resize(vid + 1, 1 << 30);
+    rv[vid] = b200_kv_capacity(b->ctx->engine) - b200_voice_len(b->ctx->engine, vid);
+    SentenceSplitter sp; sp.reset(); sp.ingest(text); sp.flush();
+    const int utt = (int)b->utt_jobs.size();
+    b->utt_jobs.emplace_back();
+    int idx = 0;
+    for (const std::string& sent : sp.sentences) {
+        BatchScheduler::Job j; j.utt = utt; j.index = idx++; j.voice = vid; j.temp = temp;
+        const int words = count_words_impl(sent);
+        j.fae = (words <= 4 ? 3 : 1) + 2; j.max_gen = (int)((words + 2.0f) * 12.5f);
+        std::vector<int> ids = b->ctx->tokenizer.encode(sent);
+        j.ids.assign(ids.begin(), ids.end());
+        b->utt_jobs[utt].push_back(b->sched->add_job(std::move(j)));
+    }
+    b->sched->on_jobs_added();
+    return utt;
+}
+int ptts_c_batch_add_tokens(ptts_batch_t* b, int voice_id, const int32_t* ids, int n_ids, int max_gen_len, int frames_after_eos, float temp, uint32_t rng_stream) {
+    if (!b || n_ids < 0 || (n_ids > 0 && !ids)) return B200_EINVAL;
+    if (b->ctx) {
+        auto& rv = b->sched->room_of_voice;
+        if ((int)rv.size() <= voice_id) rv.resize(voice_id + 1, 1 << 30);
+        const int vl = b200_voice_len(b->ctx->engine, voice_id);
+        if (vl < 0) return B200_EINVAL;
+        rv[voice_id] = b200_kv_capacity(b->ctx->engine) - vl;
+    }
+    BatchScheduler::Job j; j.utt = (int)b->utt_jobs.size(); j.index = 0; j.voice = voice_id; j.temp = temp; j.max_gen = max_gen_len; j.fae = frames_after_eos;
+    j.rng_stream = rng_stream; j.ids.assign(ids, ids + n_ids);
+    b->utt_jobs.emplace_back();
+    b->utt_jobs.back().push_back(b->sched->add_job(std::move(j)));
+    b->sched->on_jobs_added();
+    return (int)b->utt_jobs.size() - 1;
+}
+long long ptts_c_batch_run(ptts_batch_t* b) { return b ? b->sched->run() : B200_EINVAL; }
+int ptts_c_batch_frames(ptts_batch_t* b, int utt) {
+    if (!b || utt < 0 || utt >= (int)b->utt_jobs.size()) return B200_EINVAL;
+    int n = 0; for (int j : b->utt_jobs[utt]) n += b->sched->jobs()[j].frames;
+    return n;
+}
+int ptts_c_batch_read(ptts_batch_t* b, int utt, float* pcm, int max_frames) {
+    if (!b || utt < 0 || utt >= (int)b->utt_jobs.size() || !pcm) return B200_EINVAL;
+    int n = 0;
+    for (int j : b->utt_jobs[utt]) {
+        const auto& J = b->sched->jobs()[j];
+        const size_t fs = J.frames ? J.pcm.size() / (size_t)J.frames : 0;
+        for (int f = 0; f < J.frames && n < max_frames && fs; f++, n++) memcpy(pcm + (size_t)n * fs, J.pcm.data() + (size_t)f * fs, fs * sizeof(float));
+    }
+    return n;
+}
+void ptts_c_batch_stats(ptts_batch_t* b, ptts_batch_stats* out) {
+    if (!b || !out) return;
+    const BatchStats& s = b->sched->stats();
+    out->steps = s.steps; out->frames = s.frames; out->slot_steps = s.slot_steps; out->sentences = s.sentences; out->refills = s.refills; out->wall_ms = s.wall_ms;
 }
 
 // Host-only helpers (no GPU needed): tokenizer / splitter objects for CPU-side tests and FFI users.

@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(256) head_pre_kernel(const float* __restrict__
 
 // noise -> (f32, bf16) per row. Noise is either injected by the caller (identical-noise parity runs, the
 // reference's injection point is GraphContext::normal_, src/context.h:465-509) or drawn on the device from a
-// counter-based generator keyed by (seed, slot, generation step): Philox-4x32-10 + Box-Muller, std = sqrt(temp).
+// counter-based generator keyed by (seed, sentence stream id, generation step): Philox-4x32-10 + Box-Muller, std = sqrt(temp).
 __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
@@ -898,7 +898,8 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
 // One CTA (128 threads) per row: the first 32 threads draw the row's noise, then every thread computes 4 of the 512 outputs of
 // input_proj(bf16(noise)) (32 -> 512, reference modules/mlp.h:236; bf16 operands, fp32 accumulation like every linear here).
 __global__ void __launch_bounds__(128) noise_inproj_kernel(int slot0, int n, const float* __restrict__ injected, const unsigned long long* __restrict__ seed_ptr,
-                                                           const float* __restrict__ temp, const int* __restrict__ gen_step, float* __restrict__ noise_f32,
+                                                           const float* __restrict__ temp, const int* __restrict__ gen_step, const unsigned int* __restrict__ rng_id,
+                                                           float* __restrict__ noise_f32,
                                                            const __nv_bfloat16* __restrict__ w_in_t, const float* __restrict__ b_in, float* __restrict__ xh) {
     pdl_prologue();
     __shared__ float zs[LDIM];
@@ -914,7 +915,9 @@ __global__ void __launch_bounds__(128) noise_inproj_kernel(int slot0, int n, con
             else {
                 uint32_t o[4];
                 const unsigned long long seed = *seed_ptr;
-                philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)slot, (uint32_t)gen_step[slot], (uint32_t)(i >> 1), 0x5054545Au, o);
+                // counter = (sentence stream id, generation step, draw pair): the id defaults to the slot; a batch scheduler sets it to the
+                // sentence's global index so that the audio does not depend on the slot / GPU the sentence happens to land on
+                philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), rng_id[slot], (uint32_t)gen_step[slot], (uint32_t)(i >> 1), 0x5054545Au, o);
                 const float u1 = ((float)(o[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
                 const float u2 = ((float)(o[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
                 const float rad = sqrtf(-2.0f * logf(u1));

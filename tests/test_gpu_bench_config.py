@@ -109,13 +109,16 @@ def test_shared_and_private_prefix_agree(P, model_dir, oracle_mod):
         a, b = outs[0][i], outs[1][i]
         assert np.array_equal(a[1], b[1])
         for k in range(6):
-            assert np.abs(a[2][k] - b[2][k]).max() < 2e-2, (i, k)           # same math, different summation order / bf16 rounding flips
-            assert snr_db(b[0][k], a[0][k]) > 45.0, (i, k)
+            # same math, different summation order: bf16 rounding flips feed back through the latent (free running), so the bound is
+            # the engine-vs-oracle one
+            assert np.abs(a[2][k] - b[2][k]).max() < LAT_MAXABS, (i, k)
+            assert snr_db(b[0][k], a[0][k]) > SNR_MIN, (i, k)
 
 
 def test_f32_checkpoint_against_f32_weights_oracle(P, oracle_mod):
     """With an F32 checkpoint the reference computes f32 linears (src/loader.h:205-210); the engine always rounds weights and the
-    activation operand to bf16. Measured error of that choice (stated in DESIGN.md): latents within max-abs 1e-1, waveform SNR >= 30 dB."""
+    activation operand to bf16. Measured cost of that choice on B200 (teacher-forced, 12 frames): latent max-abs 1.9e-2, rel-L2 5.4e-3,
+    waveform SNR 46.0 dB -- i.e. inside the tolerances used against the BF16-checkpoint oracle, which are asserted here too."""
     from make_assets import default_model_dir
     d = default_model_dir(eos_mode="never", dtype="F32")
     orc = oracle_mod.Oracle(d, threads=os.cpu_count() or 1)
@@ -137,7 +140,7 @@ def test_f32_checkpoint_against_f32_weights_oracle(P, oracle_mod):
         # teacher forcing keeps the comparison per frame (errors of a bf16-weight model would otherwise feed back through the latent)
         c.engine.debug_set_latent(0, 4, np.stack([lat] * 4))
     print(f"\n[F32 checkpoint vs f32-weights oracle] latent max-abs {worst[0]:.4f}, rel-L2 {worst[1]:.4f}, min SNR {worst[2]:.1f} dB")
-    assert worst[0] < 1e-1 and worst[2] > 30.0, worst
+    assert worst[0] < LAT_MAXABS and worst[1] < LAT_REL and worst[2] > SNR_MIN, worst
 
 
 def test_two_voices_in_one_batch(P, model_dir, orc, oracle_mod):

@@ -130,6 +130,9 @@ def synth_weights(seed: int, eos_mode: str) -> dict[str, np.ndarray]:
     elif eos_mode == "mid":
         # parity checkpoints: P(logit_raw > 1.64) ~ 5 % per frame -> EOS lands mid-sentence
         W["flow_lm.out_eos.bias"] = np.array([-5.64], dtype=np.float32)
+    elif eos_mode == "late":
+        # ragged-throughput checkpoints: P(logit_raw > 2.46) ~ 0.7 % per frame -> sentences end after ~100+ frames or at their cap
+        W["flow_lm.out_eos.bias"] = np.array([-6.46], dtype=np.float32)
     else:
         raise ValueError(eos_mode)
     for l in range(6):
@@ -319,7 +322,7 @@ if __name__ == "__main__":
     ap.add_argument("--out", default=None)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--dtype", default="BF16", choices=["BF16", "F32"])
-    ap.add_argument("--eos", default="never", choices=["never", "mid"])
+    ap.add_argument("--eos", default="never", choices=["never", "mid", "late"])
     ap.add_argument("--t-voice", type=int, default=125)
     ap.add_argument("--train-tokenizer", action="store_true")
     a = ap.parse_args()
