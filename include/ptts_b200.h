@@ -122,8 +122,8 @@ B200_API int  b200_debug_gemm(b200_engine* e, int f16, const float* A, int n_slo
                               const float* bias, int path, float* out, float* out2_as_f32);
 /* Parity helper (teacher forcing): overwrite the backbone input latent [n][32] of slots [slot0, slot0+n). */
 B200_API int  b200_debug_set_latent(b200_engine* e, int slot0, int n, const float* latents);
-/* Per-segment device timing with CUDA events on the engine stream (bench.py roofline leg). Categories: 0 FlowLM attention
- * kernel, 1 FlowLM backbone, 2 flow head, 3 Mimi transformer, 4 SEANet, 5 whole step. out_ms[6], out_count[6]. */
+/* Per-segment device timing with CUDA events on the engine stream (bench.py roofline leg). Categories: 0 FlowLM attention streaming
+ * kernel, 1 FlowLM backbone, 2 flow head, 3 Mimi transformer, 4 SEANet, 5 whole step, 6 shared-prefix tile kernel. out_ms[7], out_count[7]. */
 B200_API int  b200_profile(b200_engine* e, int on);
 B200_API int  b200_profile_read(b200_engine* e, float* out_ms, int* out_count);
 /* cudaProfilerStart (1) / cudaProfilerStop (0): lets `ncu --profile-from-start off` capture only a bracketed region. */

@@ -290,9 +290,9 @@ class Engine:
         self.L.b200_profile(self.h, 1 if on else 0)
 
     def profile_read(self):
-        ms = np.zeros(6, np.float32); cnt = np.zeros(6, np.int32)
+        ms = np.zeros(7, np.float32); cnt = np.zeros(7, np.int32)
         self.L.b200_profile_read(self.h, _fp(ms), _ip(cnt))
-        names = ["attn_flow", "flow_backbone", "head", "mimi_transformer", "seanet", "step"]
+        names = ["attn_stream", "flow_backbone", "head", "mimi_transformer", "seanet", "step", "attn_prefix_tiles"]
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(names)}
 
     def stream_handle(self):

@@ -367,7 +367,7 @@ struct b200_engine {
         else { e.kcache = (__nv_bfloat16*)kc + l * kv_layer_stride; e.vcache = (__nv_bfloat16*)vc + l * kv_layer_stride; }
         if (l > 0 && ln_in_gemv(R)) { LnArgs a; a.w = L.n1w; a.b = L.n1b; a.eps = 1e-5f; lin_ln(h, a, L.in_proj, R, e); }   // layer 0: flow_in_kernel wrote n_bf
         else lin(n_bf, L.in_proj, R, e);
-        const int sg = seg_begin(0);
+        int sg = -1;
         const bool pdl_saved = pdl_active;
         set_pdl(pdl_small);                                  // the KV-streaming kernel fills the machine: no early dependents around it
         if (actx.prefill && !cfg.kv_f32) {
@@ -381,11 +381,14 @@ struct b200_engine {
             const bool tiles = use_prefix_tiles(R);
             AfKeys keys; keys.pfx_slot = pfx_slot; keys.pfx_len = pfx_len; keys.tiles_meta = tiles ? dec_meta : nullptr;
             if (tiles) {   // shared voice prefix x all rows of the voice -> workspace partials (merged by the streaming kernel below)
+                const int sgt = seg_begin(6);
                 launch_k(pdl_active, attn_tile_kernel<true>, dim3(dec_grid_items, N_HEADS), dim3(128), (size_t)0, stream, (const float*)q, (const __nv_bfloat16*)e.kcache,
                          (const __nv_bfloat16*)e.vcache, kv_slot_stride, (const AtItem*)dec_items, (const int*)dec_meta, (const int*)dec_rows, actx.row_pos, af_ml, af_acc, att_bf);
                 launches++;
+                seg_end(sgt);
             }
             const int splits = af_splits(R, tiles);
+            sg = seg_begin(0);
             if (cfg.kv_f32)
                 launch_k(pdl_active, attn_flow_split_kernel<float>, dim3(splits, R), dim3(288), (size_t)(AfCfg<float>::SMEM), stream, (const float*)q, (const float*)e.kcache, (const float*)e.vcache,
                          kv_slot_stride, actx.row_slot, actx.row_pos, keys, splits, af_ml, af_acc, att_bf, af_cnt);
@@ -1435,8 +1438,8 @@ int b200_debug_set_latent(b200_engine* e, int slot0, int n, const float* latents
 }
 
 // Per-segment device timing. b200_profile(e,1) arms it; after b200_sync, b200_profile_read sums the recorded event
-// pairs per category: 0 FlowLM attention kernel, 1 FlowLM backbone, 2 head, 3 Mimi transformer, 4 SEANet, 5 whole step.
-// out_ms[6], out_count[6]. Reading disarms and clears.
+// pairs per category: 0 FlowLM attention streaming kernel, 1 FlowLM backbone, 2 head, 3 Mimi transformer, 4 SEANet, 5 whole step,
+// 6 FlowLM shared-prefix tile kernel. out_ms[7], out_count[7]. Reading disarms and clears.
 int b200_profile(b200_engine* e, int on) {
     if (!e) return B200_EINVAL;
     e->profiling = on != 0; e->segs.clear(); e->ev_used = 0;
@@ -1445,11 +1448,11 @@ int b200_profile(b200_engine* e, int on) {
 int b200_profile_read(b200_engine* e, float* out_ms, int* out_count) {
     if (!e || !out_ms || !out_count) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    for (int i = 0; i < 6; i++) { out_ms[i] = 0.f; out_count[i] = 0; }
+    for (int i = 0; i < 7; i++) { out_ms[i] = 0.f; out_count[i] = 0; }
     for (auto& sg : e->segs) {
         float ms = 0.f;
         PTTS_CUDA_CHECK(cudaEventElapsedTime(&ms, sg.a, sg.b));
-        if (sg.cat >= 0 && sg.cat < 6) { out_ms[sg.cat] += ms; out_count[sg.cat]++; }
+        if (sg.cat >= 0 && sg.cat < 7) { out_ms[sg.cat] += ms; out_count[sg.cat]++; }
     }
     e->profiling = false; e->segs.clear(); e->ev_used = 0;
     return B200_OK;
