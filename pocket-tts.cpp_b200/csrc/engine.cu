@@ -37,6 +37,9 @@ struct b200_engine {
     // Two-stream pipeline: the Mimi decode of frame t (tensor/ALU bound) runs on stream_m while the FlowLM step of frame t+1 (latency
     // bound small GEMMs + the HBM-bound KV stream) runs on the main stream. Hand-off buffer mx2[t & 1], events per parity.
     cudaStream_t stream_m = nullptr;
+    cudaStream_t stream_t = nullptr;     // forked branch of the main stream: the shared-prefix tile kernel runs beside the per-utterance KV stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool fork_tiles = getenv("PTTS_B200_FORK_TILES") ? atoi(getenv("PTTS_B200_FORK_TILES")) != 0 : true;   // tuning hook
     cudaEvent_t ev_main[2] = {nullptr, nullptr}, ev_mimi[2] = {nullptr, nullptr};
     bool ev_mimi_valid[2] = {false, false};
     unsigned long long pipe_t = 0;       // frames enqueued through the pipeline
@@ -165,13 +168,13 @@ struct b200_engine {
         if (ev_used == ev_pool.size()) { cudaEvent_t ev; PTTS_CUDA_CHECK(cudaEventCreate(&ev)); ev_pool.push_back(ev); }
         return ev_pool[ev_used++];
     }
-    int seg_begin(int cat) {
+    int seg_begin(int cat, cudaStream_t st = nullptr) {
         if (!profiling) return -1;
         Seg sg; sg.cat = cat; sg.a = next_event(); sg.b = next_event();
-        PTTS_CUDA_CHECK(cudaEventRecord(sg.a, stream));
+        PTTS_CUDA_CHECK(cudaEventRecord(sg.a, st ? st : stream));
         segs.push_back(sg); return (int)segs.size() - 1;
     }
-    void seg_end(int id) { if (id >= 0) PTTS_CUDA_CHECK(cudaEventRecord(segs[id].b, stream)); }
+    void seg_end(int id, cudaStream_t st = nullptr) { if (id >= 0) PTTS_CUDA_CHECK(cudaEventRecord(segs[id].b, st ? st : stream)); }
 
     template <typename T> T* dalloc(size_t n, bool zero = true) {
         void* p = nullptr;
@@ -379,13 +382,21 @@ struct b200_engine {
             launches++;
         } else {
             const bool tiles = use_prefix_tiles(R);
-            AfKeys keys; keys.pfx_slot = pfx_slot; keys.pfx_len = pfx_len; keys.tiles_meta = tiles ? dec_meta : nullptr;
-            if (tiles) {   // shared voice prefix x all rows of the voice -> workspace partials (merged by the streaming kernel below)
-                const int sgt = seg_begin(6);
-                launch_k(pdl_active, attn_tile_kernel<true>, dim3(dec_grid_items, N_HEADS), dim3(128), (size_t)0, stream, (const float*)q, (const __nv_bfloat16*)e.kcache,
+            const bool fork = tiles && fork_tiles;      // tile kernel (tensor cores, prefix from L2) beside the streaming kernel (HBM), merged afterwards
+            AfKeys keys; keys.pfx_slot = pfx_slot; keys.pfx_len = pfx_len; keys.tiles_meta = tiles ? dec_meta : nullptr; keys.defer_merge = fork ? 1 : 0;
+            if (tiles) {   // shared voice prefix x all rows of the voice -> workspace partials
+                cudaStream_t ts = stream;
+                if (fork) {
+                    PTTS_CUDA_CHECK(cudaEventRecord(ev_fork, stream));
+                    PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream_t, ev_fork, 0));
+                    ts = stream_t;
+                }
+                const int sgt = seg_begin(6, ts);
+                launch_k(fork ? false : pdl_active, attn_tile_kernel<true>, dim3(dec_grid_items, N_HEADS), dim3(128), (size_t)0, ts, (const float*)q, (const __nv_bfloat16*)e.kcache,
                          (const __nv_bfloat16*)e.vcache, kv_slot_stride, (const AtItem*)dec_items, (const int*)dec_meta, (const int*)dec_rows, actx.row_pos, af_ml, af_acc, att_bf);
                 launches++;
-                seg_end(sgt);
+                seg_end(sgt, ts);
+                if (fork) PTTS_CUDA_CHECK(cudaEventRecord(ev_join, stream_t));
             }
             const int splits = af_splits(R, tiles);
             sg = seg_begin(0);
@@ -396,6 +407,12 @@ struct b200_engine {
                 launch_k(pdl_active, attn_flow_split_kernel<__nv_bfloat16>, dim3(splits, R), dim3(288), (size_t)(AfCfg<__nv_bfloat16>::SMEM), stream, (const float*)q, (const __nv_bfloat16*)e.kcache,
                          (const __nv_bfloat16*)e.vcache, kv_slot_stride, actx.row_slot, actx.row_pos, keys, splits, af_ml, af_acc, att_bf, af_cnt);
             launches++;
+            if (fork) {
+                seg_end(sg); sg = -1;
+                PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0));
+                launch_k(false, attn_merge_kernel, dim3(R), dim3(256), (size_t)0, stream, actx.row_slot, (const int*)pfx_len, (const int*)dec_meta, splits, (const float*)af_ml, (const float*)af_acc, att_bf);
+                launches++;
+            }
         }
         set_pdl(pdl_saved);
         seg_end(sg);
@@ -812,6 +829,9 @@ int b200_engine_create(const b200_config* cfg, b200_engine** out) {
         PTTS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, hi));
         PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_m, cudaStreamNonBlocking, lo));
+        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_t, cudaStreamNonBlocking, hi));
+        PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) {
             PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_main[i], cudaEventDisableTiming));
             PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_mimi[i], cudaEventDisableTiming));
@@ -835,6 +855,7 @@ void b200_engine_destroy(b200_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     cudaStreamSynchronize(e->stream_m);
+    cudaStreamSynchronize(e->stream_t);
     for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (void* p : e->allocs) cudaFree(p);
     for (auto& pd : e->pend) {
@@ -848,7 +869,8 @@ void b200_engine_destroy(b200_engine* e) {
     tc_plan_cache_destroy(e->tc);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(e->ev_main[i]); cudaEventDestroy(e->ev_mimi[i]); }
     for (auto& ev : e->ev_seg) cudaEventDestroy(ev);
-    cudaStreamDestroy(e->stream); cudaStreamDestroy(e->stream_m);
+    cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join);
+    cudaStreamDestroy(e->stream); cudaStreamDestroy(e->stream_m); cudaStreamDestroy(e->stream_t);
     delete e;
 }
 
@@ -1037,7 +1059,7 @@ int b200_finalize_weights(b200_engine* e) {
                             (const void*)gemv_small_kernel<__nv_bfloat16, 8>, (const void*)gemv_small_kernel<__half, 8>, (const void*)gemv_ln_kernel<D_MODEL>, (const void*)gemv_ln_kernel<D_FLOW>, (const void*)layernorm_kernel<D_MODEL>,
                             (const void*)layernorm_kernel<D_FLOW>, 
                             (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
-                            (const void*)attn_flow_split_kernel<__nv_bfloat16>, (const void*)attn_flow_split_kernel<float>, (const void*)attn_tile_kernel<true>, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
+                            (const void*)attn_flow_split_kernel<__nv_bfloat16>, (const void*)attn_flow_split_kernel<float>, (const void*)attn_tile_kernel<true>, (const void*)attn_merge_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
                             (const void*)step_front_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma4_kernel,
                             (const void*)conv_n1_kernel, (const void*)shift_states_kernel};
         for (const void* k : ks) PTTS_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

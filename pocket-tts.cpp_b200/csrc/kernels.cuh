@@ -132,7 +132,9 @@ __device__ __forceinline__ void af_bulk_load(uint32_t dst, const void* src, uint
 //   utterance of that voice, reference copy_states models/flow_lm.h:70-78 made a private copy instead); keys [P, pos] are the slot's own.
 //   tiles_meta (may be null): {item count, prefix splits} of an attn_tile_kernel launch that ALREADY reduced keys [0, P) of every row with
 //   P > 0 into workspace entries [AF_MAX_SPLITS, AF_MAX_SPLITS + prefix splits); this kernel then streams only [P, pos] and merges both.
-struct AfKeys { const int* pfx_slot; const int* pfx_len; const int* tiles_meta; };
+//   defer_merge: the tile kernel runs CONCURRENTLY (forked stream), so its partials may not exist yet: this kernel only writes its own
+//   partials and attn_merge_kernel, launched after the join, combines them.
+struct AfKeys { const int* pfx_slot; const int* pfx_len; const int* tiles_meta; int defer_merge; };
 
 // One CTA per (KV split, query row), all 16 heads at once so that every cache row is read as one contiguous 2/4 KB line. Warp 8 lane 0
 // is the producer: it streams groups of 8 consecutive K rows and V rows into a 3-stage shared-memory ring with cp.async.bulk + mbarrier
@@ -298,7 +300,7 @@ attn_flow_split_kernel(const float* __restrict__ q, const KV* __restrict__ kc, c
         const float4 a = *reinterpret_cast<const float4*>(sm_a + w * D_MODEL + 4 * t);
         o[0] = fmaf(a.x, sc, o[0]); o[1] = fmaf(a.y, sc, o[1]); o[2] = fmaf(a.z, sc, o[2]); o[3] = fmaf(a.w, sc, o[3]);
     }
-    if (splits == 1 && n_extra == 0) {
+    if (splits == 1 && n_extra == 0 && !keys.defer_merge) {
         const float inv = 1.0f / L;
         __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0] * inv, o[1] * inv), p1 = __floats2bfloat162_rn(o[2] * inv, o[3] * inv);
         uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
@@ -308,6 +310,7 @@ attn_flow_split_kernel(const float* __restrict__ q, const KV* __restrict__ kc, c
     const long long wrow = (long long)row * AF_WS_STRIDE;
     if ((t & 15) == 0) { ws_ml[(wrow + split) * 32 + h] = M; ws_ml[(wrow + split) * 32 + 16 + h] = L; }
     *reinterpret_cast<float4*>(ws_acc + (wrow + split) * D_MODEL + 4 * t) = make_float4(o[0], o[1], o[2], o[3]);
+    if (keys.defer_merge) return;
     // The LAST split CTA of a row to finish merges all of the row's partials (fixed entry order: deterministic) and writes the bf16
     // output, which removes the separate merge launch from every layer. Release/acquire through the per-row counter. The prefix
     // partials (entries AF_MAX_SPLITS..) were written by an EARLIER kernel of the same stream, hence are already visible.
@@ -543,6 +546,34 @@ __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict_
             *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<uint4*>(&pk[4]);
         }
     }
+}
+
+// Combines the partials of one row after the streaming kernel (entries [0, splits)) and the shared-prefix tile kernel (entries
+// [AF_MAX_SPLITS, AF_MAX_SPLITS + prefix splits) for rows with a shared prefix) ran side by side. One CTA per row, fixed entry order.
+__global__ void __launch_bounds__(256) attn_merge_kernel(const int* __restrict__ row_slot, const int* __restrict__ pfx_len, const int* __restrict__ tiles_meta, int splits,
+                                                         const float* __restrict__ ws_ml, const float* __restrict__ ws_acc, __nv_bfloat16* __restrict__ out) {
+    pdl_prologue();
+    const int row = blockIdx.x, t = threadIdx.x, h = t >> 4;
+    const int slot = row_slot[row];
+    if (slot < 0) return;
+    const int n_extra = pfx_len[slot] > 0 ? tiles_meta[1] : 0;
+    const long long wrow = (long long)row * AF_WS_STRIDE;
+    const int n_ent = splits + n_extra;
+    float Mm = -INFINITY;
+    for (int e = 0; e < n_ent; e++) { const int sp = e < splits ? e : AF_MAX_SPLITS + (e - splits); Mm = fmaxf(Mm, ws_ml[(wrow + sp) * 32 + h]); }
+    float Lm = 0.f, om[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int e = 0; e < n_ent; e++) {
+        const long long w2 = wrow + (e < splits ? e : AF_MAX_SPLITS + (e - splits));
+        const float ms = ws_ml[w2 * 32 + h];
+        const float sc = (ms == -INFINITY) ? 0.f : expf(ms - Mm);
+        Lm = fmaf(ws_ml[w2 * 32 + 16 + h], sc, Lm);
+        const float4 a = *reinterpret_cast<const float4*>(ws_acc + w2 * D_MODEL + 4 * t);
+        om[0] = fmaf(a.x, sc, om[0]); om[1] = fmaf(a.y, sc, om[1]); om[2] = fmaf(a.z, sc, om[2]); om[3] = fmaf(a.w, sc, om[3]);
+    }
+    const float inv = 1.0f / Lm;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(om[0] * inv, om[1] * inv), p1 = __floats2bfloat162_rn(om[2] * inv, om[3] * inv);
+    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(out + (long long)row * D_MODEL + 4 * t) = pk;
 }
 
 // ------------------------------------------------------------------------------------------------
