@@ -496,6 +496,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip private_kv / kv_f32 / multi_voice / ragged / verify / sustained")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="run the oracle check of the timed context even with --no-extras")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.no_extras:
@@ -540,7 +541,7 @@ def main():
     env = Env(args)
     B = args.batch
 
-    prim = run_mode(env, "shared" if args.prefix_share else "private", args.prefix_share, 0, primary=True, verify=(not args.no_extras and not args.no_verify and world == 1))
+    prim = run_mode(env, "shared" if args.prefix_share else "private", args.prefix_share, 0, primary=True, verify=((not args.no_extras or args.verify) and not args.no_verify and world == 1))
     extras = {}
     if not args.no_extras:
         other = 0 if args.prefix_share else 1

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <time.h>
 #include <unordered_set>
 #include <vector>
 #ifdef _OPENMP

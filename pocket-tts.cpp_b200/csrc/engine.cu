@@ -117,6 +117,7 @@ struct b200_engine {
     // decode-side work list of attn_tile_kernel (prefix x rows of a voice), rebuilt when the stepped range or the assignment changes
     AtItem* dec_items = nullptr; int* dec_meta = nullptr; int* dec_rows = nullptr; int dec_items_cap = 0;
     int dec_key_slot0 = -1, dec_key_n = -1; unsigned long long dec_key_version = 0; int dec_grid_items = 0;
+    int tile_prec = getenv("PTTS_B200_TILE_PREC") ? atoi(getenv("PTTS_B200_TILE_PREC")) : 2;   // operand precision of the decode-side tile kernel (see attn_tile_kernel)
     int tile_min_rows = getenv("PTTS_B200_TILE_MIN_ROWS") ? atoi(getenv("PTTS_B200_TILE_MIN_ROWS")) : 4;   // below: the streaming kernel reads the prefix itself
     // attention context of the forward being enqueued (decode: the fixed scratch arrays; prefill: this call's staging)
     struct AttnCtx { const int* row_slot = nullptr; const int* row_pos = nullptr; const float2* cs = nullptr;
@@ -311,7 +312,9 @@ struct b200_engine {
         int tiles = 0, max_p = 0;
         for (auto& g : groups) { tiles += ((int)g.second.size() + AT_ROWS - 1) / AT_ROWS; max_p = std::max(max_p, g.first.second); }
         if (tiles == 0) { dec_grid_items = 0; return; }
-        int splits = std::min(AF_PFX_SPLITS, std::max(1, (19 + tiles - 1) / tiles));
+        // ONE wave of tile CTAs (tiles x splits x 16 heads <= two resident CTAs per SM): a second, partly filled wave would cost a whole CTA time
+        const int sms = tc ? tc->num_sms : 148;
+        int splits = std::min(AF_PFX_SPLITS, std::max(1, (2 * sms) / (N_HEADS * tiles)));
         splits = std::max(1, std::min(splits, max_p / AT_KEYS));
         std::vector<AtItem> items; std::vector<int> rows;
         for (auto& g : groups) {
@@ -348,7 +351,7 @@ struct b200_engine {
     int af_splits(int R, bool short_stream) const {
         if (af_splits_override > 0) return std::min(af_splits_override, AF_MAX_SPLITS);
         const int sms = tc ? tc->num_sms : 148;
-        if (short_stream) return std::max(1, std::min(AF_MAX_SPLITS, (2 * sms + R - 1) / R));
+        if (short_stream) return std::max(1, std::min(AF_MAX_SPLITS, (sms + R - 1) / R));   // ~one CTA per SM: the tile kernel runs beside it (measured 1.095 -> 1.084 ms at R = 256)
         int splits = 1; double best = -1.0;
         for (int sp = 1; sp <= AF_MAX_SPLITS; sp++) {
             const long long ctas = (long long)R * sp;
@@ -358,6 +361,11 @@ struct b200_engine {
             if (ctas >= 8LL * sms) break;
         }
         return splits;
+    }
+    template <typename... A> void launch_tiles(int prec, bool pdl, dim3 grid, cudaStream_t st, A... a) {
+        if (prec >= 2) launch_k(pdl, attn_tile_kernel<2>, grid, dim3(128), (size_t)0, st, a...);
+        else if (prec == 1) launch_k(pdl, attn_tile_kernel<1>, grid, dim3(128), (size_t)0, st, a...);
+        else launch_k(pdl, attn_tile_kernel<0>, grid, dim3(128), (size_t)0, st, a...);
     }
     bool use_prefix_tiles(int R) const { return cfg.prefix_share && !cfg.kv_f32 && !actx.prefill && R >= tile_min_rows && dec_grid_items > 0; }
 
@@ -377,8 +385,8 @@ struct b200_engine {
             // T > 1 rows with the causal mask (reference transformer.h:157-169): one tensor-core tile per 64 rows of a slot and head, K/V read
             // once per tile instead of once per row
             if (actx.n_items > 0)
-                launch_k(pdl_active, attn_tile_kernel<true>, dim3(actx.n_items, N_HEADS), dim3(128), (size_t)0, stream, (const float*)q, (const __nv_bfloat16*)e.kcache,
-                         (const __nv_bfloat16*)e.vcache, kv_slot_stride, actx.items, actx.meta, (const int*)nullptr, actx.row_pos, af_ml, af_acc, att_bf);
+                launch_tiles(2, pdl_active, dim3(actx.n_items, N_HEADS), stream, (const float*)q, (const __nv_bfloat16*)e.kcache,
+                             (const __nv_bfloat16*)e.vcache, kv_slot_stride, actx.items, actx.meta, (const int*)nullptr, actx.row_pos, af_ml, af_acc, att_bf);
             launches++;
         } else {
             const bool tiles = use_prefix_tiles(R);
@@ -392,8 +400,8 @@ struct b200_engine {
                     ts = stream_t;
                 }
                 const int sgt = seg_begin(6, ts);
-                launch_k(fork ? false : pdl_active, attn_tile_kernel<true>, dim3(dec_grid_items, N_HEADS), dim3(128), (size_t)0, ts, (const float*)q, (const __nv_bfloat16*)e.kcache,
-                         (const __nv_bfloat16*)e.vcache, kv_slot_stride, (const AtItem*)dec_items, (const int*)dec_meta, (const int*)dec_rows, actx.row_pos, af_ml, af_acc, att_bf);
+                launch_tiles(tile_prec, fork ? false : pdl_active, dim3(dec_grid_items, N_HEADS), ts, (const float*)q, (const __nv_bfloat16*)e.kcache,
+                             (const __nv_bfloat16*)e.vcache, kv_slot_stride, (const AtItem*)dec_items, (const int*)dec_meta, (const int*)dec_rows, actx.row_pos, af_ml, af_acc, att_bf);
                 launches++;
                 seg_end(sgt, ts);
                 if (fork) PTTS_CUDA_CHECK(cudaEventRecord(ev_join, stream_t));
@@ -1059,7 +1067,7 @@ int b200_finalize_weights(b200_engine* e) {
                             (const void*)gemv_small_kernel<__nv_bfloat16, 8>, (const void*)gemv_small_kernel<__half, 8>, (const void*)gemv_ln_kernel<D_MODEL>, (const void*)gemv_ln_kernel<D_FLOW>, (const void*)layernorm_kernel<D_MODEL>,
                             (const void*)layernorm_kernel<D_FLOW>, 
                             (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
-                            (const void*)attn_flow_split_kernel<__nv_bfloat16>, (const void*)attn_flow_split_kernel<float>, (const void*)attn_tile_kernel<true>, (const void*)attn_merge_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
+                            (const void*)attn_flow_split_kernel<__nv_bfloat16>, (const void*)attn_flow_split_kernel<float>, (const void*)attn_tile_kernel<2>, (const void*)attn_tile_kernel<1>, (const void*)attn_tile_kernel<0>, (const void*)attn_merge_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
                             (const void*)step_front_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma4_kernel,
                             (const void*)conv_n1_kernel, (const void*)shift_states_kernel};
         for (const void* k : ks) PTTS_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -378,7 +378,9 @@ __device__ __forceinline__ void at_split2(float x, float y, uint32_t& hi, uint32
 
 constexpr int AT_ROWS = 64, AT_KEYS = 64, AT_TILE_BYTES = AT_KEYS * D_HEAD * 2;   // 8 KB
 
-template <bool PRECISE>
+// PREC: 2 = q and the probabilities as hi + lo bf16 pairs, 1 = q only (P V with plain bf16 probabilities: their rounding errors are
+// independent per key and average out over the keys a row attends to), 0 = plain bf16 operands.
+template <int PREC>
 __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kc, const __nv_bfloat16* __restrict__ vc,
                                                         long long kv_slot_stride, const AtItem* __restrict__ items, const int* __restrict__ meta,
                                                         const int* __restrict__ row_list, const int* __restrict__ row_pos,
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict_
             sc[0] = sc[1] = sc[2] = sc[3] = 0.f;
             mma_bf16_16816(sc, qh[0], ka.x, ka.y); mma_bf16_16816(sc, qh[1], ka.z, ka.w);
             mma_bf16_16816(sc, qh[2], kb.x, kb.y); mma_bf16_16816(sc, qh[3], kb.z, kb.w);
-            if (PRECISE) {
+            if (PREC >= 1) {
                 mma_bf16_16816(sc, ql[0], ka.x, ka.y); mma_bf16_16816(sc, ql[1], ka.z, ka.w);
                 mma_bf16_16816(sc, ql[2], kb.x, kb.y); mma_bf16_16816(sc, ql[3], kb.z, kb.w);
             }
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict_
                 const uint32_t b0_hi = __byte_perm(a0[w], a1[w], 0x7632), b1_hi = __byte_perm(a2[w], a3[w], 0x7632);
                 mma_bf16_16816(o[2 * w], ph, b0_lo, b1_lo);
                 mma_bf16_16816(o[2 * w + 1], ph, b0_hi, b1_hi);
-                if (PRECISE) { mma_bf16_16816(o[2 * w], pl, b0_lo, b1_lo); mma_bf16_16816(o[2 * w + 1], pl, b0_hi, b1_hi); }
+                if (PREC >= 2) { mma_bf16_16816(o[2 * w], pl, b0_lo, b1_lo); mma_bf16_16816(o[2 * w + 1], pl, b0_hi, b1_hi); }
             }
         }
         __syncthreads();                                           // this buffer is refilled two iterations from now
