@@ -61,6 +61,7 @@ def lib():
         L.oracle_mimi_reset.argtypes = [vp]
         L.oracle_mimi_frame.argtypes = [vp, fp, fp]
         L.oracle_current_end.restype = ci; L.oracle_current_end.argtypes = [vp]
+        L.oracle_set_backbone_input.argtypes = [vp, fp]
         L.oracle_mimi_offset.restype = ci; L.oracle_mimi_offset.argtypes = [vp]
         L.oracle_set_mimi_offset.argtypes = [vp, ci]
         L.oracle_get_kv.argtypes = [vp, ci, ci, fp]

@@ -367,13 +367,26 @@ template <typename F> inline void unary(ggml_tensor* d, F f) {
     const ggml_tensor* a = d->src[0];
     assert(a->type == GGML_TYPE_F32 && d->type == GGML_TYPE_F32);
     const int64_t n = ggml_nelements(d);
+    if (ggml_is_contiguous(a) && ggml_is_contiguous(d)) {
+        const float* x = (const float*)a->data; float* y = (float*)d->data;
+#pragma omp parallel for schedule(static) num_threads(g_threads) if (n > 32768)
+        for (int64_t i = 0; i < n; i++) y[i] = f(x[i]);
+        return;
+    }
     for (int64_t i = 0; i < n; i++) { float v = load(a, at_lin(a, i)); store(d, at_lin(d, i), f(v)); }
 }
 template <typename F> inline void binary(ggml_tensor* d, F f) {
     const ggml_tensor* a = d->src[0]; const ggml_tensor* b = d->src[1];
     assert(a->type == GGML_TYPE_F32 && b->type == GGML_TYPE_F32 && d->type == GGML_TYPE_F32);
+    const bool rows_contig = a->nb[0] == 4 && d->nb[0] == 4 && b->nb[0] == 4;
     for (int64_t i3 = 0; i3 < d->ne[3]; i3++) for (int64_t i2 = 0; i2 < d->ne[2]; i2++) for (int64_t i1 = 0; i1 < d->ne[1]; i1++) {
         const int64_t j1 = i1 % b->ne[1], j2 = i2 % b->ne[2], j3 = i3 % b->ne[3];
+        if (rows_contig && (b->ne[0] == d->ne[0] || b->ne[0] == 1)) {
+            const float* x = (const float*)at(a, 0, i1, i2, i3); const float* y = (const float*)at(b, 0, j1, j2, j3); float* o = (float*)at(d, 0, i1, i2, i3);
+            if (b->ne[0] == 1) { const float yv = y[0]; for (int64_t i0 = 0; i0 < d->ne[0]; i0++) o[i0] = f(x[i0], yv); }
+            else for (int64_t i0 = 0; i0 < d->ne[0]; i0++) o[i0] = f(x[i0], y[i0]);
+            continue;
+        }
         for (int64_t i0 = 0; i0 < d->ne[0]; i0++) {
             const float x = *(const float*)at(a, i0, i1, i2, i3), y = *(const float*)at(b, i0 % b->ne[0], j1, j2, j3);
             *(float*)at(d, i0, i1, i2, i3) = f(x, y);
@@ -402,6 +415,16 @@ inline void copy_convert(const ggml_tensor* a, ggml_tensor* d) {         // same
         }
         return;
     }
+    if (same_shape) {                                   // e.g. cont(transpose / permute): strided source, no index arithmetic per element
+        const size_t es = ggml_type_size(a->type);
+        for (int64_t i3 = 0; i3 < a->ne[3]; i3++) for (int64_t i2 = 0; i2 < a->ne[2]; i2++) for (int64_t i1 = 0; i1 < a->ne[1]; i1++) {
+            const char* sp = at(a, 0, i1, i2, i3); char* dp = at(d, 0, i1, i2, i3);
+            if (a->type == d->type && es == 4) for (int64_t i0 = 0; i0 < a->ne[0]; i0++) *(uint32_t*)(dp + i0 * d->nb[0]) = *(const uint32_t*)(sp + i0 * a->nb[0]);
+            else if (a->type == d->type && es == 2) for (int64_t i0 = 0; i0 < a->ne[0]; i0++) *(uint16_t*)(dp + i0 * d->nb[0]) = *(const uint16_t*)(sp + i0 * a->nb[0]);
+            else for (int64_t i0 = 0; i0 < a->ne[0]; i0++) store(d, dp + i0 * d->nb[0], load(a, sp + i0 * a->nb[0]));
+        }
+        return;
+    }
     for (int64_t i = 0; i < n; i++) store(d, at_lin(d, i), load(a, at_lin(a, i)));
 }
 
@@ -414,11 +437,13 @@ inline void mul_mat(ggml_tensor* d) {
     std::vector<float> brow((size_t)M * K), arow;
     for (int64_t i3 = 0; i3 < b->ne[3]; i3++) for (int64_t i2 = 0; i2 < b->ne[2]; i2++) {
         // gather + round the activation rows of this (i2, i3) plane
-        for (int64_t m = 0; m < M; m++) for (int64_t k = 0; k < K; k++) {
-            float v = load(b, at(b, k, m, i2, i3));
-            if (a->type == GGML_TYPE_F16) v = ggml_shim_f16_to_f32(ggml_shim_f32_to_f16(v));
-            else if (a->type == GGML_TYPE_BF16) v = ggml_shim_bf16_to_f32(ggml_shim_f32_to_bf16(v));
-            brow[(size_t)m * K + k] = v;
+#pragma omp parallel for schedule(static) num_threads(g_threads) if (M * K > 65536)
+        for (int64_t m = 0; m < M; m++) {
+            float* dst = &brow[(size_t)m * K];
+            if (b->type == GGML_TYPE_F32 && b->nb[0] == 4) memcpy(dst, at(b, 0, m, i2, i3), (size_t)K * 4);
+            else for (int64_t k = 0; k < K; k++) dst[k] = load(b, at(b, k, m, i2, i3));
+            if (a->type == GGML_TYPE_F16) for (int64_t k = 0; k < K; k++) dst[k] = (float)(_Float16)dst[k];
+            else if (a->type == GGML_TYPE_BF16) for (int64_t k = 0; k < K; k++) dst[k] = ggml_shim_bf16_to_f32(ggml_shim_f32_to_bf16(dst[k]));
         }
         const int64_t a2 = i2 / r2, a3 = i3 / r3;
 #pragma omp parallel for schedule(static) num_threads(g_threads) if (N * M * K > 65536)
@@ -426,6 +451,8 @@ inline void mul_mat(ggml_tensor* d) {
             std::vector<float> w((size_t)K);
             const char* ap = at(a, 0, n, a2, a3);
             if (a->type == GGML_TYPE_F32) memcpy(w.data(), ap, (size_t)K * 4);
+            else if (a->type == GGML_TYPE_BF16) { const uint16_t* p16 = (const uint16_t*)ap; for (int64_t k = 0; k < K; k++) w[k] = ggml_shim_bf16_to_f32(p16[k]); }
+            else if (a->type == GGML_TYPE_F16) { const _Float16* p16 = (const _Float16*)ap; for (int64_t k = 0; k < K; k++) w[k] = (float)p16[k]; }
             else for (int64_t k = 0; k < K; k++) w[k] = load(a, ap + k * a->nb[0]);
             for (int64_t m = 0; m < M; m++) {
                 const float* x = &brow[(size_t)m * K];
@@ -502,6 +529,13 @@ inline void compute(ggml_tensor* d) {
         case GGML_OP_CPY: case GGML_OP_CONT: case GGML_OP_DUP: copy_convert(a, d); break;
         case GGML_OP_CONCAT: {
             const int dim = d->op_params[0];
+            if (dim == 0 && a->nb[0] == ggml_type_size(a->type) && b->nb[0] == a->nb[0] && d->nb[0] == a->nb[0]) {      // rows are runs of bytes
+                for (int64_t i3 = 0; i3 < d->ne[3]; i3++) for (int64_t i2 = 0; i2 < d->ne[2]; i2++) for (int64_t i1 = 0; i1 < d->ne[1]; i1++) {
+                    memcpy(at(d, 0, i1, i2, i3), at(a, 0, i1, i2, i3), (size_t)a->ne[0] * a->nb[0]);
+                    memcpy(at(d, a->ne[0], i1, i2, i3), at(b, 0, i1, i2, i3), (size_t)b->ne[0] * b->nb[0]);
+                }
+                break;
+            }
             for (int64_t i3 = 0; i3 < d->ne[3]; i3++) for (int64_t i2 = 0; i2 < d->ne[2]; i2++) for (int64_t i1 = 0; i1 < d->ne[1]; i1++) for (int64_t i0 = 0; i0 < d->ne[0]; i0++) {
                 int64_t idx[4] = {i0, i1, i2, i3};
                 const ggml_tensor* s = a;
@@ -517,10 +551,16 @@ inline void compute(ggml_tensor* d) {
         case GGML_OP_IM2COL: {      // a = kernel [K, IC, OC], b = input [L, IC, N] (F32) -> d [IC*K, OL, N] F16
             const int s0 = d->op_params[0], p0 = d->op_params[1], d0 = d->op_params[2];
             const int64_t K = a->ne[0], IC = a->ne[1], L = b->ne[0], OL = d->ne[1], N = d->ne[2];
-            for (int64_t n = 0; n < N; n++) for (int64_t ol = 0; ol < OL; ol++) for (int64_t ic = 0; ic < IC; ic++) for (int64_t k = 0; k < K; k++) {
-                const int64_t il = ol * s0 + k * d0 - p0;
-                const float v = (il < 0 || il >= L) ? 0.f : load(b, at(b, il, ic, n, 0));
-                store(d, at(d, ic * K + k, ol, n, 0), v);
+            assert(b->type == GGML_TYPE_F32);
+            for (int64_t n = 0; n < N; n++) {
+#pragma omp parallel for schedule(static) num_threads(g_threads) if (OL * IC * K > 32768)
+                for (int64_t ol = 0; ol < OL; ol++) {
+                    _Float16* o = (_Float16*)at(d, 0, ol, n, 0);
+                    for (int64_t ic = 0; ic < IC; ic++) for (int64_t k = 0; k < K; k++) {
+                        const int64_t il = ol * s0 + k * d0 - p0;
+                        o[ic * K + k] = (_Float16)((il < 0 || il >= L) ? 0.f : *(const float*)at(b, il, ic, n, 0));
+                    }
+                }
             }
             break;
         }
@@ -529,8 +569,18 @@ inline void compute(ggml_tensor* d) {
             const int64_t K = a->ne[0], OC = a->ne[1], IC = a->ne[2], L = b->ne[0];
             const int64_t n_out = ggml_nelements(d);
             for (int64_t i = 0; i < n_out; i++) *(float*)at_lin(d, i) = 0.f;
-            std::vector<float> w((size_t)K * OC * IC), x((size_t)L * IC);                 // kernel -> [oc][k][ic], source -> [l][ic] (ggml's wdata permutation)
-            for (int64_t ic = 0; ic < IC; ic++) for (int64_t oc = 0; oc < OC; oc++) for (int64_t k = 0; k < K; k++) w[((size_t)oc * K + k) * IC + ic] = load(a, at(a, k, oc, ic, 0));
+            // kernel -> [oc][k][ic], source -> [l][ic] (ggml's wdata permutation). The permuted kernel is cached per weight tensor: weights
+            // are leaves that never change after loading (keyed by data pointer + shape).
+            static std::vector<std::pair<const void*, std::vector<float>>> wcache;
+            std::vector<float>* wp = nullptr;
+            for (auto& e : wcache) if (e.first == a->data && e.second.size() == (size_t)K * OC * IC) wp = &e.second;
+            if (!wp) {
+                wcache.emplace_back(a->data, std::vector<float>((size_t)K * OC * IC));
+                wp = &wcache.back().second;
+                for (int64_t ic = 0; ic < IC; ic++) for (int64_t oc = 0; oc < OC; oc++) for (int64_t k = 0; k < K; k++) (*wp)[((size_t)oc * K + k) * IC + ic] = load(a, at(a, k, oc, ic, 0));
+            }
+            const std::vector<float>& w = *wp;
+            std::vector<float> x((size_t)L * IC);
             for (int64_t ic = 0; ic < IC; ic++) for (int64_t l = 0; l < L; l++) x[(size_t)l * IC + ic] = load(b, at(b, l, ic, 0, 0));
 #pragma omp parallel for schedule(static) num_threads(g_threads)
             for (int64_t oc = 0; oc < OC; oc++)
@@ -606,6 +656,15 @@ inline void compute(ggml_tensor* d) {
 enum ggml_status { GGML_STATUS_SUCCESS = 0 };
 static inline ggml_status ggml_backend_graph_compute(ggml_backend_t backend, ggml_cgraph* g) {
     ggml_shim::g_threads = backend ? backend->n_threads : 1;
-    for (auto* t : g->nodes) ggml_shim::compute(t);
+    static const bool prof = getenv("GGML_SHIM_PROFILE") != nullptr;       // per-op wall time, printed at exit (development aid)
+    if (!prof) { for (auto* t : g->nodes) ggml_shim::compute(t); return GGML_STATUS_SUCCESS; }
+    static double acc[64] = {0}; static long cnt[64] = {0}; static bool reg = false;
+    if (!reg) { reg = true; atexit([] { for (int i = 0; i < 64; i++) if (cnt[i]) fprintf(stderr, "ggml shim op %2d: %8ld calls %9.1f ms\n", i, cnt[i], acc[i] * 1e3); }); }
+    for (auto* t : g->nodes) {
+        struct timespec a, b; clock_gettime(CLOCK_MONOTONIC, &a);
+        ggml_shim::compute(t);
+        clock_gettime(CLOCK_MONOTONIC, &b);
+        acc[t->op] += (b.tv_sec - a.tv_sec) + (b.tv_nsec - a.tv_nsec) * 1e-9; cnt[t->op]++;
+    }
     return GGML_STATUS_SUCCESS;
 }

@@ -703,6 +703,8 @@ void oracle_flow_head(oracle_ctx* c, const float* h1024, const float* noise32, f
 void oracle_mimi_reset(oracle_stream* s) { mimi_reset(s); }
 void oracle_mimi_frame(oracle_stream* s, const float* latent32, float* pcm1920) { mimi_frame(s, latent32, pcm1920); }
 int oracle_current_end(oracle_stream* s) { return s->current_end; }
+// teacher forcing: the next step's backbone input (the reference keeps it in states->output, src/pocket_tts.cpp:487)
+void oracle_set_backbone_input(oracle_stream* s, const float* latent32) { memcpy(s->backbone_input, latent32, 32 * sizeof(float)); }
 int oracle_mimi_offset(oracle_stream* s) { return s->mimi_offset; }
 void oracle_set_mimi_offset(oracle_stream* s, int off) { s->mimi_offset = off; }
 // copies KV rows [0,current_end) of layer l: out [current_end][1024]

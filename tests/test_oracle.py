@@ -82,3 +82,29 @@ def test_oracle_stop_rule(orc_eos):
         n += 1
     assert n == counts[text]["frames"]
     assert n < counts[text]["max_gen_len"]
+
+
+def test_oracle_matches_reference_sources_golden(oracle_mod):
+    """The oracle against golden vectors produced by the reference's own sources (oracle/_ref, tools/make_golden_ref.py): runs wherever
+    the fixtures are, without /root/reference. F32 checkpoint: agreement ~1e-4; BF16: bf16 rounding flips (stated tolerances)."""
+    import json
+    import os
+    import numpy as np
+    from conftest import BENCH_SENTENCE, REPO, snr_db
+    from make_assets import default_model_dir
+    gold = os.path.join(REPO, "tests", "golden")
+    for dtype, lat_tol, snr_min in (("f32", 1e-3, 58.0), ("bf16", 4e-2, 40.0)):
+        g = np.load(os.path.join(gold, f"ref_bench_noise_{dtype}.npz"))
+        o = oracle_mod.Oracle(default_model_dir(eos_mode="never", dtype=dtype.upper()), threads=os.cpu_count() or 1)
+        s = o.stream("cosette", kv_capacity=1000)
+        assert s.sentence_init(BENCH_SENTENCE) == list(g["tokens"])
+        for i in range(8):
+            ok, lat, pcm, e = s.step(g["noise"][i])
+            assert ok and s.current_end == int(g["current_end"][i])
+            assert np.abs(lat - g["latents"][i]).max() < lat_tol, (dtype, i)
+            assert snr_db(g["pcm"][i], pcm) > snr_min, (dtype, i)
+            s_lat = g["latents"][i]
+            oracle_mod.lib().oracle_set_backbone_input(s.h, s_lat.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_float)))
+    ref_counts = json.load(open(os.path.join(gold, "ref_frame_counts_eos_mid.json")))
+    own_counts = json.load(open(os.path.join(gold, "frame_counts_eos_mid.json")))
+    assert {k: v["frames"] for k, v in ref_counts.items()} == {k: v["frames"] for k, v in own_counts.items()}
