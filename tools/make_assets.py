@@ -131,8 +131,9 @@ def synth_weights(seed: int, eos_mode: str) -> dict[str, np.ndarray]:
         # parity checkpoints: P(logit_raw > 1.64) ~ 5 % per frame -> EOS lands mid-sentence
         W["flow_lm.out_eos.bias"] = np.array([-5.64], dtype=np.float32)
     elif eos_mode == "late":
-        # ragged-throughput checkpoints: P(logit_raw > 2.46) ~ 0.7 % per frame -> sentences end after ~100+ frames or at their cap
-        W["flow_lm.out_eos.bias"] = np.array([-6.46], dtype=np.float32)
+        # ragged-throughput checkpoints: the raw logit has std ~1.2 over a generation (measured: bias -6.46 ended sentences after ~50 frames),
+        # so -7.0 gives P(EOS) ~ 0.6 % per frame: sentences end after ~100+ frames or at their cap, i.e. raggedly
+        W["flow_lm.out_eos.bias"] = np.array([-7.0], dtype=np.float32)
     else:
         raise ValueError(eos_mode)
     for l in range(6):
@@ -313,7 +314,7 @@ def make_model_dir(out_dir: str, seed: int = 1234, dtype: str = "BF16", eos_mode
 
 def default_model_dir(eos_mode: str = "never", dtype: str = "BF16", t_voice: int = 125, seed: int = 1234, voices=None) -> str:
     root = os.environ.get("PTTS_B200_ASSETS", "/tmp/ptts_b200_assets")
-    name = f"model_s{seed}_{dtype.lower()}_{eos_mode}_v{t_voice}" + ("" if voices is None else "_" + "-".join(voices))
+    name = f"model_s{seed}_{dtype.lower()}_{eos_mode + ('7' if eos_mode == 'late' else '')}_v{t_voice}" + ("" if voices is None else "_" + "-".join(voices))
     return make_model_dir(os.path.join(root, name), seed=seed, dtype=dtype, eos_mode=eos_mode, t_voice=t_voice, voices=voices)
 
 
