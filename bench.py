@@ -471,13 +471,18 @@ def run_ragged(env: Env):
         return b, utts, frames, dt
 
     one_run(mine[: min(len(mine), 2 * args.batch)], 0)            # warm-up: voice prefills, graph captures for the stepped ranges
-    b, utts, frames, dt = one_run(mine, 1)
+    # (a) every frame is copied to a host buffer as it is collected (D2H + one host copy per step, like the e2e leg) but not kept;
+    # (b) the whole job's audio is accumulated in RAM per utterance (2+ GB here: first-touch page faults then dominate the host loop)
+    b_acc, _, frames_acc, dt_acc = one_run(mine, 1)
+    acc_ms = sharding.gather_stats([float(frames_acc), dt_acc * 1e3], device="cuda")
+    del b_acc
+    b, utts, frames, dt = one_run(mine, 0)
     st = b.stats()
     g = sharding.gather_stats([float(frames), dt * 1e3, float(st["steps"]), float(st["slot_steps"]), float(st["refills"]), float(sum(costs[i] for i in mine))], device="cuda")
     t_max = float(g[:, 1].max()) * 1e-3
     tot_frames = float(g[:, 0].sum())
     out = {"workload": f"configs[4]: {per_gpu} sentences per GPU (3-45 words, EOS-firing checkpoint, 8 voices), {args.batch} slots per GPU, continuous batching, "
-                       f"text in -> PCM on the host, LPT sharding of {total} sentences over {env.world} rank(s)",
+                       f"text in -> PCM frames delivered to a host buffer every step, LPT sharding of {total} sentences over {env.world} rank(s)",
            "value": round(tot_frames / t_max, 1), "unit": UNIT, "scaling": "weak", "seconds": round(t_max, 3), "frames": int(tot_frames),
            "sentences": total, "steps_max": int(g[:, 2].max()), "refills_max": int(g[:, 4].max()),
            "idle_slot_fraction": round(1.0 - float(g[:, 0].sum()) / float(g[:, 3].sum()), 4),
@@ -485,7 +490,9 @@ def run_ragged(env: Env):
            "rank_cap_imbalance": round(float(g[:, 5].max() / g[:, 5].mean() - 1.0), 5),
            "per_rank_frames": [int(x) for x in g[:, 0]], "per_rank_ms": [round(float(x), 1) for x in g[:, 1]],
            "refill_policy": {"refill_min": args.refill_min, "refill_every": args.refill_every},
-           "audio_seconds_per_wall_second": round(tot_frames / t_max / 12.5, 1)}
+           "host_ms_rank0": {k: round(st[k], 1) for k in ("wall_ms", "begin_ms", "submit_ms", "collect_ms")},
+           "audio_seconds_per_wall_second": round(tot_frames / t_max / 12.5, 1),
+           "value_accumulating_all_pcm_in_ram": round(float(acc_ms[:, 0].sum()) / (float(acc_ms[:, 1].max()) * 1e-3), 1)}
     ctx.close()
     return out
 
@@ -513,6 +520,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip private_kv / kv_f32 / multi_voice / ragged / verify / sustained")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--only-ragged", action="store_true", help="development: run only the continuous-batching workload")
     ap.add_argument("--verify", action="store_true", help="run the oracle check of the timed context even with --no-extras")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -558,6 +566,11 @@ def main():
     env = Env(args)
     B = args.batch
 
+    if args.only_ragged:
+        r = run_ragged(env)
+        if rank == 0:
+            print(json.dumps({"ragged": r}), flush=True)
+        return 0
     prim = run_mode(env, "shared" if args.prefix_share else "private", args.prefix_share, 0, primary=True, verify=((not args.no_extras or args.verify) and not args.no_verify and world == 1))
     extras = {}
     if not args.no_extras:

@@ -172,7 +172,7 @@ B200_API int ptts_c_stream_pending(ptts_stream_t* s, int index, char* buf, int b
  * sentence inside ptts_stream_receive (src/pocket_tts.cpp:494-519); here sentences of many utterances share the engine's slots and a
  * finished slot is refilled while the others keep generating. Utterance audio = its sentences' frames in order. ---- */
 typedef struct ptts_batch_t ptts_batch_t;
-typedef struct ptts_batch_stats { long long steps, frames, slot_steps, sentences, refills; double wall_ms; } ptts_batch_stats;
+typedef struct ptts_batch_stats { long long steps, frames, slot_steps, sentences, refills; double wall_ms, begin_ms, submit_ms, collect_ms; } ptts_batch_stats;
 B200_API ptts_batch_t* ptts_c_batch_create(ptts_context_t* ctx, int n_slots /* 0 = all engine slots */);
 B200_API void ptts_c_batch_destroy(ptts_batch_t* b);
 /* refill policy: start queued sentences once refill_min slots are free or refill_every steps passed; stepped range rounded up to

@@ -28,7 +28,7 @@ class B200Config(ctypes.Structure):
 
 class BatchStats(ctypes.Structure):
     _fields_ = [("steps", ctypes.c_longlong), ("frames", ctypes.c_longlong), ("slot_steps", ctypes.c_longlong), ("sentences", ctypes.c_longlong),
-                ("refills", ctypes.c_longlong), ("wall_ms", ctypes.c_double)]
+                ("refills", ctypes.c_longlong), ("wall_ms", ctypes.c_double), ("begin_ms", ctypes.c_double), ("submit_ms", ctypes.c_double), ("collect_ms", ctypes.c_double)]
 
 
 _I32P, _F32P, _U32P = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint32)

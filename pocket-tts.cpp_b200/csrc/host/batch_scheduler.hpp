@@ -35,6 +35,7 @@ struct BatchStats {
     long long sentences = 0;      // sentences completed
     long long refills = 0;        // sentence-start calls
     double wall_ms = 0.0;         // run() wall time
+    double begin_ms = 0.0, submit_ms = 0.0, collect_ms = 0.0;   // host time inside the three engine calls (collect includes waiting for the GPU)
 };
 
 class BatchScheduler {
@@ -91,11 +92,16 @@ public:
                     Job& J = jobs_[j];
                     if (effective_cap(J) <= 0) { J.done = true; stats_.sentences++; s--; continue; }   // no room (or empty cap): nothing to generate
                     slots_[s].job = j; slots_[s].live_from = submit_idx; started_[j] = true;
+                    // one allocation per sentence, sized by its cap (virtual memory only until frames arrive): growing the buffer frame by
+                    // frame re-faulted every page several times and cost more host time per step than the GPU step itself
+                    if (keep_pcm) J.pcm.reserve((size_t)effective_cap(J) * frame_);
                     sl.push_back(s); vo.push_back(J.voice); toks.insert(toks.end(), J.ids.begin(), J.ids.end()); off.push_back((int32_t)toks.size());
                     mg.push_back(J.max_gen); fae.push_back(J.fae); tp.push_back(J.temp); rs.push_back(J.rng_stream);
                 }
                 if (!sl.empty()) {
+                    const auto tb = clk::now();
                     const int rc = ops_.begin(ops_.user, (int)sl.size(), sl.data(), vo.data(), toks.data(), off.data(), mg.data(), fae.data(), tp.data(), rs.data());
+                    stats_.begin_ms += std::chrono::duration<double, std::milli>(clk::now() - tb).count();
                     if (rc != 0) return rc;
                     stats_.refills++; since_refill = 0;
                 }
@@ -106,7 +112,9 @@ public:
             // ---- submit a step while work remains and the pipeline has room ----
             if (busy > 0 && (int)inflight_n.size() < depth) {
                 int n = std::min(n_slots_, (top + range_quantum - 1) / range_quantum * range_quantum);
+                const auto ts = clk::now();
                 const int rc = ops_.submit(ops_.user, 0, n);
+                stats_.submit_ms += std::chrono::duration<double, std::milli>(clk::now() - ts).count();
                 if (rc != 0) return rc;
                 inflight_n.push_back(n); submit_idx++; since_refill++;
                 stats_.steps++; stats_.slot_steps += n;
@@ -115,7 +123,9 @@ public:
             // ---- collect the oldest step ----
             if (inflight_n.empty()) continue;
             const int n = inflight_n.front(); inflight_n.pop_front();
+            const auto tc0 = clk::now();
             const int rc = ops_.collect(ops_.user, pcm.data(), produced.data());
+            stats_.collect_ms += std::chrono::duration<double, std::milli>(clk::now() - tc0).count();
             if (rc < 0) return rc;
             for (int s = 0; s < n; s++) {
                 Slot& S = slots_[s];

@@ -385,7 +385,7 @@ int ptts_c_batch_read(ptts_batch_t* b, int utt, float* pcm, int max_frames) {
 void ptts_c_batch_stats(ptts_batch_t* b, ptts_batch_stats* out) {
     if (!b || !out) return;
     const BatchStats& s = b->sched->stats();
-    out->steps = s.steps; out->frames = s.frames; out->slot_steps = s.slot_steps; out->sentences = s.sentences; out->refills = s.refills; out->wall_ms = s.wall_ms;
+    out->steps = s.steps; out->frames = s.frames; out->slot_steps = s.slot_steps; out->sentences = s.sentences; out->refills = s.refills; out->wall_ms = s.wall_ms; out->begin_ms = s.begin_ms; out->submit_ms = s.submit_ms; out->collect_ms = s.collect_ms;
 }
 
 // Host-only helpers (no GPU needed): tokenizer / splitter objects for CPU-side tests and FFI users.

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""profiles/attn_flow_traffic.json from an `ncu --set full` capture of one attn_flow_split_kernel launch and the bench line printed by the
-same (profiled) run. Usage: python tools/make_traffic_json.py <capture.ncu-rep> <bench stdout log> <tag>"""
+"""profiles/attn_stream_traffic_<mode>.json from an `ncu --set full` capture that contains an attn_flow_split_kernel launch and the bench line
+printed by the same (profiled) run; bench.py reads it for `roofline.traffic` of that mode (shared | private_kv | kv_f32).
+Usage: python tools/make_traffic_json.py <capture.ncu-rep> <bench stdout log> <tag> [mode]"""
 import csv
 import json
 import os
@@ -15,12 +16,12 @@ def to_bytes(v, unit):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
 
 
-def main(rep, log, tag):
+def main(rep, log, tag, mode="shared"):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, units, val = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
+    val = [r for r in rows[2:] if "attn_flow_split_kernel" in r[hdr.index("Kernel Name")]][0]
     d = {h: (v, u) for h, u, v in zip(hdr, units, val)}
-    assert "attn_flow_split_kernel" in d["Kernel Name"][0], d["Kernel Name"][0]
     line = [l for l in open(log) if l.startswith("{")][-1]
     b = json.loads(line)
     j = {"kernel": "attn_flow_split_kernel", "capture": tag,
@@ -28,9 +29,9 @@ def main(rep, log, tag):
          "gpu_time_us": float(d["gpu__time_duration.sum"][0].replace(",", "")) * {"us": 1, "ns": 1e-3, "ms": 1e3}[d["gpu__time_duration.sum"][1]],
          "algorithmic_bytes_at_capture": int(b["roofline"]["algorithmic_bytes_per_launch"]),
          "note": "one launch (one FlowLM layer, all utterances of the batch); ncu --set full --clock-control none, cold-cache replay"}
-    json.dump(j, open(os.path.join(REPO, "profiles", "attn_flow_traffic.json"), "w"), indent=1)
+    json.dump(j, open(os.path.join(REPO, "profiles", f"attn_stream_traffic_{mode}.json"), "w"), indent=1)
     print(json.dumps(j))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], sys.argv[3])
+    main(*sys.argv[1:5])
