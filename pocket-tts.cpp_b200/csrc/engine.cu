@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 
 #include <cuda_profiler_api.h>
+#include <nvtx3/nvToolsExt.h>
 #include <algorithm>
 #include <map>
 #include <string>
@@ -19,6 +20,10 @@
 using namespace ptts;
 
 namespace {
+
+// NVTX ranges around the host-side phases (sentence start, prefill, step enqueue, collect): visible in Nsight Systems / ncu --nvtx; the
+// reference only has wall-clock prints around send / receive (demos/pocket-tts.cpp:456-520). Header-only NVTX3: no-ops without a tool.
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
 
 struct HostTensor { std::vector<float> f; std::vector<int64_t> shape; int dtype; };
 
@@ -1087,6 +1092,7 @@ int b200_finalize_weights(b200_engine* e) {
 //      with ascending positions. Everything is staged once (pinned ring -> device) and enqueued without a host synchronisation; the rows are
 //      processed in chunks of max_prefill_rows (a later chunk of a sentence attends to the cache rows the earlier chunk appended). ----
 static void prefill_rows(b200_engine* e, const std::vector<int>& slots, const std::vector<int>& pos, const std::vector<int>* tokens, const float* x_host) {
+    NvtxRange nvtx_range("ptts.prefill_rows");
     const int total = (int)slots.size(), MRp = e->cfg.max_prefill_rows;
     if (total == 0) return;
     const int nchunks = (total + MRp - 1) / MRp;
@@ -1150,6 +1156,7 @@ static void prefill_rows(b200_engine* e, const std::vector<int>& slots, const st
 }
 
 int b200_voice_create(b200_engine* e, const float* audio_prompt, int T) {
+    NvtxRange nvtx_range("ptts.voice_create");
     if (!e || !e->finalized || T < 0 || (T > 0 && !audio_prompt)) return B200_EINVAL;
     if (e->n_voices >= e->cfg.max_voices) return B200_ECAPACITY;
     if (T > e->cfg.kv_capacity) return B200_ECAPACITY;
@@ -1170,6 +1177,7 @@ int b200_begin_sentences(b200_engine* e, int n, const int32_t* slots, const int3
 
 int b200_begin_sentences_ex(b200_engine* e, int n, const int32_t* slots, const int32_t* voices, const int32_t* tokens, const int32_t* tok_off,
                             const int32_t* max_gen_len, const int32_t* frames_after_eos, const float* temp, const uint32_t* rng_stream) {
+    NvtxRange nvtx_range("ptts.begin_sentences");
     if (!e || !e->finalized || n < 0) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     std::vector<int> rs, rp, rt;
@@ -1273,6 +1281,7 @@ int b200_join(b200_engine* e) {
 }
 
 int b200_step(b200_engine* e, int slot0, int n, const float* noise, float* pcm, int32_t* produced, float* latents, float* eos_logit) {
+    NvtxRange nvtx_range("ptts.step");
     if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots || !pcm || !produced) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     e->ensure_pinned((size_t)n * (FRAME + 2 * LDIM + 1), (size_t)std::max(n, 16) * 3);
@@ -1305,6 +1314,7 @@ int b200_step(b200_engine* e, int slot0, int n, const float* noise, float* pcm, 
 // decode of frame t is interleaved with the FlowLM step of frame t+1 (run_step), so a caller that keeps two submits ahead of its
 // collects never leaves the GPU waiting for the host. Frames come back in submission order.
 int b200_submit(b200_engine* e, int slot0, int n, const float* noise) {
+    NvtxRange nvtx_range("ptts.submit");
     if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots) return B200_EINVAL;
     if (e->submit_t - e->collect_t >= 3) return B200_ESTATE;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
@@ -1333,6 +1343,7 @@ int b200_submit(b200_engine* e, int slot0, int n, const float* noise) {
 }
 
 int b200_collect(b200_engine* e, float* pcm, int32_t* produced) {
+    NvtxRange nvtx_range("ptts.collect");
     if (!e || !pcm || !produced) return B200_EINVAL;
     if (e->collect_t == e->submit_t) return B200_ESTATE;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));

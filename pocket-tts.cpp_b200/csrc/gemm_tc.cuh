@@ -49,6 +49,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// TMA store of a shared-memory box (written by this warp through the generic proxy, made visible with fence.proxy.async) into a 3-D tensor
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"((uint64_t)tm), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // staging may be rewritten
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }          // writes are complete
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -96,6 +105,7 @@ struct TcParams {
     long long ws_split_stride;   // elements between the partial-sum planes of consecutive splits
     int epi_class;               // index into EPI_CLASSES (0 = fully dynamic epilogue)
     int prefetch;                // 1 = small-M GEMM: prefetch the first work item's whole weight stream into L2 up front
+    int out_rps;                 // TMA-store epilogue: GEMM rows per output slot (>= R for a plain matrix)
 };
 
 // Epilogue staging per epilogue warp: a 32 x 32 f32 accumulator chunk transposed through shared memory (rows padded to 36 floats:
@@ -237,6 +247,61 @@ __device__ __forceinline__ void epi_chunk(const Epi& e, const float* stg, const 
     }
 }
 
+// ---- TMA-STORE epilogue (every generic class without a per-element gate / hi+lo split) ----
+// The transposing epilogue above costs ~0.8 warp-instructions per output element (staging round trip + per-row address arithmetic +
+// 8/16-byte global stores): the SEANet conv GEMMs were instruction-issue bound in it (ncu r1_v15: issue slots 52-59 % busy, tensor pipe
+// 3-18 %). Here every lane keeps ITS row of the 32 x 32 accumulator chunk (TMEM lane = row): bias / scale / residual / activation in
+// registers, the finished row goes to a swizzled shared-memory box (f32: 128-byte rows, SWIZZLE_128B; 16-bit: 64-byte rows, SWIZZLE_64B;
+// both conflict-free for st.shared.v4 by row) and one elected lane hands the whole box to the TMA engine. Rows / slots outside the tensor
+// are clipped by the tensor map, so ragged tails need no predicates. The residual is read with plain loads (one 128-byte line per lane).
+constexpr unsigned EF_NO_TMA_STORE = EF_ROWMUL | EF_SPLIT | EF_DYNAMIC;
+template <unsigned F>
+__device__ __forceinline__ void epi_chunk_tma(const Epi& e, float (&v)[32], uint8_t* stg, int lane, int col0, const CUtensorMap* tmO, const CUtensorMap* tmO2,
+                                              int c_row, int c_slot, bool store, const float* resid_row) {
+    constexpr bool has_cs = (F & EF_COLSCALE) != 0, has_res = (F & EF_RESID) != 0, has_out = (F & EF_OUT) != 0;
+    constexpr bool o2_bf16 = (F & EF_OUT2_BF16) != 0, o2_f16 = (F & EF_OUT2_F16) != 0;
+    constexpr int act = (F & EF_GELU) ? ACT_GELU : (F & EF_SILU) ? ACT_SILU : (F & EF_ELU) ? ACT_ELU : ACT_NONE;
+    if (e.bias) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j); v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w; }
+    }
+    if (has_cs) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.colscale + col0) + j); v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w; }
+    }
+    if (has_res && resid_row) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const float4 b = *(reinterpret_cast<const float4*>(resid_row + col0) + j); v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w; }
+    }
+    const uint32_t s32 = smem_u32(stg);
+    if (has_out) {
+        if (lane == 0) tma_store_wait_read();                   // the previous box has been read out of the staging buffer
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++) *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && store) { tma_store_3d(tmO, s32, col0, c_row, c_slot); tma_store_commit(); }
+    }
+    if (o2_bf16 || o2_f16) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            float a = v[2 * k], b = v[2 * k + 1];
+            if (act == ACT_GELU) { a = gelu_ggml(a); b = gelu_ggml(b); } else if (act == ACT_SILU) { a = silu_f(a); b = silu_f(b); } else if (act == ACT_ELU) { a = elu_f(a); b = elu_f(b); }
+            if (o2_bf16) { const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); pk[k] = *reinterpret_cast<const uint32_t*>(&h); }
+            else { const __half2 h = __floats2half2_rn(a, b); pk[k] = *reinterpret_cast<const uint32_t*>(&h); }
+        }
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; j++) *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && store) { tma_store_3d(tmO2, s32, col0, c_row, c_slot); tma_store_commit(); }
+    }
+}
+
 // ---- QKV epilogue for 32 consecutive columns (= half a head): RoPE with vector loads/stores (see epi_apply for the math) ----
 template <bool mimi>
 __device__ __forceinline__ void epi_qkv32(const Epi& e, int row, int col0, float (&v)[32]) {
@@ -314,9 +379,12 @@ struct TcCfg {
 // warps' top stall was instruction fetch (ncu r1_v11: stalled_no_instruction 2.2 per issue).
 template <int BN, int CLS>
 __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                         const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
                                                          const TcParams p, const Epi epi) {
     using Cfg = TcCfg<BN>;
     constexpr bool GEN = CLS > 0;
+    constexpr unsigned CF = EPI_CLASSES[GEN ? CLS : 0];
+    constexpr bool TMAEPI = GEN && (CF & EF_NO_TMA_STORE) == 0;   // see epi_chunk_tma
     const int STAGES = p.stages;
     pdl_trigger();                                             // the next kernel may start its prologue now
     extern __shared__ uint8_t smem_raw[];
@@ -333,6 +401,10 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW) : "memory");
+        if (TMAEPI) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmO) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmO2) : "memory");
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -421,10 +493,16 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
             const int ri = ew * 32 + lane;
             const int row = row_base + ri;
             const bool live = ri < nvalid;
-            if constexpr (GEN) {
+            if constexpr (GEN && !TMAEPI) {
                 rowinfo[lane] = make_int2(row / epi.rps, row % epi.rps);
                 __syncwarp();
             }
+            // TMA-store epilogue: this warp's 32 rows start at GEMM row g0 -> (slot, row) of the output tensor; its own row's residual line
+            const int g0 = row_base + ew * 32;
+            const bool w_store = ew * 32 < nvalid;
+            const int c_slot = g0 / p.out_rps, c_row = g0 % p.out_rps;
+            const float* resid_row = nullptr;
+            if constexpr (TMAEPI && (CF & EF_RESID) != 0) { if (live) resid_row = epi.resid + epi.resid_map.off(row, epi.rps); }
             mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
             tc_fence_after();
             const long long ws_off = (long long)split * p.ws_split_stride;
@@ -444,13 +522,15 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * buf) : "memory");
                 }
-                if constexpr (GEN) {
+                if constexpr (TMAEPI) {
+                    epi_chunk_tma<CF>(epi, v, smem_gen + (warp - 2) * 4096, lane, tile_n * BN + c0, &tmO, &tmO2, c_row, c_slot + split, w_store, resid_row);   // split-K: plane `split` of the plain workspace
+                } else if constexpr (GEN) {
                     float4* sp = reinterpret_cast<float4*>(stg + lane * EPI_STG_LD);
 #pragma unroll
                     for (int j = 0; j < 8; j++) sp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     __syncwarp();
                     const int col = tile_n * BN + c0 + cq, rows_left = nvalid - ew * 32, tile_row0 = row_base + ew * 32;
-                    epi_chunk<EPI_CLASSES[GEN ? CLS : 0]>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off);
+                    epi_chunk<CF>(epi, stg, rowinfo, sub, cq, col, rows_left, tile_row0, ws_off);
                     __syncwarp();                                  // the staging tile is overwritten by the next chunk
                 } else {
                     if (live) epi_qkv32<CLS == -2>(epi, row, tile_n * BN + c0, v);
@@ -458,12 +538,13 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
             }
         }
     }
+    if constexpr (TMAEPI) { if (warp >= 2 && lane == 0) tma_store_wait_all(); }   // every box this lane handed to the TMA engine has been written
     tc_fence_before();
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
 }
 
-using TcKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const TcParams, const Epi);
+using TcKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const Epi);
 template <int BN>
 inline TcKernelFn tc_kernel_for(int cls) {
     switch (cls) {
@@ -565,7 +646,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 
 struct TcPlanCache {
     PFN_tmapEncodeTiled encode = nullptr;
-    std::map<std::tuple<const void*, long long, long long, long long, long long, int, int>, CUtensorMap> maps;
+    std::map<std::tuple<const void*, long long, long long, long long, long long, long long, int, int>, CUtensorMap> maps;   // see tc_get_map
     int num_sms = 148;
     bool coreside = false;      // see tc_gemm_launch; switched on by the engine while it enqueues the two-stream pipeline
     bool coreside_allowed = true;   // PTTS_B200_CORESIDE=0: never (deep rings / two Mimi CTAs per SM everywhere)
@@ -669,6 +750,8 @@ inline TcPlan tc_plan(int tiles_m, int R, int N, int K, int num_sms, bool want_l
     return best;
 }
 
+inline bool tc_tma_epilogue_geometry_ok(const Epi& e, int R);
+
 template <typename T>
 inline bool tc_gemm_supported(int R, int N, int K, const RowMap& amap, int a_rps, const Epi& epi) {
     // 1-2 rows: the GEMV kernel (one pass over the weights with plain loads) wins; from 3 rows on the split-K TMA stream of the tensor-core
@@ -680,23 +763,48 @@ inline bool tc_gemm_supported(int R, int N, int K, const RowMap& amap, int a_rps
         if (!warned) { warned = true; fprintf(stderr, "ptts_b200: warning: epilogue flags 0x%x have no tensor-core class; using the CUDA-core GEMM\n", epi_flags_of(epi)); }
         return false;
     }
+    if (epi.mode == EPI_GENERIC && (EPI_CLASSES[epi_class_of(epi)] & EF_NO_TMA_STORE) == 0 && !tc_tma_epilogue_geometry_ok(epi, R)) return false;
     const TcGeom g = tc_geometry(R, K, amap, a_rps);
     return g.ok;
 }
 
-inline const CUtensorMap* tc_get_map(TcPlanCache* c, const void* ptr, bool f16, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+// kind: 0 = bf16 operand, 1 = f16 operand (both SWIZZLE_128B), 2 = f32 output box (SWIZZLE_128B), 3 = 16-bit output box (SWIZZLE_64B)
+inline const CUtensorMap* tc_get_map(TcPlanCache* c, const void* ptr, int kind, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                                      const cuuint32_t* box) {
     auto key = std::make_tuple(ptr, (long long)dims[0], (long long)dims[1], (long long)(rank > 2 ? dims[2] : 1),
-                               (long long)(rank > 2 ? strides_bytes[1] : 0), (int)(box[1] | (box[0] << 12) | ((rank > 2 ? box[2] : 1) << 22)), (int)f16);
+                               (long long)strides_bytes[0], (long long)(rank > 2 ? strides_bytes[1] : 0),
+                               (int)(box[1] | (box[0] << 12) | ((rank > 2 ? box[2] : 1) << 22)), kind);
     auto it = c->maps.find(key);
     if (it != c->maps.end()) return &it->second;
     CUtensorMap m;
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = c->encode(&m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims,
-                           strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { fprintf(stderr, "ptts_b200: cuTensorMapEncodeTiled failed (%d)\n", (int)r); abort(); }
+    const CUtensorMapDataType dt = kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = c->encode(&m, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims,
+                           strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, kind == 3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "ptts_b200: cuTensorMapEncodeTiled failed (%d) kind %d dims %llu %llu %llu\n", (int)r, kind, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 1)); abort(); }
     return &(c->maps[key] = m);
+}
+
+// Output side of the TMA-store epilogue: GEMM row g lands in slot g / rps, row g % rps of a [slots][rps][N] tensor (plain matrix: one slot
+// of R rows). A warp's 32 consecutive rows must be one box: rps a multiple of 32, or a divisor of 32 (box = rps rows x 32/rps slots).
+inline bool tc_tma_epilogue_geometry_ok(const Epi& e, int R) {
+    const bool plain = e.rps >= R;
+    if (!plain && e.rps % 32 != 0 && 32 % e.rps != 0) return false;
+    auto ok_map = [&](const RowMap& m, int es) { return (m.row_stride * es) % 16 == 0 && (m.slot_stride * es) % 16 == 0 && (m.base * es) % 16 == 0 && (plain || m.slot_stride > 0); };
+    if (e.out && !ok_map(e.out_map, 4)) return false;
+    if (e.out2 && !ok_map(e.out2_map, 2)) return false;
+    return true;
+}
+inline const CUtensorMap* tc_out_map(TcPlanCache* c, const void* base_ptr, const RowMap& m, int es, int R, int N, int rps, int planes, long long plane_stride_elems) {
+    const bool plain = rps >= R;
+    const int rows_o = plain ? R : rps, slots_o = plain ? planes : (R + rps - 1) / rps;
+    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)rows_o, (cuuint64_t)slots_o};
+    const long long s2 = plain ? (planes > 1 ? plane_stride_elems : (long long)R * m.row_stride) : m.slot_stride;
+    cuuint64_t str[2] = {(cuuint64_t)m.row_stride * es, (cuuint64_t)s2 * es};
+    const int box_rows = std::min(32, rows_o), box_slots = std::max(1, std::min(32 / box_rows, slots_o));
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_slots};
+    return tc_get_map(c, (const char*)base_ptr + m.base * es, es == 4 ? 2 : 3, 3, dims, str, box);
 }
 
 // [N][K] row-major -> [K/64][N][64] (host side, at weight upload)
@@ -722,13 +830,13 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     cuuint64_t adims[3] = {(cuuint64_t)g.C, (cuuint64_t)g.rows_per_slot_buf, (cuuint64_t)g.n_slots};
     cuuint64_t astr[2] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.slot_stride * 2};
     cuuint32_t abox[3] = {64, (cuuint32_t)g.box_rows, (cuuint32_t)g.SB};
-    const CUtensorMap* ta = tc_get_map(c, A, f16, 3, adims, astr, abox);
+    const CUtensorMap* ta = tc_get_map(c, A, f16 ? 1 : 0, 3, adims, astr, abox);
     // weights are stored k-block-major, [K/64][N][64] (tc_kblock_major): the box of any tile width is ONE contiguous bn x 128 B run,
     // so cold weight streams from HBM are page-friendly instead of bn separate 128-byte pieces 2*K bytes apart
     cuuint64_t wdims[3] = {64, (cuuint64_t)N, (cuuint64_t)(K / 64)};
     cuuint64_t wstr[2] = {128, (cuuint64_t)N * 128};
     cuuint32_t wbox[3] = {64, (cuuint32_t)bn, 1};
-    const CUtensorMap* tw = tc_get_map(c, W, f16, 3, wdims, wstr, wbox);
+    const CUtensorMap* tw = tc_get_map(c, W, f16 ? 1 : 0, 3, wdims, wstr, wbox);
     TcParams p; p.R = R; p.N = N; p.K = K; p.kb_per_tap = g.C / 64; p.T = g.T; p.SB = g.SB; p.tps = g.tps; p.tiles_m = g.tiles_m;
     p.a_bytes = (uint32_t)(128 * g.box_rows * g.SB);
     // Small-M GEMMs (FlowLM decode: R = batch) cannot fill the SMs with output tiles alone: split K deterministically.
@@ -761,7 +869,15 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     const int st2 = bn == 128 ? TcCfg<128>::STAGES_2CTA : bn == 64 ? TcCfg<64>::STAGES_2CTA : TcCfg<32>::STAGES_2CTA;
     const int stage_bytes = 128 * 128 + bn * 128;
     p.stages = one_cta ? st1 : st2;
-    launch_k(c->pdl, kern, grid, dim3(320), (size_t)(p.stages * stage_bytes + EPI_SMEM + 1024 + 256), stream, *ta, *tw, p, kepi);
+    const CUtensorMap *to = ta, *to2 = ta;                    // unused by the other epilogues: any valid map
+    p.out_rps = 1 << 30;
+    if (cls > 0 && (EPI_CLASSES[cls] & EF_NO_TMA_STORE) == 0) {
+        const bool plain = kepi.rps >= R;
+        p.out_rps = plain ? (1 << 30) : kepi.rps;
+        if (kepi.out) to = tc_out_map(c, kepi.out, kepi.out_map, 4, R, N, kepi.rps, splits, p.ws_split_stride);
+        if (kepi.out2) to2 = tc_out_map(c, kepi.out2, kepi.out2_map, 2, R, N, kepi.rps, 1, 0);
+    }
+    launch_k(c->pdl, kern, grid, dim3(320), (size_t)(p.stages * stage_bytes + EPI_SMEM + 1024 + 256), stream, *ta, *tw, *to, *to2, p, kepi);
     if (ln_done) *ln_done = false;
     if (splits > 1) {
         if (ln_ok) {
