@@ -44,6 +44,7 @@ struct b200_engine {
     cudaStream_t stream_m = nullptr;
     cudaStream_t stream_t = nullptr;     // forked branch of the main stream: the shared-prefix tile kernel runs beside the per-utterance KV stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool tma_epilogue_allowed = getenv("PTTS_B200_TMA_EPILOGUE") ? atoi(getenv("PTTS_B200_TMA_EPILOGUE")) != 0 : true;   // tuning hook
     bool fork_tiles = getenv("PTTS_B200_FORK_TILES") ? atoi(getenv("PTTS_B200_FORK_TILES")) != 0 : true;   // tuning hook
     cudaEvent_t ev_main[2] = {nullptr, nullptr}, ev_mimi[2] = {nullptr, nullptr};
     bool ev_mimi_valid[2] = {false, false};
@@ -639,6 +640,8 @@ struct b200_engine {
         pdl_small = cfg.pdl >= 2 || (cfg.pdl == 1 && n <= 128);  // every kernel of the step
         pdl_chain = cfg.pdl >= 2;
         set_pdl(pdl_small);
+        // TMA-store epilogue for the large Mimi GEMMs only when no second stream runs beside them (see EPI_CLASSES in gemm_tc.cuh)
+        tc->tma_epilogue = tma_epilogue_allowed && (kind == 0 || kind == 1);
         auto body = [&]() {
             if (kind == 0) step_enqueue(slot0, n, injected);
             else if (kind == 1) { mimi_front(slot0, n, mx); mimi(slot0, n, mx); }
@@ -1136,6 +1139,7 @@ static void prefill_rows(b200_engine* e, const std::vector<int>& slots, const st
     if (x_host) PTTS_CUDA_CHECK(cudaMemcpyAsync(e->pf_x, px, b_x, cudaMemcpyHostToDevice, e->stream));
     e->pin_release(e->stream);
     e->set_pdl(false);
+    e->tc->tma_epilogue = false;                                  // the Mimi stream may be running beside the prefill
     const b200_engine::AttnCtx saved = e->actx;
     for (int c = 0; c < nchunks; c++) {
         const int r0 = c * MRp, R = std::min(MRp, total - r0);

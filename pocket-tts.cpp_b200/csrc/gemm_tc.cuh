@@ -119,7 +119,13 @@ constexpr int EPI_SMEM = EPI_WARPS * (EPI_STG_BYTES + EPI_ROW_BYTES);   // 38,91
 // of a few flag sets (epi_class) that the kernel switches on ONCE per 32-column chunk; everything inside is straight-line code.
 // EF_DYNAMIC keeps the fully general runtime version for anything not in the list.
 enum : unsigned { EF_BIAS = 1, EF_COLSCALE = 2, EF_ROWMUL = 4, EF_RESID = 8, EF_OUT = 16, EF_OUT2_BF16 = 32, EF_OUT2_F16 = 64, EF_SPLIT = 128,
-                  EF_GELU = 256, EF_SILU = 512, EF_ELU = 1024, EF_DYNAMIC = 1u << 31 };
+                  EF_GELU = 256, EF_SILU = 512, EF_ELU = 1024, EF_TMA = 1u << 30, EF_DYNAMIC = 1u << 31 };
+// EF_TMA marks the instantiations that use the TMA-store epilogue (epi_chunk_tma) instead of the transposing one; the host picks the
+// variant per launch (TcPlanCache::tma_epilogue && many M tiles). Measured on B200: the Mimi decoder alone 0.600 -> 0.563 ms per step at
+// batch 256 (every large conv / linear GEMM 5-20 % faster), but inside the two-stream pipeline the step got SLOWER (1.054 -> 1.115 ms:
+// the bulk stores of a co-resident Mimi CTA compete with the FlowLM stream's bulk loads for the SM's TMA path), and the decode-sized
+// GEMMs of the FlowLM chain lose ~3 % to the extra tensor-map prefetch and the store drain at CTA exit. Hence: TMA variants for the
+// Mimi-only / single-stream paths, transposing epilogue inside the pipeline and for all decode-sized GEMMs.
 constexpr unsigned EPI_CLASSES[] = {
     EF_DYNAMIC,                                             // 0 = not supported by the tensor-core kernel (CUDA-core fallback)
     EF_ELU | EF_OUT2_F16,                                   // 1 SEANet conv
@@ -133,9 +139,15 @@ constexpr unsigned EPI_CLASSES[] = {
     EF_SILU | EF_OUT2_BF16,                                 // 9 flow head mlp.0
     EF_ROWMUL | EF_RESID | EF_OUT,                          // 10 flow head mlp.2 (gate + residual)
     EF_RESID | EF_SILU | EF_OUT2_BF16,                      // 11 flow head cond_embed (+ t_combined, SiLU)
-    EF_OUT | EF_ELU | EF_OUT2_BF16,                         // 12 unit tests (bf16 flavour of class 2)
+    EF_OUT | EF_ELU | EF_OUT2_BF16 | EF_TMA,                // 12 unit tests (bf16 flavour of class 2, TMA-store epilogue)
     EF_ELU | EF_OUT2_F16 | EF_SPLIT,                        // 13 convt_split=1: conv feeding a transposed conv (hi | lo f16)
     EF_RESID | EF_ELU | EF_OUT2_F16 | EF_SPLIT,             // 14 convt_split=1: residual-block tail feeding a transposed conv
+    EF_GELU | EF_OUT2_BF16 | EF_TMA,                        // 15 = 5 with the TMA-store epilogue
+    EF_ELU | EF_OUT2_F16 | EF_TMA,                          // 16 = 1
+    EF_OUT | EF_ELU | EF_OUT2_F16 | EF_TMA,                 // 17 = 2
+    EF_RESID | EF_ELU | EF_OUT2_F16 | EF_TMA,               // 18 = 3
+    EF_COLSCALE | EF_RESID | EF_OUT | EF_TMA,               // 19 = 4
+    EF_COLSCALE | EF_RESID | EF_OUT2_F16 | EF_TMA,          // 20 = 8
 };
 constexpr int EPI_NCLASSES = sizeof(EPI_CLASSES) / sizeof(EPI_CLASSES[0]);
 
@@ -152,10 +164,16 @@ inline unsigned epi_flags_of(const Epi& e) {
     if (e.out2_type != OUT2_NONE) { if (e.act == ACT_GELU) f |= EF_GELU; else if (e.act == ACT_SILU) f |= EF_SILU; else if (e.act == ACT_ELU) f |= EF_ELU; }
     return f;
 }
-inline int epi_class_of(const Epi& e) {
+// want_tma: prefer the TMA-store variant when both exist, the transposing one otherwise
+inline int epi_class_of(const Epi& e, bool want_tma = false) {
     const unsigned f = epi_flags_of(e);
-    for (int i = 1; i < EPI_NCLASSES; i++) if (EPI_CLASSES[i] == f) return i;
-    return 0;
+    int any = 0;
+    for (int i = 1; i < EPI_NCLASSES; i++) {
+        if ((EPI_CLASSES[i] & ~EF_TMA) != f) continue;
+        if (((EPI_CLASSES[i] & EF_TMA) != 0) == want_tma) return i;
+        if (!any) any = i;
+    }
+    return any;
 }
 
 // One 32x32 accumulator chunk, already transposed into `stg` ([32][EPI_STG_LD] f32): lane (sub, cq) handles rows 4i + sub, columns
@@ -254,7 +272,6 @@ __device__ __forceinline__ void epi_chunk(const Epi& e, const float* stg, const 
 // registers, the finished row goes to a swizzled shared-memory box (f32: 128-byte rows, SWIZZLE_128B; 16-bit: 64-byte rows, SWIZZLE_64B;
 // both conflict-free for st.shared.v4 by row) and one elected lane hands the whole box to the TMA engine. Rows / slots outside the tensor
 // are clipped by the tensor map, so ragged tails need no predicates. The residual is read with plain loads (one 128-byte line per lane).
-constexpr unsigned EF_NO_TMA_STORE = EF_ROWMUL | EF_SPLIT | EF_DYNAMIC;
 template <unsigned F>
 __device__ __forceinline__ void epi_chunk_tma(const Epi& e, float (&v)[32], uint8_t* stg, int lane, int col0, const CUtensorMap* tmO, const CUtensorMap* tmO2,
                                               int c_row, int c_slot, bool store, const float* resid_row) {
@@ -384,7 +401,7 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
     using Cfg = TcCfg<BN>;
     constexpr bool GEN = CLS > 0;
     constexpr unsigned CF = EPI_CLASSES[GEN ? CLS : 0];
-    constexpr bool TMAEPI = GEN && (CF & EF_NO_TMA_STORE) == 0;   // see epi_chunk_tma
+    constexpr bool TMAEPI = GEN && (CF & EF_TMA) != 0;   // see epi_chunk_tma
     const int STAGES = p.stages;
     pdl_trigger();                                             // the next kernel may start its prologue now
     extern __shared__ uint8_t smem_raw[];
@@ -502,7 +519,13 @@ __global__ void __launch_bounds__(320, 2) gemm_tc_kernel(const __grid_constant__
             const bool w_store = ew * 32 < nvalid;
             const int c_slot = g0 / p.out_rps, c_row = g0 % p.out_rps;
             const float* resid_row = nullptr;
-            if constexpr (TMAEPI && (CF & EF_RESID) != 0) { if (live) resid_row = epi.resid + epi.resid_map.off(row, epi.rps); }
+            if constexpr (TMAEPI && (CF & EF_RESID) != 0) {
+                if (live) {
+                    resid_row = epi.resid + epi.resid_map.off(row, epi.rps);
+                    // the residual line(s) of this lane's row: ask L2 for them now, the accumulator is not ready yet
+                    for (int c0 = half * 32; c0 < BN; c0 += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(resid_row + tile_n * BN + c0));
+                }
+            }
             mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
             tc_fence_after();
             const long long ws_off = (long long)split * p.ws_split_stride;
@@ -564,6 +587,12 @@ inline TcKernelFn tc_kernel_for(int cls) {
         case 12: return gemm_tc_kernel<BN, 12>;
         case 13: return gemm_tc_kernel<BN, 13>;
         case 14: return gemm_tc_kernel<BN, 14>;
+        case 15: return gemm_tc_kernel<BN, 15>;
+        case 16: return gemm_tc_kernel<BN, 16>;
+        case 17: return gemm_tc_kernel<BN, 17>;
+        case 18: return gemm_tc_kernel<BN, 18>;
+        case 19: return gemm_tc_kernel<BN, 19>;
+        case 20: return gemm_tc_kernel<BN, 20>;
         default: return nullptr;
     }
 }
@@ -651,6 +680,7 @@ struct TcPlanCache {
     bool coreside = false;      // see tc_gemm_launch; switched on by the engine while it enqueues the two-stream pipeline
     bool coreside_allowed = true;   // PTTS_B200_CORESIDE=0: never (deep rings / two Mimi CTAs per SM everywhere)
     bool pdl = false;
+    bool tma_epilogue = false;  // large-M GEMMs use the TMA-store epilogue (set by the engine outside the two-stream pipeline)
     float* ws_buf[2] = {nullptr, nullptr}; size_t ws_elems = (size_t)32 << 20;   // split-K partial sums, one workspace per engine stream
     int cur_ws = 0;
 };
@@ -758,12 +788,12 @@ inline bool tc_gemm_supported(int R, int N, int K, const RowMap& amap, int a_rps
     // kernel is faster even though its 128-row tile is almost empty (measured per decode step: batch 4 0.75 -> 0.54 ms, batch 8 1.21 -> 0.55 ms)
     static const int min_rows = getenv("PTTS_B200_TC_MIN_ROWS") ? atoi(getenv("PTTS_B200_TC_MIN_ROWS")) : 3;
     if (R < min_rows || K % 64 != 0 || N % 32 != 0) return false;
-    if (epi.mode == EPI_GENERIC && epi_class_of(epi) == 0) {
+    if (epi.mode == EPI_GENERIC && epi_class_of(epi, false) == 0) {
         static bool warned = false;
         if (!warned) { warned = true; fprintf(stderr, "ptts_b200: warning: epilogue flags 0x%x have no tensor-core class; using the CUDA-core GEMM\n", epi_flags_of(epi)); }
         return false;
     }
-    if (epi.mode == EPI_GENERIC && (EPI_CLASSES[epi_class_of(epi)] & EF_NO_TMA_STORE) == 0 && !tc_tma_epilogue_geometry_ok(epi, R)) return false;
+    if (epi.mode == EPI_GENERIC && (EPI_CLASSES[epi_class_of(epi, false)] & EF_TMA) != 0 && !tc_tma_epilogue_geometry_ok(epi, R)) return false;   // TMA-only class
     const TcGeom g = tc_geometry(R, K, amap, a_rps);
     return g.ok;
 }
@@ -802,7 +832,7 @@ inline const CUtensorMap* tc_out_map(TcPlanCache* c, const void* base_ptr, const
     cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)rows_o, (cuuint64_t)slots_o};
     const long long s2 = plain ? (planes > 1 ? plane_stride_elems : (long long)R * m.row_stride) : m.slot_stride;
     cuuint64_t str[2] = {(cuuint64_t)m.row_stride * es, (cuuint64_t)s2 * es};
-    const int box_rows = std::min(32, rows_o), box_slots = std::max(1, std::min(32 / box_rows, slots_o));
+    const int box_rows = std::min(32, rows_o), box_slots = plain ? 1 : std::max(1, std::min(32 / box_rows, slots_o));   // plain: planes are split-K partials
     cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_slots};
     return tc_get_map(c, (const char*)base_ptr + m.base * es, es == 4 ? 2 : 3, 3, dims, str, box);
 }
@@ -851,7 +881,7 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
         if (!c->ws_buf[c->cur_ws]) PTTS_CUDA_CHECK(cudaMalloc(&c->ws_buf[c->cur_ws], c->ws_elems * sizeof(float)));
         kepi = Epi{}; kepi.out = c->ws_buf[c->cur_ws]; kepi.out_map.row_stride = N; p.ws_split_stride = (long long)R * N;
     } else { p.splits = 1; p.kb_per_split = num_kb; }
-    p.epi_class = kepi.mode == EPI_GENERIC ? epi_class_of(kepi) : 0;
+    p.epi_class = kepi.mode == EPI_GENERIC ? epi_class_of(kepi, c->tma_epilogue && R > 512 && tc_tma_epilogue_geometry_ok(kepi, R)) : 0;
     p.prefetch = g.tiles_m <= 4 ? 1 : 0;
     // instruction descriptor (kind::f16): D=f32, A/B = bf16|f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     p.idesc = (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -871,7 +901,7 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     p.stages = one_cta ? st1 : st2;
     const CUtensorMap *to = ta, *to2 = ta;                    // unused by the other epilogues: any valid map
     p.out_rps = 1 << 30;
-    if (cls > 0 && (EPI_CLASSES[cls] & EF_NO_TMA_STORE) == 0) {
+    if (cls > 0 && (EPI_CLASSES[cls] & EF_TMA) != 0) {
         const bool plain = kepi.rps >= R;
         p.out_rps = plain ? (1 << 30) : kepi.rps;
         if (kepi.out) to = tc_out_map(c, kepi.out, kepi.out_map, 4, R, N, kepi.rps, splits, p.ws_split_stride);
