@@ -227,10 +227,12 @@ __device__ __forceinline__ void epi_chunk(const Epi& e, const float* stg, const 
                 const float4 w4 = *reinterpret_cast<const float4*>(stg + r * EPI_STG_LD + cq);
                 const int2 ri = rowinfo[r];
                 float v[4] = {w4.x, w4.y, w4.z, w4.w};
-                if (has_bias) { v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w; }
-                if (has_cs) { v[0] *= cs4.x; v[1] *= cs4.y; v[2] *= cs4.z; v[3] *= cs4.w; }
-                if (has_rm) { v[0] *= rm4[i].x; v[1] *= rm4[i].y; v[2] *= rm4[i].z; v[3] *= rm4[i].w; }
-                if (has_res) { v[0] += rs4[i].x; v[1] += rs4[i].y; v[2] += rs4[i].z; v[3] += rs4[i].w; }
+                // explicit round-to-nearest adds / multiplies (no FMA contraction): the transposing and the TMA-store epilogue must round
+                // identically, a frame must not depend on which of them ran (synchronous step vs two-stream pipeline)
+                if (has_bias) { v[0] = __fadd_rn(v[0], bias4.x); v[1] = __fadd_rn(v[1], bias4.y); v[2] = __fadd_rn(v[2], bias4.z); v[3] = __fadd_rn(v[3], bias4.w); }
+                if (has_cs) { v[0] = __fmul_rn(v[0], cs4.x); v[1] = __fmul_rn(v[1], cs4.y); v[2] = __fmul_rn(v[2], cs4.z); v[3] = __fmul_rn(v[3], cs4.w); }
+                if (has_rm) { v[0] = __fmul_rn(v[0], rm4[i].x); v[1] = __fmul_rn(v[1], rm4[i].y); v[2] = __fmul_rn(v[2], rm4[i].z); v[3] = __fmul_rn(v[3], rm4[i].w); }
+                if (has_res) { v[0] = __fadd_rn(v[0], rs4[i].x); v[1] = __fadd_rn(v[1], rs4[i].y); v[2] = __fadd_rn(v[2], rs4[i].z); v[3] = __fadd_rn(v[3], rs4[i].w); }
                 if (has_out) *reinterpret_cast<float4*>(e.out + ((long long)ri.x * out_ss + (long long)ri.y * out_rs + e.out_map.base + ws_off) + col) = make_float4(v[0], v[1], v[2], v[3]);
                 if (o2_bf16 || o2_f16) {
                     if (act == ACT_GELU) {
@@ -280,15 +282,15 @@ __device__ __forceinline__ void epi_chunk_tma(const Epi& e, float (&v)[32], uint
     constexpr int act = (F & EF_GELU) ? ACT_GELU : (F & EF_SILU) ? ACT_SILU : (F & EF_ELU) ? ACT_ELU : ACT_NONE;
     if (e.bias) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j); v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w; }
+        for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j); v[4 * j] = __fadd_rn(v[4 * j], b.x); v[4 * j + 1] = __fadd_rn(v[4 * j + 1], b.y); v[4 * j + 2] = __fadd_rn(v[4 * j + 2], b.z); v[4 * j + 3] = __fadd_rn(v[4 * j + 3], b.w); }
     }
     if (has_cs) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.colscale + col0) + j); v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w; }
+        for (int j = 0; j < 8; j++) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.colscale + col0) + j); v[4 * j] = __fmul_rn(v[4 * j], b.x); v[4 * j + 1] = __fmul_rn(v[4 * j + 1], b.y); v[4 * j + 2] = __fmul_rn(v[4 * j + 2], b.z); v[4 * j + 3] = __fmul_rn(v[4 * j + 3], b.w); }
     }
     if (has_res && resid_row) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) { const float4 b = *(reinterpret_cast<const float4*>(resid_row + col0) + j); v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w; }
+        for (int j = 0; j < 8; j++) { const float4 b = *(reinterpret_cast<const float4*>(resid_row + col0) + j); v[4 * j] = __fadd_rn(v[4 * j], b.x); v[4 * j + 1] = __fadd_rn(v[4 * j + 1], b.y); v[4 * j + 2] = __fadd_rn(v[4 * j + 2], b.z); v[4 * j + 3] = __fadd_rn(v[4 * j + 3], b.w); }
     }
     const uint32_t s32 = smem_u32(stg);
     if (has_out) {
