@@ -7,6 +7,7 @@
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include "persistent.cuh"
 
 #include <cuda_profiler_api.h>
 #include <nvtx3/nvToolsExt.h>
@@ -590,11 +591,50 @@ struct b200_engine {
         seg_end(s_sea);
     }
 
+    // ---- batch 1-2: the FlowLM step + head as ONE cooperative kernel (persistent.cuh) instead of ~75 dependent launches ----
+    bool persistent_allowed = getenv("PTTS_B200_PERSISTENT") ? atoi(getenv("PTTS_B200_PERSISTENT")) != 0 : true;
+    bool use_persistent(int n) const {
+        return persistent_allowed && n <= PF_RMAX && !cfg.kv_f32 && cfg.gemm_path == 0 && !taps_on && !profiling && cfg.kv_capacity <= 8 * PF_MAX_KEYS;
+    }
+    void flow_persistent(int slot0, int n, bool injected, float* xbuf) {
+        PfParams p{};
+        const int sms = tc ? tc->num_sms : 148;
+        p.slot0 = slot0; p.R = n;
+        p.n_splits = std::max(std::max(1, sms / (n * N_HEADS)), (cfg.kv_capacity + PF_MAX_KEYS - 1) / PF_MAX_KEYS);
+        p.lat_in = lat_in_bf16; p.cur_len = cur_len; p.active = active; p.freq = freq_flow;
+        p.kc = (__nv_bfloat16*)kc; p.vc = (__nv_bfloat16*)vc; p.kv_slot_stride = kv_slot_stride; p.kv_layer_stride = kv_layer_stride;
+        p.pfx_slot = pfx_slot; p.pfx_len = pfx_len;
+        p.input_linear_t = input_linear_t; p.input_linear_b = input_linear.b;
+        for (int l = 0; l < N_LAYERS; l++) {
+            p.L[l].in_proj = {fl[l].in_proj.w, fl[l].in_proj.b}; p.L[l].out_proj = {fl[l].out_proj.w, fl[l].out_proj.b};
+            p.L[l].lin1 = {fl[l].lin1.w, fl[l].lin1.b}; p.L[l].lin2 = {fl[l].lin2.w, fl[l].lin2.b};
+            p.L[l].n1w = fl[l].n1w; p.L[l].n1b = fl[l].n1b; p.L[l].n2w = fl[l].n2w; p.L[l].n2b = fl[l].n2b;
+        }
+        p.onw = onw; p.onb = onb; p.w_eos = w_eos; p.b_eos = b_eos;
+        p.cond = {cond_embed.w, cond_embed.b}; p.ada = {ada_all.w, ada_all.b}; p.fin = {final_lin.w, final_lin.b}; p.ada_out = ada_all.out; p.t_combined = t_combined;
+        for (int r = 0; r < N_RES; r++) { p.rb[r].lnw = rb[r].lnw; p.rb[r].lnb = rb[r].lnb; p.rb[r].m0 = {rb[r].mlp0.w, rb[r].mlp0.b}; p.rb[r].m2 = {rb[r].mlp2.w, rb[r].mlp2.b}; }
+        p.fnw = fnw; p.fnb = fnb; p.input_proj_t = input_proj_t; p.input_proj_b = input_proj.b;
+        p.injected = injected ? noise_inj : nullptr; p.seed = d_seed; p.temp = temp; p.gen_step = gen_step; p.rng_id = rng_id;
+        p.h = h; p.q = q; p.ws_ml = af_ml; p.ws_acc = af_acc; p.mod = mod; p.xh = xh; p.noise_f32 = noise_f32; p.latent = latent; p.eos = eos;
+        p.ff_bf = ff_bf; p.sy_bf = sy_bf; p.h1_bf = h1_bf;
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(sms); lc.blockDim = dim3(PF_THREADS); lc.dynamicSmemBytes = PF_SMEM_BYTES; lc.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        PTTS_CUDA_CHECK(cudaLaunchKernelEx(&lc, flow_persistent_kernel, p));
+        launches++;
+        launch_k(false, step_front_kernel, dim3(n), dim3(M_DIM), (size_t)(0), stream, slot0, n, (const float*)eos, (const float*)latent, cur_len, gen_step, eos_step, (const int*)max_gen,
+                 (const int*)fae, active, lat_in_bf16, lat_f32, produced, eos_out, (const float*)emb_std, (const float*)emb_mean, (const __half*)wq, (const float*)wup, (const float*)bup, e_prev, xbuf);
+        launches++;
+    }
+
     // One generation step for slots [slot0, slot0+n) (reference _stream_sentence_step, src/pocket_tts.cpp:446-492).
     // FlowLM step + head + stop rule + Mimi front end (everything that consumes / produces the latent hand-off), cut into N_LAYERS + 1
     // segments: segment l < 6 ends with the attention kernel of layer l, segment 6 is the rest. seg < 0 enqueues all of them.
     static constexpr int N_SEG = N_LAYERS + 1;
     void flow_part(int slot0, int n, bool injected, float* xbuf, int seg = -1) {
+        if (seg < 0 && use_persistent(n)) { flow_persistent(slot0, n, injected, xbuf); return; }
         set_pdl(pdl_small || pdl_chain);
         const int s_flow = (seg < 0) ? seg_begin(1) : -1;
         for (int sg = 0; sg < N_SEG; sg++) {
@@ -714,7 +754,7 @@ struct b200_engine {
 
     // One generation step for slots [slot0, slot0+n).
     int immediate_below = getenv("PTTS_B200_IMMEDIATE_BELOW") ? atoi(getenv("PTTS_B200_IMMEDIATE_BELOW")) : 32;   // tuning hook
-    bool one_graph_per_stream(int n) const { return n >= 4 && n < immediate_below; }
+    bool one_graph_per_stream(int n) const { return (n >= 4 && n < immediate_below) || use_persistent(n); }
     bool last_step_piped = false;        // the last run_step left its Mimi decode (and PCM copy, for b200_submit frames) to the Mimi stream
     void run_step(int slot0, int n, bool injected, long long tag = -1) {
         last_step_piped = false;
@@ -1077,7 +1117,7 @@ int b200_finalize_weights(b200_engine* e) {
                             (const void*)gemv_small_kernel<__nv_bfloat16, 8>, (const void*)gemv_small_kernel<__half, 8>, (const void*)gemv_ln_kernel<D_MODEL>, (const void*)gemv_ln_kernel<D_FLOW>, (const void*)layernorm_kernel<D_MODEL>,
                             (const void*)layernorm_kernel<D_FLOW>, 
                             (const void*)splitk_reduce_kernel, (const void*)splitk_reduce_ln_kernel<1024>, (const void*)splitk_reduce_ln_kernel<512>,
-                            (const void*)attn_flow_split_kernel<__nv_bfloat16>, (const void*)attn_flow_split_kernel<float>, (const void*)attn_tile_kernel<2>, (const void*)attn_tile_kernel<1>, (const void*)attn_tile_kernel<0>, (const void*)attn_merge_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
+                            (const void*)attn_flow_split_kernel<__nv_bfloat16>, (const void*)attn_flow_split_kernel<float>, (const void*)attn_tile_kernel<2>, (const void*)attn_tile_kernel<1>, (const void*)attn_tile_kernel<0>, (const void*)attn_merge_kernel, (const void*)flow_persistent_kernel, (const void*)noise_inproj_kernel, (const void*)flow_in_kernel, (const void*)head_pre_kernel,
                             (const void*)step_front_kernel, (const void*)mimi_front_kernel, (const void*)attn_mimi_kernel, (const void*)attn_mimi_mma4_kernel,
                             (const void*)conv_n1_kernel, (const void*)shift_states_kernel};
         for (const void* k : ks) PTTS_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1085,6 +1125,7 @@ int b200_finalize_weights(b200_engine* e) {
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_mimi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM));
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_split_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AfCfg<__nv_bfloat16>::SMEM));
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_split_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AfCfg<float>::SMEM));
+    PTTS_CUDA_CHECK(cudaFuncSetAttribute(flow_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM_BYTES));
     e->actx.row_slot = e->row_slot; e->actx.row_pos = e->row_pos; e->actx.cs = e->cs;
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     e->finalized = true;
