@@ -592,6 +592,7 @@ struct b200_engine {
     }
 
     // ---- batch 1-2: the FlowLM step + head as ONE cooperative kernel (persistent.cuh) instead of ~75 dependent launches ----
+    unsigned int* pf_barrier = nullptr;
     bool persistent_allowed = getenv("PTTS_B200_PERSISTENT") ? atoi(getenv("PTTS_B200_PERSISTENT")) != 0 : true;
     bool use_persistent(int n) const {
         return persistent_allowed && n <= PF_RMAX && !cfg.kv_f32 && cfg.gemm_path == 0 && !taps_on && !profiling && cfg.kv_capacity <= 8 * PF_MAX_KEYS;
@@ -616,7 +617,7 @@ struct b200_engine {
         p.fnw = fnw; p.fnb = fnb; p.input_proj_t = input_proj_t; p.input_proj_b = input_proj.b;
         p.injected = injected ? noise_inj : nullptr; p.seed = d_seed; p.temp = temp; p.gen_step = gen_step; p.rng_id = rng_id;
         p.h = h; p.q = q; p.ws_ml = af_ml; p.ws_acc = af_acc; p.mod = mod; p.xh = xh; p.noise_f32 = noise_f32; p.latent = latent; p.eos = eos;
-        p.ff_bf = ff_bf; p.sy_bf = sy_bf; p.h1_bf = h1_bf;
+        p.ff_bf = ff_bf; p.sy_bf = sy_bf; p.h1_bf = h1_bf; p.barrier = pf_barrier;
         cudaLaunchConfig_t lc{};
         lc.gridDim = dim3(sms); lc.blockDim = dim3(PF_THREADS); lc.dynamicSmemBytes = PF_SMEM_BYTES; lc.stream = stream;
         cudaLaunchAttribute at[1];
@@ -1079,6 +1080,7 @@ int b200_finalize_weights(b200_engine* e) {
     e->pfx_slot = e->dalloc<int>(TS); e->pfx_len = e->dalloc<int>(TS);
     e->dec_items_cap = ((S + AT_ROWS - 1) / AT_ROWS + e->cfg.max_voices + 1) * AF_PFX_SPLITS + 8;
     e->dec_items = e->dalloc<AtItem>(e->dec_items_cap); e->dec_meta = e->dalloc<int>(4); e->dec_rows = e->dalloc<int>(S);
+    e->pf_barrier = e->dalloc<unsigned int>(4);
     e->tap_up = e->dalloc<float>((size_t)S * M_T * M_DIM);
     e->tap_h = e->dalloc<float>((size_t)N_LAYERS * S * D_MODEL); e->tap_att = e->dalloc<__nv_bfloat16>((size_t)N_LAYERS * S * D_MODEL);
     e->row_slot = e->dalloc<int>(MR); e->row_pos = e->dalloc<int>(MR); e->tok = e->dalloc<int>(MR); e->cs = e->dalloc<float2>((size_t)MR * 32);

@@ -13,7 +13,6 @@
 // rounded to bf16 before every product, fp32 accumulation, ggml f16-table GELU). Reference: models/flow_lm.h:84-147,
 // modules/transformer.h:55-199,253-278, modules/mlp.h:233-251.
 #pragma once
-#include <cooperative_groups.h>
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
@@ -45,33 +44,39 @@ struct PfParams {
     // global scratch
     float *h, *q, *ws_ml, *ws_acc, *mod, *xh, *noise_f32, *latent, *eos;
     __nv_bfloat16 *ff_bf, *sy_bf, *h1_bf;
+    unsigned int* barrier;   // [0] arrival counter of PfBarrier (never reset), [1] its value when the current launch started (written by the previous launch)
 };
 
-// y[n0], y[n0+1] for every row: dot products of two weight rows with the rows of xs (smem, already rounded to bf16), spread over the grid
-template <int K, typename F>
-__device__ __forceinline__ void pf_gemv(const __nv_bfloat16* __restrict__ W, int N, const float* xs /*[PF_RMAX][K]*/, int R, F&& epi) {
+// y[n0 .. n0+NC) for every row: dot products of NC weight rows with the rows of xs (smem, already rounded to bf16), spread over the warps of
+// the whole grid. NC = 2 columns per warp while that keeps every warp busy; matrices with fewer column pairs than warps (N = 1024, 512, 32)
+// use one column per warp, which halves the weight bytes on the critical path of the phase (the slowest warp sets the barrier time).
+template <int K, int NC, typename F>
+__device__ __forceinline__ void pf_gemv_nc(const __nv_bfloat16* __restrict__ W, int N, const float* xs /*[PF_RMAX][K]*/, int R, F&& epi) {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * PF_THREADS + threadIdx.x) >> 5, nw = (gridDim.x * PF_THREADS) >> 5;
-    for (int pair = gw; pair < N / 2; pair += nw) {
-        const int n0 = 2 * pair;
+    for (int unit = gw; unit < N / NC; unit += nw) {
+        const int n0 = NC * unit;
         const __nv_bfloat16* w0 = W + (long long)n0 * K;
-        const __nv_bfloat16* w1 = w0 + K;
-        float acc[PF_RMAX][2];
+        float acc[PF_RMAX][NC];
 #pragma unroll
-        for (int r = 0; r < PF_RMAX; r++) acc[r][0] = acc[r][1] = 0.f;
+        for (int r = 0; r < PF_RMAX; r++)
+#pragma unroll
+            for (int c = 0; c < NC; c++) acc[r][c] = 0.f;
 #pragma unroll 4
         for (int k = lane * 8; k < K; k += 256) {
-            const uint4 wv0 = __ldg(reinterpret_cast<const uint4*>(w0 + k)), wv1 = __ldg(reinterpret_cast<const uint4*>(w1 + k));
-            const uint32_t a0[4] = {wv0.x, wv0.y, wv0.z, wv0.w}, a1[4] = {wv1.x, wv1.y, wv1.z, wv1.w};
+            uint4 wv[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++) wv[c] = __ldg(reinterpret_cast<const uint4*>(w0 + (long long)c * K + k));
 #pragma unroll
             for (int r = 0; r < PF_RMAX; r++) {
                 if (r < R) {
                     const float4 xa = *reinterpret_cast<const float4*>(xs + r * K + k), xb = *reinterpret_cast<const float4*>(xs + r * K + k + 4);
                     const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        acc[r][0] = fmaf(x[2 * j], __uint_as_float(a0[j] << 16), acc[r][0]); acc[r][0] = fmaf(x[2 * j + 1], __uint_as_float(a0[j] & 0xffff0000u), acc[r][0]);
-                        acc[r][1] = fmaf(x[2 * j], __uint_as_float(a1[j] << 16), acc[r][1]); acc[r][1] = fmaf(x[2 * j + 1], __uint_as_float(a1[j] & 0xffff0000u), acc[r][1]);
+                    for (int c = 0; c < NC; c++) {
+                        const uint32_t a[4] = {wv[c].x, wv[c].y, wv[c].z, wv[c].w};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { acc[r][c] = fmaf(x[2 * j], __uint_as_float(a[j] << 16), acc[r][c]); acc[r][c] = fmaf(x[2 * j + 1], __uint_as_float(a[j] & 0xffff0000u), acc[r][c]); }
                     }
                 }
             }
@@ -79,11 +84,20 @@ __device__ __forceinline__ void pf_gemv(const __nv_bfloat16* __restrict__ W, int
 #pragma unroll
         for (int r = 0; r < PF_RMAX; r++) {
             if (r < R) {
-                const float v0 = warp_sum(acc[r][0]), v1 = warp_sum(acc[r][1]);
-                if (lane == 0) epi(r, n0, v0, v1);
+                float v[2] = {0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < NC; c++) v[c] = warp_sum(acc[r][c]);
+                if (lane == 0) epi(r, n0, v[0], v[1], NC);
             }
         }
     }
+}
+// epi(r, n0, v0, v1) is called once per column PAIR (RoPE rotates pairs): with one column per warp the pair is completed by a shuffle
+template <int K, typename F>
+__device__ __forceinline__ void pf_gemv(const __nv_bfloat16* __restrict__ W, int N, const float* xs, int R, F&& epi, bool pairs_needed = false) {
+    const int nw = (gridDim.x * PF_THREADS) >> 5;
+    if (N / 2 >= nw || pairs_needed) pf_gemv_nc<K, 2>(W, N, xs, R, [&](int r, int n0, float v0, float v1, int) { epi(r, n0, v0, v1, 2); });
+    else pf_gemv_nc<K, 1>(W, N, xs, R, [&](int r, int n0, float v0, float, int) { epi(r, n0, v0, 0.f, 1); });
 }
 
 // L2 prefetch of the weight rows this warp will read in the NEXT phase (issued before the grid barrier: hides the cold-DRAM latency)
@@ -137,9 +151,26 @@ __device__ __forceinline__ void pf_layernorm(const float* __restrict__ x, long l
     }
 }
 
-__global__ void __launch_bounds__(PF_THREADS, 1) flow_persistent_kernel(const PfParams p) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
+// Grid-wide barrier for a cooperative launch (all CTAs resident): one arrival counter, monotonically increasing; thread 0 of every CTA
+// arrives with a release fence and spins on an acquire load until the phase's target is reached. ~1 us on 148 CTAs, about a third of
+// cooperative_groups' grid.sync() (which also has to work for multi-device grids).
+struct PfBarrier {
+    unsigned int* counter; unsigned int target;
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            target += gridDim.x;
+            __threadfence();
+            atomicAdd(counter, 1u);
+            unsigned int v;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int)(v - target) < 0);
+        }
+        __syncthreads();
+    }
+};
+
+__global__ void __launch_bounds__(PF_THREADS, 2) flow_persistent_kernel(const PfParams p) {
+    PfBarrier grid; grid.counter = p.barrier; grid.target = p.barrier[1];          // the count all earlier launches left behind (stable: written after their last barrier)
     extern __shared__ __align__(16) float pf_smem[];
     float* xs = pf_smem;                                   // [PF_RMAX][4096] GEMV input rows
     float* sc = xs + PF_RMAX * D_FF;                       // [PF_MAX_KEYS] attention scores of one task | scratch
@@ -182,7 +213,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) flow_persistent_kernel(const Pf
         {
             Epi e; e.mode = EPI_FLOW_QKV; e.row_slot = rs_slot; e.row_pos = rs_pos; e.cs = cs; e.kv_f32 = 0; e.kv_slot_stride = p.kv_slot_stride;
             e.q_out_f32 = p.q; e.kcache = kc; e.vcache = vc; e.bias = L.in_proj.b;
-            pf_gemv<D_MODEL>(L.in_proj.w, 3 * D_MODEL, xs, R, [&](int r, int n0, float v0, float v1) { const float v[2] = {v0, v1}; epi_apply<2>(e, r, n0, v, 3 * D_MODEL); });
+            pf_gemv<D_MODEL>(L.in_proj.w, 3 * D_MODEL, xs, R, [&](int r, int n0, float v0, float v1, int) { const float v[2] = {v0, v1}; epi_apply<2>(e, r, n0, v, 3 * D_MODEL); }, true);
         }
         pf_prefetch(L.out_proj.w, D_MODEL, D_MODEL);
         grid.sync();
@@ -274,28 +305,29 @@ __global__ void __launch_bounds__(PF_THREADS, 1) flow_persistent_kernel(const Pf
             xs[r * D_MODEL + c] = __bfloat162float(__float2bfloat16_rn(o));
         }
         __syncthreads();
-        pf_gemv<D_MODEL>(L.out_proj.w, D_MODEL, xs, R, [&](int r, int n0, float v0, float v1) {
+        pf_gemv<D_MODEL>(L.out_proj.w, D_MODEL, xs, R, [&](int r, int n0, float v0, float v1, int nc) {
             float* hp = p.h + (long long)r * D_MODEL + n0;
-            if (L.out_proj.b) { v0 += L.out_proj.b[n0]; v1 += L.out_proj.b[n0 + 1]; }
-            hp[0] += v0; hp[1] += v1;
+            hp[0] += v0 + (L.out_proj.b ? L.out_proj.b[n0] : 0.f);
+            if (nc == 2) hp[1] += v1 + (L.out_proj.b ? L.out_proj.b[n0 + 1] : 0.f);
         });
         pf_prefetch(L.lin2.w, D_MODEL, D_FF);
         grid.sync();
         // ---- P4: norm2 + linear1 + GELU (reference transformer.h:266-272) ----
         pf_layernorm<D_MODEL>(p.h, D_MODEL, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, xs, red);
-        pf_gemv<D_MODEL>(L.lin1.w, D_FF, xs, R, [&](int r, int n0, float v0, float v1) {
-            if (L.lin1.b) { v0 += L.lin1.b[n0]; v1 += L.lin1.b[n0 + 1]; }
-            *reinterpret_cast<__nv_bfloat162*>(p.ff_bf + (long long)r * D_FF + n0) = __floats2bfloat162_rn(gelu_ggml(v0), gelu_ggml(v1));
+        pf_gemv<D_MODEL>(L.lin1.w, D_FF, xs, R, [&](int r, int n0, float v0, float v1, int nc) {
+            __nv_bfloat16* fp = p.ff_bf + (long long)r * D_FF + n0;
+            fp[0] = __float2bfloat16_rn(gelu_ggml(v0 + (L.lin1.b ? L.lin1.b[n0] : 0.f)));
+            if (nc == 2) fp[1] = __float2bfloat16_rn(gelu_ggml(v1 + (L.lin1.b ? L.lin1.b[n0 + 1] : 0.f)));
         });
         if (l + 1 < N_LAYERS) pf_prefetch(p.L[l + 1].in_proj.w, 3 * D_MODEL, D_MODEL);
         grid.sync();
         // ---- P5: linear2 + residual ----
         for (int i = tid; i < R * D_FF; i += PF_THREADS) xs[i] = __bfloat162float(p.ff_bf[i]);
         __syncthreads();
-        pf_gemv<D_FF>(L.lin2.w, D_MODEL, xs, R, [&](int r, int n0, float v0, float v1) {
+        pf_gemv<D_FF>(L.lin2.w, D_MODEL, xs, R, [&](int r, int n0, float v0, float v1, int nc) {
             float* hp = p.h + (long long)r * D_MODEL + n0;
-            if (L.lin2.b) { v0 += L.lin2.b[n0]; v1 += L.lin2.b[n0 + 1]; }
-            hp[0] += v0; hp[1] += v1;
+            hp[0] += v0 + (L.lin2.b ? L.lin2.b[n0] : 0.f);
+            if (nc == 2) hp[1] += v1 + (L.lin2.b ? L.lin2.b[n0 + 1] : 0.f);
         });
         if (l + 1 == N_LAYERS) pf_prefetch(p.cond.w, D_FLOW, D_MODEL);
         grid.sync();
@@ -344,18 +376,20 @@ __global__ void __launch_bounds__(PF_THREADS, 1) flow_persistent_kernel(const Pf
             p.xh[(long long)r * D_FLOW + c] = a + (p.input_proj_b ? p.input_proj_b[c] : 0.f);
         }
     }
-    pf_gemv<D_MODEL>(p.cond.w, D_FLOW, xs, R, [&](int r, int n0, float v0, float v1) {
-        v0 += (p.cond.b ? p.cond.b[n0] : 0.f) + p.t_combined[n0]; v1 += (p.cond.b ? p.cond.b[n0 + 1] : 0.f) + p.t_combined[n0 + 1];
-        *reinterpret_cast<__nv_bfloat162*>(p.sy_bf + (long long)r * D_FLOW + n0) = __floats2bfloat162_rn(silu_f(v0), silu_f(v1));
+    pf_gemv<D_MODEL>(p.cond.w, D_FLOW, xs, R, [&](int r, int n0, float v0, float v1, int nc) {
+        __nv_bfloat16* sp = p.sy_bf + (long long)r * D_FLOW + n0;
+        sp[0] = __float2bfloat16_rn(silu_f(v0 + (p.cond.b ? p.cond.b[n0] : 0.f) + p.t_combined[n0]));
+        if (nc == 2) sp[1] = __float2bfloat16_rn(silu_f(v1 + (p.cond.b ? p.cond.b[n0 + 1] : 0.f) + p.t_combined[n0 + 1]));
     });
     pf_prefetch(p.ada.w, p.ada_out, D_FLOW);
     grid.sync();
     // ---- H2: the seven adaLN projections of silu(y) ----
     for (int i = tid; i < R * D_FLOW; i += PF_THREADS) xs[i] = __bfloat162float(p.sy_bf[i]);
     __syncthreads();
-    pf_gemv<D_FLOW>(p.ada.w, p.ada_out, xs, R, [&](int r, int n0, float v0, float v1) {
+    pf_gemv<D_FLOW>(p.ada.w, p.ada_out, xs, R, [&](int r, int n0, float v0, float v1, int nc) {
         float* mp = p.mod + (long long)r * p.ada_out + n0;
-        mp[0] = v0 + (p.ada.b ? p.ada.b[n0] : 0.f); mp[1] = v1 + (p.ada.b ? p.ada.b[n0 + 1] : 0.f);
+        mp[0] = v0 + (p.ada.b ? p.ada.b[n0] : 0.f);
+        if (nc == 2) mp[1] = v1 + (p.ada.b ? p.ada.b[n0 + 1] : 0.f);
     });
     pf_prefetch(p.rb[0].m0.w, D_FLOW, D_FLOW);
     grid.sync();
@@ -363,19 +397,20 @@ __global__ void __launch_bounds__(PF_THREADS, 1) flow_persistent_kernel(const Pf
     for (int b = 0; b < N_RES; b++) {
         const float* m = p.mod + b * 3 * D_FLOW;
         pf_layernorm<D_FLOW>(p.xh, D_FLOW, R, 1e-6f, p.rb[b].lnw, p.rb[b].lnb, m, m + D_FLOW, p.ada_out, xs, red);
-        pf_gemv<D_FLOW>(p.rb[b].m0.w, D_FLOW, xs, R, [&](int r, int n0, float v0, float v1) {
-            if (p.rb[b].m0.b) { v0 += p.rb[b].m0.b[n0]; v1 += p.rb[b].m0.b[n0 + 1]; }
-            *reinterpret_cast<__nv_bfloat162*>(p.h1_bf + (long long)r * D_FLOW + n0) = __floats2bfloat162_rn(silu_f(v0), silu_f(v1));
+        pf_gemv<D_FLOW>(p.rb[b].m0.w, D_FLOW, xs, R, [&](int r, int n0, float v0, float v1, int nc) {
+            __nv_bfloat16* hp = p.h1_bf + (long long)r * D_FLOW + n0;
+            hp[0] = __float2bfloat16_rn(silu_f(v0 + (p.rb[b].m0.b ? p.rb[b].m0.b[n0] : 0.f)));
+            if (nc == 2) hp[1] = __float2bfloat16_rn(silu_f(v1 + (p.rb[b].m0.b ? p.rb[b].m0.b[n0 + 1] : 0.f)));
         });
         pf_prefetch(p.rb[b].m2.w, D_FLOW, D_FLOW);
         grid.sync();
         for (int i = tid; i < R * D_FLOW; i += PF_THREADS) xs[i] = __bfloat162float(p.h1_bf[i]);
         __syncthreads();
-        pf_gemv<D_FLOW>(p.rb[b].m2.w, D_FLOW, xs, R, [&](int r, int n0, float v0, float v1) {
-            if (p.rb[b].m2.b) { v0 += p.rb[b].m2.b[n0]; v1 += p.rb[b].m2.b[n0 + 1]; }
+        pf_gemv<D_FLOW>(p.rb[b].m2.w, D_FLOW, xs, R, [&](int r, int n0, float v0, float v1, int nc) {
             const float* g = m + 2 * D_FLOW + (long long)r * p.ada_out;
             float* xp = p.xh + (long long)r * D_FLOW + n0;
-            xp[0] += v0 * g[n0]; xp[1] += v1 * g[n0 + 1];
+            xp[0] += (v0 + (p.rb[b].m2.b ? p.rb[b].m2.b[n0] : 0.f)) * g[n0];
+            if (nc == 2) xp[1] += (v1 + (p.rb[b].m2.b ? p.rb[b].m2.b[n0 + 1] : 0.f)) * g[n0 + 1];
         });
         if (b + 1 < N_RES) pf_prefetch(p.rb[b + 1].m0.w, D_FLOW, D_FLOW);
         grid.sync();
@@ -384,12 +419,14 @@ __global__ void __launch_bounds__(PF_THREADS, 1) flow_persistent_kernel(const Pf
     {
         const float* m = p.mod + N_RES * 3 * D_FLOW;
         pf_layernorm<D_FLOW>(p.xh, D_FLOW, R, 1e-6f, p.fnw, p.fnb, m, m + D_FLOW, p.ada_out, xs, red);
-        pf_gemv<D_FLOW>(p.fin.w, LDIM, xs, R, [&](int r, int n0, float v0, float v1) {
+        pf_gemv<D_FLOW>(p.fin.w, LDIM, xs, R, [&](int r, int n0, float v0, float v1, int nc) {
             float* lp = p.latent + (long long)r * LDIM + n0;
             lp[0] = v0 + (p.fin.b ? p.fin.b[n0] : 0.f) + p.noise_f32[r * LDIM + n0];
-            lp[1] = v1 + (p.fin.b ? p.fin.b[n0 + 1] : 0.f) + p.noise_f32[r * LDIM + n0 + 1];
+            if (nc == 2) lp[1] = v1 + (p.fin.b ? p.fin.b[n0 + 1] : 0.f) + p.noise_f32[r * LDIM + n0 + 1];
         });
     }
+    grid.sync();                                               // nobody is still waiting on an earlier target when the base moves
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.barrier[1] = grid.target;
 }
 
 constexpr size_t PF_SMEM_BYTES = (size_t)(PF_RMAX * D_FF + PF_MAX_KEYS + 16) * 4 + PF_RMAX * 32 * 8 + PF_RMAX * 2 * 4 + PF_RMAX * 64 * 4;
