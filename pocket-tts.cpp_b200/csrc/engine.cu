@@ -126,7 +126,7 @@ struct b200_engine {
     int dec_key_slot0 = -1, dec_key_n = -1; unsigned long long dec_key_version = 0; int dec_grid_items = 0;
     int tile_prec = getenv("PTTS_B200_TILE_PREC") ? atoi(getenv("PTTS_B200_TILE_PREC")) : 1;   // operand precision of the decode-side tile kernel (see attn_tile_kernel): q as
     // hi + lo (the scores go through exp), plain bf16 probabilities; measured on the bench context 2 -> 1 -> 0: 1.084 / 1.067 / 1.054 ms per step,
-    // latent max-abs 0.020 / 0.018 / 0.020 and SNR 44.9 / 46.4 / 45.4 dB against the oracle (no measurable parity difference)
+    // latent max-abs 0.020 / 0.018 / 0.020 and SNR 44.9 / 46.4 / 45.4 dB against the CPU restatement (no measurable parity difference)
     int tile_min_rows = getenv("PTTS_B200_TILE_MIN_ROWS") ? atoi(getenv("PTTS_B200_TILE_MIN_ROWS")) : 4;   // below: the streaming kernel reads the prefix itself
     // attention context of the forward being enqueued (decode: the fixed scratch arrays; prefill: this call's staging)
     struct AttnCtx { const int* row_slot = nullptr; const int* row_pos = nullptr; const float2* cs = nullptr;
