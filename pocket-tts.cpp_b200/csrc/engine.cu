@@ -8,6 +8,7 @@
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "persistent.cuh"
+#include "head_fused.cuh"
 
 #include <cuda_profiler_api.h>
 #include <nvtx3/nvToolsExt.h>
@@ -465,6 +466,9 @@ struct b200_engine {
         for (int l = 0; l < N_LAYERS; l++) { flow_attn_part(l, R); flow_chain_part(l, R); }
     }
 
+    bool fused_head_allowed = getenv("PTTS_B200_FUSED_HEAD") ? atoi(getenv("PTTS_B200_FUSED_HEAD")) != 0 : true;   // tuning hook
+    int fused_head_min_rows = getenv("PTTS_B200_FUSED_HEAD_MIN") ? atoi(getenv("PTTS_B200_FUSED_HEAD_MIN")) : 3;
+    bool use_fused_head(int R) const { return fused_head_allowed && cfg.gemm_path == 0 && !taps_on && R >= fused_head_min_rows; }
     // out_norm + EOS + 1-step LSD head over R rows of `h` (reference models/flow_lm.h:114-142, modules/mlp.h:233-251).
     void flow_head(int R) {
         const int BIG = 1 << 30;
@@ -475,6 +479,16 @@ struct b200_engine {
         // all seven adaLN projections of silu(y) in one GEMM: [6 x (shift|scale|gate)] + [shift|scale]
         Epi em; em.out = mod; em.out_map = rows(ada_all.out);
         lin(sy_bf, ada_all, R, em);
+        if (use_fused_head(R)) {
+            // six residual blocks + final layer in one cluster kernel (head_fused.cuh): activations stay in (distributed) shared memory
+            HfParams hp{};
+            hp.R = R; hp.xh = xh; hp.mod = mod; hp.mod_ld = ada_all.out;
+            for (int r = 0; r < N_RES; r++) hp.rb[r] = {rb[r].lnw, rb[r].lnb, rb[r].mlp0.w, rb[r].mlp0.b, rb[r].mlp2.w, rb[r].mlp2.b};
+            hp.fnw = fnw; hp.fnb = fnb; hp.wf = final_lin.w; hp.bf = final_lin.b; hp.noise = noise_f32; hp.latent = latent;
+            launch_k(pdl_active, head_res_cluster_kernel, dim3((R + HF_ROWS - 1) / HF_ROWS * HF_CLUSTER), dim3(HF_THREADS), HF_SMEM_BYTES, stream, hp);
+            launches += 2;                                   // + head_pre_kernel
+            return;
+        }
         for (int r = 0; r < N_RES; r++) {
             const float* m = mod + r * 3 * D_FLOW;
             Epi e0; e0.out2 = h1_bf; e0.out2_map = rows(D_FLOW); e0.out2_type = OUT2_BF16; e0.act = ACT_SILU;
@@ -1128,6 +1142,7 @@ int b200_finalize_weights(b200_engine* e) {
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_split_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AfCfg<__nv_bfloat16>::SMEM));
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_split_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AfCfg<float>::SMEM));
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(flow_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM_BYTES));
+    PTTS_CUDA_CHECK(cudaFuncSetAttribute(head_res_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HF_SMEM_BYTES));
     e->actx.row_slot = e->row_slot; e->actx.row_pos = e->row_pos; e->actx.cs = e->cs;
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     e->finalized = true;
