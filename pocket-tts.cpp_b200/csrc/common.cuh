@@ -77,7 +77,12 @@ __device__ __forceinline__ float gelu_ggml(float x) {
     return __half2float(__float2half_rn(fmaf(hx, tanh_fast(u), hx)));
 }
 __device__ __forceinline__ float silu_f(float x) { const float hx = 0.5f * x; return fmaf(hx, tanh_fast(hx), hx); }   // x * sigmoid(x)
-__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
+// ELU through ex2.approx.ftz: __expf without -ftz wraps the same MUFU op in denormal scaling (2 FMUL + 2 FSETP + selects per call); for x <= 0
+// both give exp(x) - 1 to ~2^-22, and a flushed denormal changes nothing once 1 is subtracted.
+__device__ __forceinline__ float elu_f(float x) {
+    float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return x > 0.f ? x : e - 1.0f;
+}
 __device__ __forceinline__ float apply_act(float v, int act) {
     switch (act) {
         case ACT_GELU: return gelu_ggml(v);

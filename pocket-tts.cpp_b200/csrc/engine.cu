@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "persistent.cuh"
 #include "head_fused.cuh"
+#include "seanet_tail.cuh"
 
 #include <cuda_profiler_api.h>
 #include <nvtx3/nvToolsExt.h>
@@ -144,6 +145,12 @@ struct b200_engine {
     __half *buf0 = nullptr, *buf2 = nullptr, *buf3a = nullptr, *buf3b = nullptr, *buf5 = nullptr, *buf6a = nullptr, *buf6b = nullptr,
            *buf8 = nullptr, *buf9a = nullptr, *buf9b = nullptr, *buf11 = nullptr;
     float *y3 = nullptr, *y6 = nullptr, *y9 = nullptr, *pcm = nullptr;
+    float* dtail = nullptr;   // [slot][2 + 1920][4] per-row tap products of the output conv (seanet_tail.cuh), two carried rows in front
+    bool fused_tail_allowed = getenv("PTTS_B200_FUSED_TAIL") ? atoi(getenv("PTTS_B200_FUSED_TAIL")) != 0 : true;   // tuning hook
+    // The tap "seanet.res9" reads the f16 a3 rows, which only the unfused launches produce. (Switching taps in the middle of a sentence leaves a
+    // stale two-row output-conv state for one frame: the two paths carry it in different buffers. Debug only.)
+    int tail_ipw = getenv("PTTS_B200_TAIL_IPW") ? atoi(getenv("PTTS_B200_TAIL_IPW")) : 0;   // tuning hook: work items per warp of seanet_tail_kernel (0 = persistent)
+    bool use_fused_tail() const { return fused_tail_allowed && cfg.gemm_path == 0 && !taps_on; }
     int C2 = 512, C5 = 256, C8 = 128;
     ShiftAll shifts{};
     // pinned staging
@@ -591,12 +598,26 @@ struct b200_engine {
         if (on(5)) { Epi e; e.rps = T2; e.bias = t8.b; e.out = y9 + slot0 * 1920LL * 64; e.out_map = smap(1920LL * 64, 256, 0);
           e.act = ACT_ELU; e.out2 = buf9a + slot0 * s9a; e.out2_map = smap(s9a, 256, 2 * 64); e.out2_type = OUT2_F16;
           gemm<__half>(buf8 + slot0 * s8, smap(s8, C8, 0), T2, t8.w, t8.wk, n * T2, t8.N, t8.K, e); }
-        if (on(5)) { Epi e; e.rps = T3; e.bias = r9a.b; e.act = ACT_ELU; e.out2 = buf9b + slot0 * s9b; e.out2_map = smap(s9b, 64, 0); e.out2_type = OUT2_F16;
+        if (on(5) && use_fused_tail()) {
+            // resnet block 9 + output conv in one streaming kernel (seanet_tail.cuh): no padded intermediate, no a3 tensor
+            StParams sp{};
+            sp.a1 = buf9a; sp.a1_slot_stride = s9a; sp.y = y9; sp.y_slot_stride = 1920LL * 64; sp.d = dtail; sp.d_slot_stride = 1922LL * ST_DROW;
+            sp.w3 = r9a.w; sp.b3 = r9a.b; sp.w1 = r9b.w; sp.w1_ld = r9b.K; sp.b1 = r9b.b; sp.w11 = c11.w; sp.slot0 = slot0; sp.n_slots = n; sp.T = T3;
+            const long long items = (long long)n * (T3 / ST_ROWS);
+            sp.ipw = tail_ipw;
+            const int sms = tc ? tc->num_sms : 148;
+            const int grid = tail_ipw > 0 ? (int)((items + ST_WARPS * tail_ipw - 1) / (ST_WARPS * tail_ipw)) : (int)std::min<long long>(2LL * sms, (items + ST_WARPS - 1) / ST_WARPS);
+            launch_k(pdl_active, seanet_tail_kernel, dim3(grid), dim3(ST_THREADS), ST_SMEM_BYTES, stream, sp);
+            launch_k(pdl_active, pcm_combine_kernel, dim3((unsigned)(((long long)n * T3 + 255) / 256)), dim3(256), (size_t)0, stream, (const float*)dtail, 1922LL * ST_DROW, slot0, n, T3,
+                     (const float*)c11.b, pcm);
+            launch_k(pdl_active, shift_states_kernel, dim3(n, shifts.n), dim3(128), (size_t)(0), stream, shifts, slot0, mimi_off);
+            launches += 3;
+        } else if (on(5)) {
+        { Epi e; e.rps = T3; e.bias = r9a.b; e.act = ACT_ELU; e.out2 = buf9b + slot0 * s9b; e.out2_map = smap(s9b, 64, 0); e.out2_type = OUT2_F16;
           gemm<__half>(buf9a + slot0 * s9a, smap(s9a, 64, 0), T3, r9a.w, r9a.wk, n * T3, r9a.N, r9a.K, e); }
-        if (on(5)) { Epi e; e.rps = T3; e.bias = r9b.b; e.resid = y9 + slot0 * 1920LL * 64; e.resid_map = smap(1920LL * 64, 64, 0);
+        { Epi e; e.rps = T3; e.bias = r9b.b; e.resid = y9 + slot0 * 1920LL * 64; e.resid_map = smap(1920LL * 64, 64, 0);
           e.act = ACT_ELU; e.out2 = buf11 + slot0 * s11; e.out2_map = smap(s11, 64, 2 * 64); e.out2_type = OUT2_F16;
           gemm<__half>(buf9b + slot0 * s9b, smap(s9b, 64, 0), T3, r9b.w, r9b.wk, n * T3, r9b.N, r9b.K, e); }
-        if (on(5)) {
             const int Rr = n * T3;
             launch_k(pdl_active, conv_n1_kernel, dim3((Rr * 4 + 255) / 256), dim3(256), (size_t)(0), stream, buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm + (long long)slot0 * FRAME);
             launch_k(pdl_active, shift_states_kernel, dim3(n, shifts.n), dim3(128), (size_t)(0), stream, shifts, slot0, mimi_off);
@@ -1117,7 +1138,7 @@ int b200_finalize_weights(b200_engine* e) {
     e->buf11 = e->dalloc<__half>((size_t)S * 1922 * 64);
     e->y3 = e->dalloc<float>((size_t)S * 96 * 256); e->y6 = e->dalloc<float>((size_t)S * 480 * 128); e->y9 = e->dalloc<float>((size_t)S * 1920 * 64);
     e->pcm = e->dalloc<float>((size_t)S * FRAME);
-    e->shifts.n = 8;
+    e->shifts.n = 9;
     e->shifts.d[0] = {e->buf0, 22LL * 512, 6, 16, 512};
     e->shifts.d[1] = {e->buf2, 17LL * e->C2, 1, 16, e->C2};
     e->shifts.d[2] = {e->buf3a, 98LL * 256, 2, 96, 256};
@@ -1126,6 +1147,8 @@ int b200_finalize_weights(b200_engine* e) {
     e->shifts.d[5] = {e->buf8, 481LL * e->C8, 1, 480, e->C8};
     e->shifts.d[6] = {e->buf9a, 1922LL * 64, 2, 1920, 64};
     e->shifts.d[7] = {e->buf11, 1922LL * 64, 2, 1920, 64};
+    e->dtail = e->dalloc<float>((size_t)S * 1922 * ST_DROW);
+    e->shifts.d[8] = {(__half*)e->dtail, 1922LL * ST_DROW * 2, 2, 1920, ST_DROW * 2};   // f32 rows seen as 16-bit pairs: plain row copies / zeroing
     // Keep the shared-memory carve-out identical for every kernel of the step: mixed carve-outs force an SM reconfiguration
     // between consecutive launches, which shows up as microseconds of idle time on the ~100 small kernels of a frame.
     {
@@ -1143,6 +1166,7 @@ int b200_finalize_weights(b200_engine* e) {
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(attn_flow_split_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AfCfg<float>::SMEM));
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(flow_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM_BYTES));
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(head_res_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HF_SMEM_BYTES));
+    PTTS_CUDA_CHECK(cudaFuncSetAttribute(seanet_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES));
     e->actx.row_slot = e->row_slot; e->actx.row_pos = e->row_pos; e->actx.cs = e->cs;
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     e->finalized = true;

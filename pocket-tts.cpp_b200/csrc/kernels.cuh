@@ -1118,13 +1118,13 @@ __global__ void __launch_bounds__(512) step_front_kernel(int slot0, int n, const
 // rows first (reference modules/conv.h:60-76 keeps the last K-stride inputs; the transposed convs keep the last
 // input row instead of the reference's partial output). Copies the last S rows to the front.
 struct ShiftDesc { __half* buf; long long slot_stride; int S, T, C; };
-struct ShiftAll { ShiftDesc d[8]; int n; };
+struct ShiftAll { ShiftDesc d[9]; int n; };
 __global__ void shift_states_kernel(ShiftAll sa, int slot0, int* __restrict__ mimi_off) {
     pdl_prologue();
     const ShiftDesc d = sa.d[blockIdx.y];
     const int slot = slot0 + blockIdx.x;
     __half* base = d.buf + (long long)slot * d.slot_stride;
-    const int n8 = d.S * d.C / 8;                               // 16-byte pieces (every C here is a multiple of 64)
+    const int n8 = d.S * d.C / 8;                               // 16-byte pieces (every C here is a multiple of 8)
     // source rows [T, T+S) and destination rows [0, S) never overlap because T >= S for every conv here.
     const uint4* src = reinterpret_cast<const uint4*>(base + (long long)d.T * d.C);
     uint4* dst = reinterpret_cast<uint4*>(base);
