@@ -150,6 +150,7 @@ struct b200_engine {
     // The tap "seanet.res9" reads the f16 a3 rows, which only the unfused launches produce. (Switching taps in the middle of a sentence leaves a
     // stale two-row output-conv state for one frame: the two paths carry it in different buffers. Debug only.)
     int tail_ipw = getenv("PTTS_B200_TAIL_IPW") ? atoi(getenv("PTTS_B200_TAIL_IPW")) : 0;   // tuning hook: work items per warp of seanet_tail_kernel (0 = persistent)
+    int tail_ctas_per_sm = getenv("PTTS_B200_TAIL_CTAS") ? atoi(getenv("PTTS_B200_TAIL_CTAS")) : 2;   // tuning hook: persistent CTAs per SM of seanet_tail_kernel
     bool use_fused_tail() const { return fused_tail_allowed && cfg.gemm_path == 0 && !taps_on; }
     int C2 = 512, C5 = 256, C8 = 128;
     ShiftAll shifts{};
@@ -606,7 +607,7 @@ struct b200_engine {
             const long long items = (long long)n * (T3 / ST_ROWS);
             sp.ipw = tail_ipw;
             const int sms = tc ? tc->num_sms : 148;
-            const int grid = tail_ipw > 0 ? (int)((items + ST_WARPS * tail_ipw - 1) / (ST_WARPS * tail_ipw)) : (int)std::min<long long>(2LL * sms, (items + ST_WARPS - 1) / ST_WARPS);
+            const int grid = tail_ipw > 0 ? (int)((items + ST_WARPS * tail_ipw - 1) / (ST_WARPS * tail_ipw)) : (int)std::min<long long>((long long)tail_ctas_per_sm * sms, (items + ST_WARPS - 1) / ST_WARPS);
             launch_k(pdl_active, seanet_tail_kernel, dim3(grid), dim3(ST_THREADS), ST_SMEM_BYTES, stream, sp);
             launch_k(pdl_active, pcm_combine_kernel, dim3((unsigned)(((long long)n * T3 + 255) / 256)), dim3(256), (size_t)0, stream, (const float*)dtail, 1922LL * ST_DROW, slot0, n, T3,
                      (const float*)c11.b, pcm);
@@ -789,7 +790,11 @@ struct b200_engine {
     }
 
     // One generation step for slots [slot0, slot0+n).
-    int immediate_below = getenv("PTTS_B200_IMMEDIATE_BELOW") ? atoi(getenv("PTTS_B200_IMMEDIATE_BELOW")) : 32;   // tuning hook
+    // Below this many utterances the step runs as ONE FlowLM graph + ONE Mimi graph enqueued right away; above, as 7 + 6 graphs with the Mimi
+    // chunks gated behind the attention kernels. Round 1 measured the gated form ahead at batch >= 32; with the fused head / SEANet tail
+    // (fewer, longer kernels) the single-graph form wins everywhere (batch 32: 0.551 -> 0.536 ms, 128: 0.715 -> 0.695, 192: 0.857 -> 0.794,
+    // 256: 0.983 -> 0.933), so the default is "always"; the gated form stays selectable.
+    int immediate_below = getenv("PTTS_B200_IMMEDIATE_BELOW") ? atoi(getenv("PTTS_B200_IMMEDIATE_BELOW")) : (1 << 30);   // tuning hook
     bool one_graph_per_stream(int n) const { return (n >= 4 && n < immediate_below) || use_persistent(n); }
     bool last_step_piped = false;        // the last run_step left its Mimi decode (and PCM copy, for b200_submit frames) to the Mimi stream
     void run_step(int slot0, int n, bool injected, long long tag = -1) {
