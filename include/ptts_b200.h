@@ -98,6 +98,9 @@ B200_API int  b200_step(b200_engine* e, int slot0, int n, const float* noise, fl
  * With cfg.overlap the step is pipelined over two streams (its Mimi decode may be enqueued together with the NEXT step, see
  * DESIGN.md 4.1): call b200_join (stream-ordered) or b200_sync (host) before reading "pcm". */
 B200_API int  b200_step_enqueue(b200_engine* e, int slot0, int n, int use_injected_noise);
+/* `count` consecutive b200_step_enqueue(e, slot0, n, 0) calls made natively (a driver loop in an interpreted host language can starve the
+ * stream: one step is ~1 ms of device time behind two graph launches). */
+B200_API int  b200_steps_enqueue(b200_engine* e, int slot0, int n, int count);
 /* Pipelined pair for throughput serving (up to three frames in flight): submit enqueues a frame and returns at once, collect blocks until the
    oldest submitted frame is complete and copies out its n x 1920 samples + produced flags; returns n (or a negative error).         */
 B200_API int  b200_submit(b200_engine* e, int slot0, int n, const float* noise /* [n][32] or NULL */);

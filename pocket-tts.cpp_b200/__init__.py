@@ -68,6 +68,7 @@ def lib():
         "b200_begin_sentences": (ci, [vp, ci, ip, ip, ip, ip, ip, ip, fp]),
         "b200_step": (ci, [vp, ci, ci, fp, fp, ip, fp, fp]),
         "b200_step_enqueue": (ci, [vp, ci, ci, ci]),
+        "b200_steps_enqueue": (ci, [vp, ci, ci, ci]),
         "b200_submit": (ci, [vp, ci, ci, fp]),
         "b200_collect": (ci, [vp, fp, ip]),
         "b200_sync": (ci, [vp]),
@@ -229,6 +230,11 @@ class Engine:
         if rc < 0:
             raise RuntimeError(f"b200_collect failed: {rc}")
         return rc
+
+    def steps_enqueue(self, slot0, n, count):
+        rc = self.L.b200_steps_enqueue(self.h, slot0, n, count)
+        if rc != 0:
+            raise RuntimeError(f"b200_steps_enqueue failed: {rc}")
 
     def step_enqueue(self, slot0, n, injected=False):
         rc = self.L.b200_step_enqueue(self.h, slot0, n, 1 if injected else 0)

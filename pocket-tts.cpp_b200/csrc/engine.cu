@@ -1352,6 +1352,14 @@ int b200_step_enqueue(b200_engine* e, int slot0, int n, int use_injected_noise) 
     return B200_OK;
 }
 
+// `count` consecutive steps enqueued by one native call (no host-language overhead between them).
+int b200_steps_enqueue(b200_engine* e, int slot0, int n, int count) {
+    if (!e || !e->finalized || slot0 < 0 || n < 1 || slot0 + n > e->cfg.max_slots || count < 0) return B200_EINVAL;
+    PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    for (int i = 0; i < count; i++) e->run_step(slot0, n, false);
+    return B200_OK;
+}
+
 int b200_sync(b200_engine* e) {
     if (!e) return B200_EINVAL;
     PTTS_CUDA_CHECK(cudaSetDevice(e->cfg.device));
