@@ -49,6 +49,9 @@ struct b200_engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool tma_epilogue_allowed = getenv("PTTS_B200_TMA_EPILOGUE") ? atoi(getenv("PTTS_B200_TMA_EPILOGUE")) != 0 : true;   // tuning hook
     bool fork_tiles = getenv("PTTS_B200_FORK_TILES") ? atoi(getenv("PTTS_B200_FORK_TILES")) != 0 : true;   // tuning hook
+    // 1: no attn_merge_kernel; the last CTA (of either attention kernel) to arrive for a (row, head) merges it. Bit-identical output, but no
+    // gain: the tile CTAs usually arrive last and their extra fence + merge tail costs what the 7 us launch saved (0.9405 vs 0.9341 ms per step).
+    bool counted_merge = getenv("PTTS_B200_COUNTED_MERGE") ? atoi(getenv("PTTS_B200_COUNTED_MERGE")) != 0 : false;
     cudaEvent_t ev_main[2] = {nullptr, nullptr}, ev_mimi[2] = {nullptr, nullptr};
     bool ev_mimi_valid[2] = {false, false};
     unsigned long long pipe_t = 0;       // frames enqueued through the pipeline
@@ -120,6 +123,7 @@ struct b200_engine {
     int *row_slot = nullptr, *row_pos = nullptr, *tok = nullptr; float2* cs = nullptr;
     float *af_ml = nullptr, *af_acc = nullptr;   // split-KV attention workspace [rows][splits][32] / [rows][splits][1024]
     int* af_cnt = nullptr;                       // per-row arrival counters of the in-kernel split merge (zero between launches)
+    int* af_cnt2 = nullptr;                      // per (row, head) arrival counters of the counted merge (streaming + tile kernel side by side)
     // ---- shared voice prefix (cfg.prefix_share): per-slot {slot holding the prefix rows, number of prefix rows}; 0 rows = private cache ----
     int *pfx_slot = nullptr, *pfx_len = nullptr; std::vector<int> h_pfx_slot, h_pfx_len;
     unsigned long long pfx_version = 1;          // bumped whenever a slot's prefix assignment changes
@@ -404,12 +408,15 @@ struct b200_engine {
             // once per tile instead of once per row
             if (actx.n_items > 0)
                 launch_tiles(2, pdl_active, dim3(actx.n_items, N_HEADS), stream, (const float*)q, (const __nv_bfloat16*)e.kcache,
-                             (const __nv_bfloat16*)e.vcache, kv_slot_stride, actx.items, actx.meta, (const int*)nullptr, actx.row_pos, af_ml, af_acc, att_bf);
+                             (const __nv_bfloat16*)e.vcache, kv_slot_stride, actx.items, actx.meta, (const int*)nullptr, actx.row_pos, af_ml, af_acc, att_bf, (const int*)nullptr, (int*)nullptr, 0);
             launches++;
         } else {
             const bool tiles = use_prefix_tiles(R);
             const bool fork = tiles && fork_tiles;      // tile kernel (tensor cores, prefix from L2) beside the streaming kernel (HBM), merged afterwards
-            AfKeys keys; keys.pfx_slot = pfx_slot; keys.pfx_len = pfx_len; keys.tiles_meta = tiles ? dec_meta : nullptr; keys.defer_merge = fork ? 1 : 0;
+            const bool counted = fork && counted_merge;  // both kernels count per (row, head); the last arriver merges: no merge launch
+            const int splits = af_splits(R, tiles);
+            AfKeys keys; keys.pfx_slot = pfx_slot; keys.pfx_len = pfx_len; keys.tiles_meta = tiles ? dec_meta : nullptr; keys.defer_merge = fork ? (counted ? 2 : 1) : 0;
+            keys.merge_cnt2 = af_cnt2;
             if (tiles) {   // shared voice prefix x all rows of the voice -> workspace partials
                 cudaStream_t ts = stream;
                 if (fork) {
@@ -419,12 +426,12 @@ struct b200_engine {
                 }
                 const int sgt = seg_begin(6, ts);
                 launch_tiles(tile_prec, fork ? false : pdl_active, dim3(dec_grid_items, N_HEADS), ts, (const float*)q, (const __nv_bfloat16*)e.kcache,
-                             (const __nv_bfloat16*)e.vcache, kv_slot_stride, (const AtItem*)dec_items, (const int*)dec_meta, (const int*)dec_rows, actx.row_pos, af_ml, af_acc, att_bf);
+                             (const __nv_bfloat16*)e.vcache, kv_slot_stride, (const AtItem*)dec_items, (const int*)dec_meta, (const int*)dec_rows, actx.row_pos, af_ml, af_acc, att_bf,
+                             actx.row_slot, counted ? af_cnt2 : (int*)nullptr, splits);
                 launches++;
                 seg_end(sgt, ts);
                 if (fork) PTTS_CUDA_CHECK(cudaEventRecord(ev_join, stream_t));
             }
-            const int splits = af_splits(R, tiles);
             sg = seg_begin(0);
             if (cfg.kv_f32)
                 launch_k(pdl_active, attn_flow_split_kernel<float>, dim3(splits, R), dim3(288), (size_t)(AfCfg<float>::SMEM), stream, (const float*)q, (const float*)e.kcache, (const float*)e.vcache,
@@ -436,8 +443,8 @@ struct b200_engine {
             if (fork) {
                 seg_end(sg); sg = -1;
                 PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0));
-                launch_k(false, attn_merge_kernel, dim3(R), dim3(256), (size_t)0, stream, actx.row_slot, (const int*)pfx_len, (const int*)dec_meta, splits, (const float*)af_ml, (const float*)af_acc, att_bf);
-                launches++;
+                if (!counted) launch_k(false, attn_merge_kernel, dim3(R), dim3(256), (size_t)0, stream, actx.row_slot, (const int*)pfx_len, (const int*)dec_meta, splits, (const float*)af_ml, (const float*)af_acc, att_bf);
+                if (!counted) launches++;
             }
         }
         set_pdl(pdl_saved);
@@ -1116,7 +1123,7 @@ int b200_finalize_weights(b200_engine* e) {
     e->h = e->dalloc<float>((size_t)MR * D_MODEL); e->q = e->dalloc<float>((size_t)MR * D_MODEL);
     e->n_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_MODEL); e->att_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_MODEL);
     e->ff_bf = e->dalloc<__nv_bfloat16>((size_t)MR * D_FF);
-    e->af_ml = e->dalloc<float>((size_t)MR * AF_WS_STRIDE * 32); e->af_acc = e->dalloc<float>((size_t)MR * AF_WS_STRIDE * D_MODEL); e->af_cnt = e->dalloc<int>(MR);
+    e->af_ml = e->dalloc<float>((size_t)MR * AF_WS_STRIDE * 32); e->af_acc = e->dalloc<float>((size_t)MR * AF_WS_STRIDE * D_MODEL); e->af_cnt = e->dalloc<int>(MR); e->af_cnt2 = e->dalloc<int>((size_t)MR * N_HEADS);
     e->pfx_slot = e->dalloc<int>(TS); e->pfx_len = e->dalloc<int>(TS);
     e->dec_items_cap = ((S + AT_ROWS - 1) / AT_ROWS + e->cfg.max_voices + 1) * AF_PFX_SPLITS + 8;
     e->dec_items = e->dalloc<AtItem>(e->dec_items_cap); e->dec_meta = e->dalloc<int>(4); e->dec_rows = e->dalloc<int>(S);

@@ -133,8 +133,11 @@ __device__ __forceinline__ void af_bulk_load(uint32_t dst, const void* src, uint
 //   tiles_meta (may be null): {item count, prefix splits} of an attn_tile_kernel launch that ALREADY reduced keys [0, P) of every row with
 //   P > 0 into workspace entries [AF_MAX_SPLITS, AF_MAX_SPLITS + prefix splits); this kernel then streams only [P, pos] and merges both.
 //   defer_merge: the tile kernel runs CONCURRENTLY (forked stream), so its partials may not exist yet: this kernel only writes its own
-//   partials and attn_merge_kernel, launched after the join, combines them.
-struct AfKeys { const int* pfx_slot; const int* pfx_len; const int* tiles_meta; int defer_merge; };
+//   partials and attn_merge_kernel, launched after the join, combines them (defer_merge = 1). defer_merge = 2: no merge launch either;
+//   every CTA of both kernels counts into merge_cnt2[row][head] after it has published its partials, and whichever arrives LAST for a
+//   (row, head) combines that head's partials (fixed entry order, same arithmetic as attn_merge_kernel: bit-identical) and writes the
+//   bf16 output. Expected arrivals = streaming splits + prefix splits; dead rows are counted by nobody.
+struct AfKeys { const int* pfx_slot; const int* pfx_len; const int* tiles_meta; int defer_merge; int* merge_cnt2; };
 
 // One CTA per (KV split, query row), all 16 heads at once so that every cache row is read as one contiguous 2/4 KB line. Warp 8 lane 0
 // is the producer: it streams groups of 8 consecutive K rows and V rows into a 3-stage shared-memory ring with cp.async.bulk + mbarrier
@@ -310,16 +313,28 @@ attn_flow_split_kernel(const float* __restrict__ q, const KV* __restrict__ kc, c
     const long long wrow = (long long)row * AF_WS_STRIDE;
     if ((t & 15) == 0) { ws_ml[(wrow + split) * 32 + h] = M; ws_ml[(wrow + split) * 32 + 16 + h] = L; }
     *reinterpret_cast<float4*>(ws_acc + (wrow + split) * D_MODEL + 4 * t) = make_float4(o[0], o[1], o[2], o[3]);
-    if (keys.defer_merge) return;
+    if (keys.defer_merge == 1) return;
     // The LAST split CTA of a row to finish merges all of the row's partials (fixed entry order: deterministic) and writes the bf16
     // output, which removes the separate merge launch from every layer. Release/acquire through the per-row counter. The prefix
     // partials (entries AF_MAX_SPLITS..) were written by an EARLIER kernel of the same stream, hence are already visible.
+    // defer_merge == 2: the tile kernel runs concurrently and counts too, per (row, head); see AfKeys.
     __threadfence();
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    int* flag = reinterpret_cast<int*>(af_smem);
-    if (t == 0) { const int prev = atomicAdd(merge_cnt + row, 1); *flag = (prev == splits - 1); if (prev == splits - 1) merge_cnt[row] = 0; }
+    int* flag = reinterpret_cast<int*>(af_smem);                   // [16] (per head; one entry broadcast in the per-row scheme)
+    if (keys.defer_merge == 2) {
+        if (t < N_HEADS) {
+            const int expect = splits + n_extra;
+            const int prev = atomicAdd(keys.merge_cnt2 + row * N_HEADS + t, 1);
+            flag[t] = (prev == expect - 1);
+            if (prev == expect - 1) keys.merge_cnt2[row * N_HEADS + t] = 0;
+        }
+    } else if (t == 0) {
+        const int prev = atomicAdd(merge_cnt + row, 1); const int last = (prev == splits - 1);
+        if (last) merge_cnt[row] = 0;
+        for (int i = 0; i < N_HEADS; i++) flag[i] = last;
+    }
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (!*flag) return;
+    if (!flag[h]) return;
     __threadfence();
     const int n_ent = splits + n_extra;
     float Mm = -INFINITY;
@@ -384,9 +399,11 @@ template <int PREC>
 __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kc, const __nv_bfloat16* __restrict__ vc,
                                                         long long kv_slot_stride, const AtItem* __restrict__ items, const int* __restrict__ meta,
                                                         const int* __restrict__ row_list, const int* __restrict__ row_pos,
-                                                        float* __restrict__ ws_ml, float* __restrict__ ws_acc, __nv_bfloat16* __restrict__ out) {
+                                                        float* __restrict__ ws_ml, float* __restrict__ ws_acc, __nv_bfloat16* __restrict__ out,
+                                                        const int* __restrict__ row_slot, int* __restrict__ merge_cnt2, int stream_splits) {
     pdl_prologue();
     __shared__ __align__(128) uint8_t sKV[2][2][AT_TILE_BYTES];    // [buffer][K | V]
+    __shared__ int s_merge[AT_ROWS];                               // rows of this tile whose (row, head) this CTA completed (counted merge)
     if ((int)blockIdx.x >= meta[0]) return;
     const AtItem it = items[blockIdx.x];
     const int h = blockIdx.y;
@@ -546,6 +563,55 @@ __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict_
             __nv_bfloat16* dst = out + (long long)r * D_MODEL + h * D_HEAD + 16 * t;
             *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(&pk[0]);
             *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<uint4*>(&pk[4]);
+        }
+    }
+    if (!merge_cnt2 || it.out_split < 0) return;
+    // ---- counted merge (AfKeys::defer_merge == 2): arrive for every live row of the tile; rows this CTA completed are merged here ----
+    __threadfence();
+    __syncthreads();
+    const int n_extra = meta[1], expect = stream_splits + n_extra;
+    if ((int)threadIdx.x < AT_ROWS) {
+        int mine = -1;
+        if ((int)threadIdx.x < it.nrows) {
+            const int r = row_list ? row_list[it.row0 + threadIdx.x] : it.row0 + (int)threadIdx.x;
+            if (row_slot[r] >= 0) {                                  // dead rows are counted by nobody (their streaming CTA exits at once)
+                const int prev = atomicAdd(merge_cnt2 + r * N_HEADS + h, 1);
+                if (prev == expect - 1) { merge_cnt2[r * N_HEADS + h] = 0; mine = r; }
+            }
+        }
+        s_merge[threadIdx.x] = mine;
+    }
+    __syncthreads();
+    __threadfence();
+    for (int i = threadIdx.x >> 1; i < it.nrows; i += 64) {          // two threads per row: 32 dims each
+        const int r = s_merge[i];
+        if (r < 0) continue;
+        const long long wrow = (long long)r * AF_WS_STRIDE;
+        const int d0 = h * D_HEAD + (threadIdx.x & 1) * 32;
+        float Mm = -INFINITY;
+        for (int e = 0; e < expect; e++) { const int sp = e < stream_splits ? e : AF_MAX_SPLITS + (e - stream_splits); Mm = fmaxf(Mm, __ldcg(ws_ml + (wrow + sp) * 32 + h)); }
+        float Lm = 0.f, om[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) om[j] = 0.f;
+        for (int e = 0; e < expect; e++) {
+            const long long w2 = wrow + (e < stream_splits ? e : AF_MAX_SPLITS + (e - stream_splits));
+            const float ms = __ldcg(ws_ml + w2 * 32 + h);
+            const float sc = (ms == -INFINITY) ? 0.f : expf(ms - Mm);
+            Lm = fmaf(__ldcg(ws_ml + w2 * 32 + 16 + h), sc, Lm);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(ws_acc + w2 * D_MODEL + d0 + j));
+                om[j] = fmaf(a.x, sc, om[j]); om[j + 1] = fmaf(a.y, sc, om[j + 1]); om[j + 2] = fmaf(a.z, sc, om[j + 2]); om[j + 3] = fmaf(a.w, sc, om[j + 3]);
+            }
+        }
+        const float inv = 1.0f / Lm;
+        __nv_bfloat16* dst = out + (long long)r * D_MODEL + d0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            __nv_bfloat162 pk[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) pk[u] = __floats2bfloat162_rn(om[j + 2 * u] * inv, om[j + 2 * u + 1] * inv);
+            *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<uint4*>(&pk[0]);
         }
     }
 }

@@ -1,4 +1,4 @@
-"""A/B of the fused flow-head cluster kernel (head_fused.cuh) against the unfused launch chain: same weights, same injected noise, B utterances
+"""A/B of an engine switch (environment variable AB_VAR = 0 / 1; default: the fused flow-head cluster kernel (head_fused.cuh) against the unfused launch chain: same weights, same injected noise, B utterances
 (default 40: not a multiple of the 16-row cluster tile), a few free-running frames. Prints the worst latent / PCM difference per frame."""
 import os, sys
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tools")
@@ -10,7 +10,7 @@ B = int(os.environ.get("B", "40"))
 texts = ["The quick brown fox jumped over the sleeping dog.", "Hello world, this is a test of the head.", "One two three four five six seven."]
 out = {}
 for mode in ("0", "1"):
-    os.environ["PTTS_B200_FUSED_HEAD"] = mode
+    os.environ[os.environ.get("AB_VAR", "PTTS_B200_FUSED_HEAD")] = mode
     ctx = P.Context(d, max_slots=B, kv_capacity=512)
     eng = ctx.engine
     st = ctx.stream("cosette", temp=0.7)
