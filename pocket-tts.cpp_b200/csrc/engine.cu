@@ -133,6 +133,7 @@ struct b200_engine {
     int tile_prec = getenv("PTTS_B200_TILE_PREC") ? atoi(getenv("PTTS_B200_TILE_PREC")) : 1;   // operand precision of the decode-side tile kernel (see attn_tile_kernel): q as
     // hi + lo (the scores go through exp), plain bf16 probabilities; measured on the bench context 2 -> 1 -> 0: 1.084 / 1.067 / 1.054 ms per step,
     // latent max-abs 0.020 / 0.018 / 0.020 and SNR 44.9 / 46.4 / 45.4 dB against the CPU restatement (no measurable parity difference)
+    int prefill_prec = getenv("PTTS_B200_PREFILL_PREC") ? atoi(getenv("PTTS_B200_PREFILL_PREC")) : 2;   // operand precision of the prefill tiles (same scale)
     int tile_min_rows = getenv("PTTS_B200_TILE_MIN_ROWS") ? atoi(getenv("PTTS_B200_TILE_MIN_ROWS")) : 4;   // below: the streaming kernel reads the prefix itself
     // attention context of the forward being enqueued (decode: the fixed scratch arrays; prefill: this call's staging)
     struct AttnCtx { const int* row_slot = nullptr; const int* row_pos = nullptr; const float2* cs = nullptr;
@@ -407,7 +408,7 @@ struct b200_engine {
             // T > 1 rows with the causal mask (reference transformer.h:157-169): one tensor-core tile per 64 rows of a slot and head, K/V read
             // once per tile instead of once per row
             if (actx.n_items > 0)
-                launch_tiles(2, pdl_active, dim3(actx.n_items, N_HEADS), stream, (const float*)q, (const __nv_bfloat16*)e.kcache,
+                launch_tiles(prefill_prec, pdl_active, dim3(actx.n_items, N_HEADS), stream, (const float*)q, (const __nv_bfloat16*)e.kcache,
                              (const __nv_bfloat16*)e.vcache, kv_slot_stride, actx.items, actx.meta, (const int*)nullptr, actx.row_pos, af_ml, af_acc, att_bf, (const int*)nullptr, (int*)nullptr, 0);
             launches++;
         } else {
