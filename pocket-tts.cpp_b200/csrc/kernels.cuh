@@ -838,6 +838,17 @@ __global__ void __launch_bounds__(128) attn_mimi_mma4_kernel(const __nv_bfloat16
             }
         }
     }
+    // ---- V rows of this warp's 64 keys: issued now, consumed after the softmax (its two block barriers would otherwise sit between the
+    //      K stream and the V stream: the kernel is HBM-latency bound, 135 MB per launch) ----
+    uint4 vreg[4][4];
+#pragma unroll
+    for (int s4 = 0; s4 < 4; s4++) {
+        const int k0 = 64 * warp + 16 * s4 + 2 * t;
+        vreg[s4][0] = *reinterpret_cast<const uint4*>(V + (long long)min(k0, M_CTX - 1) * M_DIM + 8 * g);
+        vreg[s4][1] = *reinterpret_cast<const uint4*>(V + (long long)min(k0 + 1, M_CTX - 1) * M_DIM + 8 * g);
+        vreg[s4][2] = *reinterpret_cast<const uint4*>(V + (long long)min(k0 + 8, M_CTX - 1) * M_DIM + 8 * g);
+        vreg[s4][3] = *reinterpret_cast<const uint4*>(V + (long long)min(k0 + 9, M_CTX - 1) * M_DIM + 8 * g);
+    }
     // ---- row max over all 250 keys ----
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -875,11 +886,7 @@ __global__ void __launch_bounds__(128) attn_mimi_mma4_kernel(const __nv_bfloat16
             x = __floats2bfloat162_rn(S[2 * s4 + 1][0] * inv0, S[2 * s4 + 1][1] * inv0); pa[2] = *reinterpret_cast<uint32_t*>(&x);
             x = __floats2bfloat162_rn(S[2 * s4 + 1][2] * inv1, S[2 * s4 + 1][3] * inv1); pa[3] = *reinterpret_cast<uint32_t*>(&x);
         }
-        const int k0 = 64 * warp + 16 * s4 + 2 * t;
-        const uint4 v0 = *reinterpret_cast<const uint4*>(V + (long long)min(k0, M_CTX - 1) * M_DIM + 8 * g);
-        const uint4 v1 = *reinterpret_cast<const uint4*>(V + (long long)min(k0 + 1, M_CTX - 1) * M_DIM + 8 * g);
-        const uint4 v2 = *reinterpret_cast<const uint4*>(V + (long long)min(k0 + 8, M_CTX - 1) * M_DIM + 8 * g);
-        const uint4 v3 = *reinterpret_cast<const uint4*>(V + (long long)min(k0 + 9, M_CTX - 1) * M_DIM + 8 * g);
+        const uint4 v0 = vreg[s4][0], v1 = vreg[s4][1], v2 = vreg[s4][2], v3 = vreg[s4][3];
         const uint32_t a0[4] = {v0.x, v0.y, v0.z, v0.w}, a1[4] = {v1.x, v1.y, v1.z, v1.w}, a2[4] = {v2.x, v2.y, v2.z, v2.w}, a3[4] = {v3.x, v3.y, v3.z, v3.w};
 #pragma unroll
         for (int w = 0; w < 4; w++) {
