@@ -384,6 +384,10 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// The tile kernel keeps its scores in the log2 domain (q pre-scaled by log2(e) / 8) so that every probability is ONE ex2.approx (plus the
+// subtract): expf costs ~10 instructions, and at 32 of them per lane and 64-key block they outweighed the block's 80 MMAs in issue slots.
+constexpr float AT_QSCALE = 0.125f * 1.4426950408889634f;
+__device__ __forceinline__ float at_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void at_split2(float x, float y, uint32_t& hi, uint32_t& lo) {      // (x, y) -> bf16x2 hi, bf16x2 lo
     const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
     const float2 hf = __bfloat1622float2(h);
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict_
             x1[0] = a.x; x1[1] = a.y; x1[2] = a.z; x1[3] = a.w; x1[4] = b.x; x1[5] = b.y; x1[6] = b.z; x1[7] = b.w;
         }
 #pragma unroll
-        for (int e = 0; e < 8; e++) { x0[e] *= 0.125f; x1[e] *= 0.125f; }
+        for (int e = 0; e < 8; e++) { x0[e] *= AT_QSCALE; x1[e] *= AT_QSCALE; }
         // k16 step 2p: slots (2t, 2t+1) = values 0,1 and (2t+8, 2t+9) = values 2,3; step 2p+1: values 4,5 and 6,7
         at_split2(x0[0], x0[1], qh[2 * p][0], ql[2 * p][0]); at_split2(x1[0], x1[1], qh[2 * p][1], ql[2 * p][1]);
         at_split2(x0[2], x0[3], qh[2 * p][2], ql[2 * p][2]); at_split2(x1[2], x1[3], qh[2 * p][3], ql[2 * p][3]);
@@ -501,13 +505,13 @@ __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict_
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
         const float mu0 = mn0 == -INFINITY ? 0.f : mn0, mu1 = mn1 == -INFINITY ? 0.f : mn1;    // nothing visible yet: exp(-inf - 0) = 0
-        const float c0 = expf(m0 - mu0), c1 = expf(m1 - mu1);
+        const float c0 = at_exp2(m0 - mu0), c1 = at_exp2(m1 - mu1);
         m0 = mn0; m1 = mn1; l0 *= c0; l1 *= c1;
 #pragma unroll
         for (int n = 0; n < 8; n++) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            S[j][0] = expf(S[j][0] - mu0); S[j][1] = expf(S[j][1] - mu0); S[j][2] = expf(S[j][2] - mu1); S[j][3] = expf(S[j][3] - mu1);
+            S[j][0] = at_exp2(S[j][0] - mu0); S[j][1] = at_exp2(S[j][1] - mu0); S[j][2] = at_exp2(S[j][2] - mu1); S[j][3] = at_exp2(S[j][3] - mu1);
             l0 += S[j][0] + S[j][1]; l1 += S[j][2] + S[j][3];
         }
         // ---- O += P V (4 key steps of 16) ----
@@ -546,7 +550,7 @@ __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict_
         const float mr = rr ? m1 : m0, lr = rr ? l1 : l0;
         if (it.out_split >= 0) {
             const long long w = (long long)r * AF_WS_STRIDE + it.out_split;
-            if (t == 0) { ws_ml[w * 32 + h] = mr; ws_ml[w * 32 + 16 + h] = lr; }
+            if (t == 0) { ws_ml[w * 32 + h] = mr * 0.69314718055994530942f; ws_ml[w * 32 + 16 + h] = lr; }   // the merge works in the natural-log domain
             float* dst = ws_acc + w * D_MODEL + h * D_HEAD + 16 * t;
 #pragma unroll
             for (int e = 0; e < 2; e++) {
