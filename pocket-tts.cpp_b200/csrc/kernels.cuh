@@ -127,6 +127,12 @@ __device__ __forceinline__ void af_bulk_load(uint32_t dst, const void* src, uint
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 
+// The attention kernels keep their scores in the log2 domain (q pre-scaled by log2(e) / 8) so that every probability is ONE ex2.approx (plus the
+// subtract): expf costs ~10 instructions, and at 32 of them per lane and 64-key block they outweighed the 80 MMAs of a
+// tile-kernel block in issue slots. Maxima written to the merge workspace are converted back to the natural-log domain.
+constexpr float AT_QSCALE = 0.125f * 1.4426950408889634f;
+__device__ __forceinline__ float at_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // Per-launch description of the keys a row attends to.
 //   pfx_slot / pfx_len (per SLOT, may be null): keys [0, P) of the row live in ANOTHER slot's cache (the voice prefix shared by every
 //   utterance of that voice, reference copy_states models/flow_lm.h:70-78 made a private copy instead); keys [P, pos] are the slot's own.
@@ -218,7 +224,7 @@ attn_flow_split_kernel(const float* __restrict__ q, const KV* __restrict__ kc, c
 #pragma unroll
         for (int e = 0; e < C::EPC; e += 4) {
             const float4 a = *reinterpret_cast<const float4*>(qp + e);
-            qr[i][e] = a.x * 0.125f; qr[i][e + 1] = a.y * 0.125f; qr[i][e + 2] = a.z * 0.125f; qr[i][e + 3] = a.w * 0.125f;
+            qr[i][e] = a.x * AT_QSCALE; qr[i][e + 1] = a.y * AT_QSCALE; qr[i][e + 2] = a.z * AT_QSCALE; qr[i][e + 3] = a.w * AT_QSCALE;   // log2 domain, see at_exp2
         }
     }
     float m[C::NCH], l[C::NCH], acc[C::NCH][C::EPC];
@@ -256,7 +262,7 @@ attn_flow_split_kernel(const float* __restrict__ q, const KV* __restrict__ kc, c
 #pragma unroll
             for (int i = 0; i < C::NCH; i++) {
                 const float mn = fmaxf(m[i], sc[i]);
-                const float corr = expf(m[i] - mn), p = expf(sc[i] - mn);
+                const float corr = at_exp2(m[i] - mn), p = at_exp2(sc[i] - mn);
                 m[i] = mn; l[i] = l[i] * corr + p;
                 const uint4 vv = *reinterpret_cast<const uint4*>(vr + i * 512);
                 if constexpr (sizeof(KV) == 2) {
@@ -298,7 +304,7 @@ attn_flow_split_kernel(const float* __restrict__ q, const KV* __restrict__ kc, c
 #pragma unroll
     for (int w = 0; w < 8; w++) {
         const float mw = sm_m[w * 16 + h];
-        const float sc = (mw == -INFINITY) ? 0.f : expf(mw - M);
+        const float sc = (mw == -INFINITY) ? 0.f : at_exp2(mw - M);
         L = fmaf(sm_l[w * 16 + h], sc, L);
         const float4 a = *reinterpret_cast<const float4*>(sm_a + w * D_MODEL + 4 * t);
         o[0] = fmaf(a.x, sc, o[0]); o[1] = fmaf(a.y, sc, o[1]); o[2] = fmaf(a.z, sc, o[2]); o[3] = fmaf(a.w, sc, o[3]);
@@ -311,7 +317,7 @@ attn_flow_split_kernel(const float* __restrict__ q, const KV* __restrict__ kc, c
         return;
     }
     const long long wrow = (long long)row * AF_WS_STRIDE;
-    if ((t & 15) == 0) { ws_ml[(wrow + split) * 32 + h] = M; ws_ml[(wrow + split) * 32 + 16 + h] = L; }
+    if ((t & 15) == 0) { ws_ml[(wrow + split) * 32 + h] = M * 0.69314718055994530942f; ws_ml[(wrow + split) * 32 + 16 + h] = L; }   // workspace maxima: natural-log domain
     *reinterpret_cast<float4*>(ws_acc + (wrow + split) * D_MODEL + 4 * t) = make_float4(o[0], o[1], o[2], o[3]);
     if (keys.defer_merge == 1) return;
     // The LAST split CTA of a row to finish merges all of the row's partials (fixed entry order: deterministic) and writes the bf16
@@ -384,10 +390,6 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// The tile kernel keeps its scores in the log2 domain (q pre-scaled by log2(e) / 8) so that every probability is ONE ex2.approx (plus the
-// subtract): expf costs ~10 instructions, and at 32 of them per lane and 64-key block they outweighed the block's 80 MMAs in issue slots.
-constexpr float AT_QSCALE = 0.125f * 1.4426950408889634f;
-__device__ __forceinline__ float at_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void at_split2(float x, float y, uint32_t& hi, uint32_t& lo) {      // (x, y) -> bf16x2 hi, bf16x2 lo
     const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
     const float2 hf = __bfloat1622float2(h);
@@ -406,6 +408,11 @@ __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict_
                                                         float* __restrict__ ws_ml, float* __restrict__ ws_acc, __nv_bfloat16* __restrict__ out,
                                                         const int* __restrict__ row_slot, int* __restrict__ merge_cnt2, int stream_splits) {
     pdl_prologue();
+    // log2-domain scores + ex2.approx for the decode-side tiles (PREC < 2), where the exponentials bound the kernel; the full-precision
+    // variant (prefill: MMA / L2 bound, and its K/V rows feed every later frame) keeps expf on natural-log scores
+    constexpr bool LOG2 = PREC < 2;
+    constexpr float QS = LOG2 ? AT_QSCALE : 0.125f;
+    auto EX = [](float x) { return LOG2 ? at_exp2(x) : expf(x); };
     __shared__ __align__(128) uint8_t sKV[2][2][AT_TILE_BYTES];    // [buffer][K | V]
     __shared__ int s_merge[AT_ROWS];                               // rows of this tile whose (row, head) this CTA completed (counted merge)
     if ((int)blockIdx.x >= meta[0]) return;
@@ -432,7 +439,7 @@ __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict_
             x1[0] = a.x; x1[1] = a.y; x1[2] = a.z; x1[3] = a.w; x1[4] = b.x; x1[5] = b.y; x1[6] = b.z; x1[7] = b.w;
         }
 #pragma unroll
-        for (int e = 0; e < 8; e++) { x0[e] *= AT_QSCALE; x1[e] *= AT_QSCALE; }
+        for (int e = 0; e < 8; e++) { x0[e] *= QS; x1[e] *= QS; }
         // k16 step 2p: slots (2t, 2t+1) = values 0,1 and (2t+8, 2t+9) = values 2,3; step 2p+1: values 4,5 and 6,7
         at_split2(x0[0], x0[1], qh[2 * p][0], ql[2 * p][0]); at_split2(x1[0], x1[1], qh[2 * p][1], ql[2 * p][1]);
         at_split2(x0[2], x0[3], qh[2 * p][2], ql[2 * p][2]); at_split2(x1[2], x1[3], qh[2 * p][3], ql[2 * p][3]);
@@ -505,13 +512,13 @@ __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict_
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
         const float mu0 = mn0 == -INFINITY ? 0.f : mn0, mu1 = mn1 == -INFINITY ? 0.f : mn1;    // nothing visible yet: exp(-inf - 0) = 0
-        const float c0 = at_exp2(m0 - mu0), c1 = at_exp2(m1 - mu1);
+        const float c0 = EX(m0 - mu0), c1 = EX(m1 - mu1);
         m0 = mn0; m1 = mn1; l0 *= c0; l1 *= c1;
 #pragma unroll
         for (int n = 0; n < 8; n++) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            S[j][0] = at_exp2(S[j][0] - mu0); S[j][1] = at_exp2(S[j][1] - mu0); S[j][2] = at_exp2(S[j][2] - mu1); S[j][3] = at_exp2(S[j][3] - mu1);
+            S[j][0] = EX(S[j][0] - mu0); S[j][1] = EX(S[j][1] - mu0); S[j][2] = EX(S[j][2] - mu1); S[j][3] = EX(S[j][3] - mu1);
             l0 += S[j][0] + S[j][1]; l1 += S[j][2] + S[j][3];
         }
         // ---- O += P V (4 key steps of 16) ----
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(128) attn_tile_kernel(const float* __restrict_
         const float mr = rr ? m1 : m0, lr = rr ? l1 : l0;
         if (it.out_split >= 0) {
             const long long w = (long long)r * AF_WS_STRIDE + it.out_split;
-            if (t == 0) { ws_ml[w * 32 + h] = mr * 0.69314718055994530942f; ws_ml[w * 32 + 16 + h] = lr; }   // the merge works in the natural-log domain
+            if (t == 0) { ws_ml[w * 32 + h] = LOG2 ? mr * 0.69314718055994530942f : mr; ws_ml[w * 32 + 16 + h] = lr; }   // the merge works in the natural-log domain
             float* dst = ws_acc + w * D_MODEL + h * D_HEAD + 16 * t;
 #pragma unroll
             for (int e = 0; e < 2; e++) {
