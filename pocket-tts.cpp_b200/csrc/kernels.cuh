@@ -844,8 +844,8 @@ __global__ void __launch_bounds__(128) attn_mimi_mma4_kernel(const __nv_bfloat16
                 bool m0, m1;
                 if (mask_mode == 0) { m0 = mimi_masked_fast(mr0, c); m1 = mimi_masked_fast(mr1, c); }
                 else { m0 = c >= M_CTX || mimi_masked(offset, g, c, mask_mode); m1 = c >= M_CTX || mimi_masked(offset, g + 8, c, mask_mode); }
-                sc[e] = m0 ? -INFINITY : sc[e] * 0.125f;
-                sc[2 + e] = m1 ? -INFINITY : sc[2 + e] * 0.125f;
+                sc[e] = m0 ? -INFINITY : sc[e] * AT_QSCALE;            // log2 domain: one ex2.approx per probability below
+                sc[2 + e] = m1 ? -INFINITY : sc[2 + e] * AT_QSCALE;
             }
         }
     }
@@ -874,7 +874,7 @@ __global__ void __launch_bounds__(128) attn_mimi_mma4_kernel(const __nv_bfloat16
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        S[j][0] = expf(S[j][0] - mx0); S[j][1] = expf(S[j][1] - mx0); S[j][2] = expf(S[j][2] - mx1); S[j][3] = expf(S[j][3] - mx1);
+        S[j][0] = at_exp2(S[j][0] - mx0); S[j][1] = at_exp2(S[j][1] - mx0); S[j][2] = at_exp2(S[j][2] - mx1); S[j][3] = at_exp2(S[j][3] - mx1);
         l0 += S[j][0] + S[j][1]; l1 += S[j][2] + S[j][3];
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
