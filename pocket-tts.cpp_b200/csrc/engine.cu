@@ -45,6 +45,7 @@ struct b200_engine {
     // Two-stream pipeline: the Mimi decode of frame t (tensor/ALU bound) runs on stream_m while the FlowLM step of frame t+1 (latency
     // bound small GEMMs + the HBM-bound KV stream) runs on the main stream. Hand-off buffer mx2[t & 1], events per parity.
     cudaStream_t stream_m = nullptr;
+    cudaStream_t stream_c = nullptr;     // device->host PCM copies of b200_submit frames (beside the next frame's Mimi decode instead of in front of it)
     cudaStream_t stream_t = nullptr;     // forked branch of the main stream: the shared-prefix tile kernel runs beside the per-utterance KV stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool tma_epilogue_allowed = getenv("PTTS_B200_TMA_EPILOGUE") ? atoi(getenv("PTTS_B200_TMA_EPILOGUE")) != 0 : true;   // tuning hook
@@ -150,6 +151,10 @@ struct b200_engine {
     __half *buf0 = nullptr, *buf2 = nullptr, *buf3a = nullptr, *buf3b = nullptr, *buf5 = nullptr, *buf6a = nullptr, *buf6b = nullptr,
            *buf8 = nullptr, *buf9a = nullptr, *buf9b = nullptr, *buf11 = nullptr;
     float *y3 = nullptr, *y6 = nullptr, *y9 = nullptr, *pcm = nullptr;
+    // b200_submit frames decode into pcm_alt[frame parity] so that the copy of frame t can run while frame t+1 is decoded; every other path
+    // (b200_step, b200_step_enqueue + b200_device_ptr("pcm"), b200_mimi_decode) writes `pcm`. pcm_out = the buffer the enqueued decode writes.
+    float* pcm_alt[2] = {nullptr, nullptr}; float* pcm_out = nullptr;
+    cudaEvent_t ev_dec[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr}; bool ev_copy_valid[2] = {false, false}; int last_copy_par = -1;
     float* dtail = nullptr;   // [slot][2 + 1920][4] per-row tap products of the output conv (seanet_tail.cuh), two carried rows in front
     bool fused_tail_allowed = getenv("PTTS_B200_FUSED_TAIL") ? atoi(getenv("PTTS_B200_FUSED_TAIL")) != 0 : true;   // tuning hook
     // The tap "seanet.res9" reads the f16 a3 rows, which only the unfused launches produce. (Switching taps in the middle of a sentence leaves a
@@ -618,7 +623,7 @@ struct b200_engine {
             const int grid = tail_ipw > 0 ? (int)((items + ST_WARPS * tail_ipw - 1) / (ST_WARPS * tail_ipw)) : (int)std::min<long long>((long long)tail_ctas_per_sm * sms, (items + ST_WARPS - 1) / ST_WARPS);
             launch_k(pdl_active, seanet_tail_kernel, dim3(grid), dim3(ST_THREADS), ST_SMEM_BYTES, stream, sp);
             launch_k(pdl_active, pcm_combine_kernel, dim3((unsigned)(((long long)n * T3 + 255) / 256)), dim3(256), (size_t)0, stream, (const float*)dtail, 1922LL * ST_DROW, slot0, n, T3,
-                     (const float*)c11.b, pcm);
+                     (const float*)c11.b, pcm_out);
             launch_k(pdl_active, shift_states_kernel, dim3(n, shifts.n), dim3(128), (size_t)(0), stream, shifts, slot0, mimi_off);
             launches += 3;
         } else if (on(5)) {
@@ -628,7 +633,7 @@ struct b200_engine {
           e.act = ACT_ELU; e.out2 = buf11 + slot0 * s11; e.out2_map = smap(s11, 64, 2 * 64); e.out2_type = OUT2_F16;
           gemm<__half>(buf9b + slot0 * s9b, smap(s9b, 64, 0), T3, r9b.w, r9b.wk, n * T3, r9b.N, r9b.K, e); }
             const int Rr = n * T3;
-            launch_k(pdl_active, conv_n1_kernel, dim3((Rr * 4 + 255) / 256), dim3(256), (size_t)(0), stream, buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm + (long long)slot0 * FRAME);
+            launch_k(pdl_active, conv_n1_kernel, dim3((Rr * 4 + 255) / 256), dim3(256), (size_t)(0), stream, buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm_out + (long long)slot0 * FRAME);
             launch_k(pdl_active, shift_states_kernel, dim3(n, shifts.n), dim3(128), (size_t)(0), stream, shifts, slot0, mimi_off);
             launches += 2;
         }
@@ -734,7 +739,7 @@ struct b200_engine {
             else mimi(slot0, n, mx2[par], part == ALL_PARTS ? -1 : part);
         };
         if (!cfg.cuda_graphs || profiling || taps_on) { body(); return; }
-        const auto gkey = std::make_tuple((kind * 2 + par) * 16 + part, slot0, n, injected ? 1 : 0, (kind == 0 || kind == 2) ? dec_grid_items : 0);
+        const auto gkey = std::make_tuple((kind * 2 + par) * 16 + part, slot0, n, (injected ? 1 : 0) | (pcm_out != pcm ? 2 : 0), (kind == 0 || kind == 2) ? dec_grid_items : 0);
         if (!graphs.count(gkey)) { graphs[gkey].last_use = ++graph_clock; evict_graphs(); }
         GraphEntry& g = graphs[gkey];
         g.last_use = ++graph_clock;
@@ -762,17 +767,25 @@ struct b200_engine {
 
     void mimi_chunk_on_side(const PendingFrame& f, int chunk) {
         std::swap(stream, stream_m); tc->cur_ws = 1;          // the Mimi stream has its own split-K workspace
+        if (f.tag >= 0) {
+            pcm_out = pcm_alt[f.par];
+            if ((chunk == ALL_PARTS || chunk == 0) && ev_copy_valid[f.par]) PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_copy[f.par], 0));   // frame t-2's copy read this buffer
+        }
         run_graphed(3, f.slot0, f.n, false, f.par, chunk);
+        pcm_out = pcm;
         std::swap(stream, stream_m); tc->cur_ws = 0;
     }
     void finish_mimi_frame(const PendingFrame& f) {
         PTTS_CUDA_CHECK(cudaEventRecord(ev_mimi[f.par], stream_m));
         ev_mimi_valid[f.par] = true; mimi_pending = true; last_mimi_par = f.par;
-        if (f.tag >= 0) {   // b200_submit frame: its PCM copy follows its Mimi decode on the Mimi stream
+        if (f.tag >= 0) {   // b200_submit frame: its PCM copy runs on the copy stream behind its Mimi decode (join_mimi covers it through ev_copy)
             auto& pd = pend[f.tag & 3];
-            PTTS_CUDA_CHECK(cudaMemcpyAsync(pd.pcm, pcm + (size_t)f.slot0 * FRAME, (size_t)f.n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, stream_m));
-            PTTS_CUDA_CHECK(cudaEventRecord(pd.done_mimi, stream_m));
-            PTTS_CUDA_CHECK(cudaEventRecord(ev_mimi[f.par], stream_m));      // later joins must cover the copy as well
+            PTTS_CUDA_CHECK(cudaEventRecord(ev_dec[f.par], stream_m));
+            PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream_c, ev_dec[f.par], 0));
+            PTTS_CUDA_CHECK(cudaMemcpyAsync(pd.pcm, pcm_alt[f.par] + (size_t)f.slot0 * FRAME, (size_t)f.n * FRAME * sizeof(float), cudaMemcpyDeviceToHost, stream_c));
+            PTTS_CUDA_CHECK(cudaEventRecord(pd.done_mimi, stream_c));
+            PTTS_CUDA_CHECK(cudaEventRecord(ev_copy[f.par], stream_c));
+            ev_copy_valid[f.par] = true; last_copy_par = f.par;
         }
     }
     // Enqueue the whole Mimi decode of the pending frame now (no interleaving partner).
@@ -794,6 +807,7 @@ struct b200_engine {
         if (reset_pending) { PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_reset, 0)); reset_pending = false; }
         if (!mimi_pending) return;
         if (ev_mimi_valid[last_mimi_par]) PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_mimi[last_mimi_par], 0));
+        if (last_copy_par >= 0) { PTTS_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_copy[last_copy_par], 0)); last_copy_par = -1; }
         mimi_pending = false;
     }
 
@@ -937,11 +951,14 @@ int b200_engine_create(const b200_config* cfg, b200_engine** out) {
         PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, hi));
         PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_m, cudaStreamNonBlocking, lo));
         PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_t, cudaStreamNonBlocking, hi));
+        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_c, cudaStreamNonBlocking, lo));
         PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
         PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) {
             PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_main[i], cudaEventDisableTiming));
             PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_mimi[i], cudaEventDisableTiming));
+            PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_dec[i], cudaEventDisableTiming));
+            PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming));
         }
         for (auto& ev : e->ev_seg) PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_begin, cudaEventDisableTiming));
@@ -961,7 +978,7 @@ void b200_engine_destroy(b200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
-    cudaStreamSynchronize(e->stream_m);
+    cudaStreamSynchronize(e->stream_m); cudaStreamSynchronize(e->stream_c);
     cudaStreamSynchronize(e->stream_t);
     for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (void* p : e->allocs) cudaFree(p);
@@ -974,10 +991,10 @@ void b200_engine_destroy(b200_engine* e) {
     for (auto& ps : e->pins) { if (ps.p) cudaFreeHost(ps.p); if (ps.ev) cudaEventDestroy(ps.ev); }
     if (e->ev_begin) cudaEventDestroy(e->ev_begin); if (e->ev_reset) cudaEventDestroy(e->ev_reset);
     tc_plan_cache_destroy(e->tc);
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(e->ev_main[i]); cudaEventDestroy(e->ev_mimi[i]); }
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(e->ev_main[i]); cudaEventDestroy(e->ev_mimi[i]); cudaEventDestroy(e->ev_dec[i]); cudaEventDestroy(e->ev_copy[i]); }
     for (auto& ev : e->ev_seg) cudaEventDestroy(ev);
     cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join);
-    cudaStreamDestroy(e->stream); cudaStreamDestroy(e->stream_m); cudaStreamDestroy(e->stream_t);
+    cudaStreamDestroy(e->stream); cudaStreamDestroy(e->stream_m); cudaStreamDestroy(e->stream_t); cudaStreamDestroy(e->stream_c);
     delete e;
 }
 
@@ -1150,7 +1167,8 @@ int b200_finalize_weights(b200_engine* e) {
     e->buf9a = e->dalloc<__half>((size_t)S * 1922 * 64); e->buf9b = e->dalloc<__half>((size_t)S * 1920 * 64);   // 32 channels zero-padded to 64 (K % 64 == 0 for the tensor-core path)
     e->buf11 = e->dalloc<__half>((size_t)S * 1922 * 64);
     e->y3 = e->dalloc<float>((size_t)S * 96 * 256); e->y6 = e->dalloc<float>((size_t)S * 480 * 128); e->y9 = e->dalloc<float>((size_t)S * 1920 * 64);
-    e->pcm = e->dalloc<float>((size_t)S * FRAME);
+    e->pcm = e->dalloc<float>((size_t)S * FRAME); e->pcm_out = e->pcm;
+    for (int i = 0; i < 2; i++) e->pcm_alt[i] = e->dalloc<float>((size_t)S * FRAME);
     e->shifts.n = 9;
     e->shifts.d[0] = {e->buf0, 22LL * 512, 6, 16, 512};
     e->shifts.d[1] = {e->buf2, 17LL * e->C2, 1, 16, e->C2};
@@ -1374,6 +1392,7 @@ int b200_sync(b200_engine* e) {
     e->flush_pending();                                      // a frame whose Mimi decode was waiting for an interleaving partner
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream_m));
+    PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream_c));
     PTTS_CUDA_CHECK(cudaGetLastError());
     return B200_OK;
 }
