@@ -46,6 +46,7 @@ struct b200_engine {
     // bound small GEMMs + the HBM-bound KV stream) runs on the main stream. Hand-off buffer mx2[t & 1], events per parity.
     cudaStream_t stream_m = nullptr;
     cudaStream_t stream_c = nullptr;     // device->host PCM copies of b200_submit frames (beside the next frame's Mimi decode instead of in front of it)
+    cudaStream_t stream_n = nullptr;     // host->device noise uploads of b200_submit (its own stream: behind a PCM copy they would wait for a Mimi decode)
     cudaStream_t stream_t = nullptr;     // forked branch of the main stream: the shared-prefix tile kernel runs beside the per-utterance KV stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool tma_epilogue_allowed = getenv("PTTS_B200_TMA_EPILOGUE") ? atoi(getenv("PTTS_B200_TMA_EPILOGUE")) != 0 : true;   // tuning hook
@@ -154,6 +155,9 @@ struct b200_engine {
     // b200_submit frames decode into pcm_alt[frame parity] so that the copy of frame t can run while frame t+1 is decoded; every other path
     // (b200_step, b200_step_enqueue + b200_device_ptr("pcm"), b200_mimi_decode) writes `pcm`. pcm_out = the buffer the enqueued decode writes.
     float* pcm_alt[2] = {nullptr, nullptr}; float* pcm_out = nullptr;
+    // Same idea for the injected noise of b200_submit: uploaded on the copy stream into noise_alt[frame parity] (ahead of the step, not between two
+    // graph launches of the main stream); noise_src = the buffer the enqueued step reads.
+    float* noise_alt[2] = {nullptr, nullptr}; float* noise_src = nullptr; cudaEvent_t ev_noise[2] = {nullptr, nullptr};
     cudaEvent_t ev_dec[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr}; bool ev_copy_valid[2] = {false, false}; int last_copy_par = -1;
     float* dtail = nullptr;   // [slot][2 + 1920][4] per-row tap products of the output conv (seanet_tail.cuh), two carried rows in front
     bool fused_tail_allowed = getenv("PTTS_B200_FUSED_TAIL") ? atoi(getenv("PTTS_B200_FUSED_TAIL")) != 0 : true;   // tuning hook
@@ -664,7 +668,7 @@ struct b200_engine {
         p.cond = {cond_embed.w, cond_embed.b}; p.ada = {ada_all.w, ada_all.b}; p.fin = {final_lin.w, final_lin.b}; p.ada_out = ada_all.out; p.t_combined = t_combined;
         for (int r = 0; r < N_RES; r++) { p.rb[r].lnw = rb[r].lnw; p.rb[r].lnb = rb[r].lnb; p.rb[r].m0 = {rb[r].mlp0.w, rb[r].mlp0.b}; p.rb[r].m2 = {rb[r].mlp2.w, rb[r].mlp2.b}; }
         p.fnw = fnw; p.fnb = fnb; p.input_proj_t = input_proj_t; p.input_proj_b = input_proj.b;
-        p.injected = injected ? noise_inj : nullptr; p.seed = d_seed; p.temp = temp; p.gen_step = gen_step; p.rng_id = rng_id;
+        p.injected = injected ? noise_src : nullptr; p.seed = d_seed; p.temp = temp; p.gen_step = gen_step; p.rng_id = rng_id;
         p.h = h; p.q = q; p.ws_ml = af_ml; p.ws_acc = af_acc; p.mod = mod; p.xh = xh; p.noise_f32 = noise_f32; p.latent = latent; p.eos = eos;
         p.ff_bf = ff_bf; p.sy_bf = sy_bf; p.h1_bf = h1_bf; p.barrier = pf_barrier;
         cudaLaunchConfig_t lc{};
@@ -701,7 +705,7 @@ struct b200_engine {
         if (seg >= 0 && seg != N_SEG - 1) return;
         seg_end(s_flow);
         const int s_head = seg_begin(2);
-        launch_k(pdl_active, noise_inproj_kernel, dim3(n), dim3(128), (size_t)(0), stream, slot0, n, (const float*)(injected ? noise_inj : nullptr), (const unsigned long long*)d_seed,
+        launch_k(pdl_active, noise_inproj_kernel, dim3(n), dim3(128), (size_t)(0), stream, slot0, n, (const float*)(injected ? noise_src : nullptr), (const unsigned long long*)d_seed,
                  (const float*)temp, (const int*)gen_step, (const unsigned int*)rng_id, noise_f32, (const __nv_bfloat16*)input_proj_t, (const float*)input_proj.b, xh);
         flow_head(n);
         launches += 1;
@@ -739,7 +743,7 @@ struct b200_engine {
             else mimi(slot0, n, mx2[par], part == ALL_PARTS ? -1 : part);
         };
         if (!cfg.cuda_graphs || profiling || taps_on) { body(); return; }
-        const auto gkey = std::make_tuple((kind * 2 + par) * 16 + part, slot0, n, (injected ? 1 : 0) | (pcm_out != pcm ? 2 : 0), (kind == 0 || kind == 2) ? dec_grid_items : 0);
+        const auto gkey = std::make_tuple((kind * 2 + par) * 16 + part, slot0, n, (injected ? 1 : 0) | (pcm_out != pcm ? 2 : 0) | (noise_src != noise_inj ? 4 : 0), (kind == 0 || kind == 2) ? dec_grid_items : 0);
         if (!graphs.count(gkey)) { graphs[gkey].last_use = ++graph_clock; evict_graphs(); }
         GraphEntry& g = graphs[gkey];
         g.last_use = ++graph_clock;
@@ -952,6 +956,7 @@ int b200_engine_create(const b200_config* cfg, b200_engine** out) {
         PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_m, cudaStreamNonBlocking, lo));
         PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_t, cudaStreamNonBlocking, hi));
         PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_c, cudaStreamNonBlocking, lo));
+        PTTS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_n, cudaStreamNonBlocking, hi));
         PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
         PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) {
@@ -959,6 +964,7 @@ int b200_engine_create(const b200_config* cfg, b200_engine** out) {
             PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_mimi[i], cudaEventDisableTiming));
             PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_dec[i], cudaEventDisableTiming));
             PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming));
+            PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_noise[i], cudaEventDisableTiming));
         }
         for (auto& ev : e->ev_seg) PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_begin, cudaEventDisableTiming));
@@ -991,10 +997,10 @@ void b200_engine_destroy(b200_engine* e) {
     for (auto& ps : e->pins) { if (ps.p) cudaFreeHost(ps.p); if (ps.ev) cudaEventDestroy(ps.ev); }
     if (e->ev_begin) cudaEventDestroy(e->ev_begin); if (e->ev_reset) cudaEventDestroy(e->ev_reset);
     tc_plan_cache_destroy(e->tc);
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(e->ev_main[i]); cudaEventDestroy(e->ev_mimi[i]); cudaEventDestroy(e->ev_dec[i]); cudaEventDestroy(e->ev_copy[i]); }
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(e->ev_main[i]); cudaEventDestroy(e->ev_mimi[i]); cudaEventDestroy(e->ev_dec[i]); cudaEventDestroy(e->ev_copy[i]); cudaEventDestroy(e->ev_noise[i]); }
     for (auto& ev : e->ev_seg) cudaEventDestroy(ev);
     cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join);
-    cudaStreamDestroy(e->stream); cudaStreamDestroy(e->stream_m); cudaStreamDestroy(e->stream_t); cudaStreamDestroy(e->stream_c);
+    cudaStreamDestroy(e->stream); cudaStreamDestroy(e->stream_m); cudaStreamDestroy(e->stream_t); cudaStreamDestroy(e->stream_c); cudaStreamDestroy(e->stream_n);
     delete e;
 }
 
@@ -1152,7 +1158,8 @@ int b200_finalize_weights(b200_engine* e) {
     e->c_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_MODEL); e->sy_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW);
     e->hn_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW); e->h1_bf = e->dalloc<__nv_bfloat16>((size_t)S * D_FLOW);
     e->eos = e->dalloc<float>(S); e->eos_out = e->dalloc<float>(S); e->mod = e->dalloc<float>((size_t)S * e->ada_all.out); e->xh = e->dalloc<float>((size_t)S * D_FLOW);
-    e->noise_f32 = e->dalloc<float>((size_t)S * LDIM); e->noise_inj = e->dalloc<float>((size_t)S * LDIM); e->latent = e->dalloc<float>((size_t)S * LDIM);
+    e->noise_f32 = e->dalloc<float>((size_t)S * LDIM); e->noise_inj = e->dalloc<float>((size_t)S * LDIM); e->noise_src = e->noise_inj;
+    for (int i = 0; i < 2; i++) e->noise_alt[i] = e->dalloc<float>((size_t)S * LDIM); e->latent = e->dalloc<float>((size_t)S * LDIM);
     e->produced = e->dalloc<int>(S);
     e->d_seed = e->dalloc<unsigned long long>(1);
     PTTS_CUDA_CHECK(cudaMemcpyAsync(e->d_seed, &e->seed, sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
@@ -1455,9 +1462,19 @@ int b200_submit(b200_engine* e, int slot0, int n, const float* noise) {
     if (!pd.done_main) { PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&pd.done_main, cudaEventDisableTiming)); PTTS_CUDA_CHECK(cudaEventCreateWithFlags(&pd.done_mimi, cudaEventDisableTiming)); }
     if (noise) {
         memcpy(pd.noise, noise, (size_t)n * LDIM * sizeof(float));
-        PTTS_CUDA_CHECK(cudaMemcpyAsync(e->noise_inj, pd.noise, (size_t)n * LDIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        if (e->cfg.overlap && e->cfg.cuda_graphs && !e->profiling && !e->taps_on) {       // the step will be pipelined with parity pipe_t & 1 (run_step)
+            const int par = (int)(e->pipe_t & 1);
+            PTTS_CUDA_CHECK(cudaStreamWaitEvent(e->stream_n, e->ev_main[par], 0));         // frame t-2 has read this buffer
+            PTTS_CUDA_CHECK(cudaMemcpyAsync(e->noise_alt[par], pd.noise, (size_t)n * LDIM * sizeof(float), cudaMemcpyHostToDevice, e->stream_n));
+            PTTS_CUDA_CHECK(cudaEventRecord(e->ev_noise[par], e->stream_n));
+            PTTS_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_noise[par], 0));
+            e->noise_src = e->noise_alt[par];
+        } else {
+            PTTS_CUDA_CHECK(cudaMemcpyAsync(e->noise_inj, pd.noise, (size_t)n * LDIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        }
     }
     e->run_step(slot0, n, noise != nullptr, (long long)e->submit_t);
+    e->noise_src = e->noise_inj;
     PTTS_CUDA_CHECK(cudaMemcpyAsync(pd.produced, e->produced, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     PTTS_CUDA_CHECK(cudaEventRecord(pd.done_main, e->stream));
     if (!e->last_step_piped) {   // non-pipelined step (overlap off): the frame is already decoded on the main stream
