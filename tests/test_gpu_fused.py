@@ -94,3 +94,26 @@ def test_fused_tail_state_resets_with_the_sentence(P, model_dir):
     eng.mimi_reset(0, B)
     again = eng.mimi_decode(0, B, lat)
     assert np.array_equal(first, again)
+
+
+def test_steps_enqueue_equals_repeated_step_enqueue(P, model_dir):
+    """b200_steps_enqueue(count) is count native b200_step_enqueue calls: same positions and, with the device RNG, the same next frame."""
+    outs = []
+    for native in (False, True):
+        ctx = P.Context(model_dir, max_slots=4, kv_capacity=512)
+        eng = ctx.engine
+        st = ctx.stream("cosette", temp=0.7)
+        toks = [ctx.tokenize(TEXTS[i % 3]) for i in range(4)]
+        eng.set_seed(11)
+        eng.begin_sentences([0, 1, 2, 3], [st.voice] * 4, toks, [600] * 4, [1 << 20] * 4, [0.7] * 4)
+        if native:
+            eng.steps_enqueue(0, 4, 3)
+        else:
+            for _ in range(3):
+                eng.step_enqueue(0, 4)
+        eng.sync()
+        pos = [eng.slot_position(s) for s in range(4)]
+        pcm, prod, lat, eos = eng.step(0, 4, None)
+        outs.append((pos, lat.copy(), pcm.copy()))
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
