@@ -545,6 +545,11 @@ struct b200_engine {
     // Mimi decoder body for slots [slot0, slot0+n) from the front end's rows in `xbuf` (reference models/mimi.h:85-104).
     // chunk < 0: everything; otherwise one of N_MCHUNK pieces of roughly equal duration (run_step interleaves them with the FlowLM segments)
     static constexpr int N_MCHUNK = 6;
+    void mimi_ln(const float* x, int R, const float* w, const float* b) {      // LayerNorm(eps 0) of the Mimi transformer rows -> mn_bf
+        const int BIG = 1 << 30;
+        if (R >= 512) launch_k(pdl_active, layernorm_rows_kernel<M_DIM>, dim3((R + 7) / 8), dim3(256), (size_t)0, stream, x, R, 0.0f, w, b, mn_bf);
+        else launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3(R), dim3(M_DIM / 4), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, w, b, nullptr, nullptr, 0, mn_bf, nullptr);
+    }
     void mimi(int slot0, int n, float* xbuf, int chunk = -1) {
         const int BIG = 1 << 30, R = n * M_T;
         auto on = [&](int c) { return chunk < 0 || chunk == c; };
@@ -561,7 +566,7 @@ struct b200_engine {
             Epi e; e.mode = EPI_MIMI_QKV; e.row_slot = mrow_slot; e.row_pos = mrow_pos; e.cs = mcs; e.kv_slot_stride = mkv_slot_stride;
             e.kcache = mkc + l * mkv_layer_stride; e.vcache = mvc + l * mkv_layer_stride; e.q_out_bf16 = mq_bf;
             if (on(c_qkv)) {
-                launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3(R), dim3(M_DIM / 4), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n1w, L.n1b, nullptr, nullptr, 0, mn_bf, nullptr);
+                mimi_ln(x, R, L.n1w, L.n1b);
                 launches++;
                 lin(mn_bf, L.in_proj, R, e);
             }
@@ -574,7 +579,7 @@ struct b200_engine {
                 lin(matt_bf, L.out_proj, R, eo);
             }
             if (on(c_mlp)) {
-                launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3(R), dim3(M_DIM / 4), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, L.n2w, L.n2b, nullptr, nullptr, 0, mn_bf, nullptr);
+                mimi_ln(x, R, L.n2w, L.n2b);
                 launches++;
                 Epi e1; e1.out2 = mff_bf; e1.out2_map = rows(M_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
                 lin(mn_bf, L.lin1, R, e1);

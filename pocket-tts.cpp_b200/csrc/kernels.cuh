@@ -89,6 +89,37 @@ __global__ void __launch_bounds__(C / 4) layernorm_kernel(const float* __restric
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)row * C + col) = make_float4(y[0], y[1], y[2], y[3]);
 }
 
+// Many-row variant (Mimi: 16 rows per utterance, 4096 rows at batch 256): one WARP per row, eight rows per CTA, the row in registers
+// (C / 32 values per lane), shuffles only. Same arithmetic (two-pass ggml_norm); contiguous [R][C] f32 in, bf16 out. The one-CTA-per-row
+// kernel above needs 4096 CTAs of 128 threads and two block barriers for 2 KB of data per row (8 us per launch).
+template <int C>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, int R, float eps, const float* __restrict__ w, const float* __restrict__ b,
+                                                             __nv_bfloat16* __restrict__ out_bf16) {
+    pdl_prologue();
+    constexpr int NV = C / 128;                                  // float4 per lane
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= R) return;
+    const float* xr = x + (long long)row * C;
+    float4 v[NV]; float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; j++) { v[j] = *reinterpret_cast<const float4*>(xr + 128 * j + lane * 4); s += v[j].x + v[j].y + v[j].z + v[j].w; }
+    const float mean = warp_sum(s) / C;
+    float s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; j++) { v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean; s2 += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w; }
+    const float rs = 1.0f / sqrtf(warp_sum(s2) / C + eps);
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        const int c = 128 * j + lane * 4;
+        float y[4] = {v[j].x * rs, v[j].y * rs, v[j].z * rs, v[j].w * rs};
+        if (w) { const float4 ww = *reinterpret_cast<const float4*>(w + c); y[0] *= ww.x; y[1] *= ww.y; y[2] *= ww.z; y[3] *= ww.w; }
+        if (b) { const float4 bb = *reinterpret_cast<const float4*>(b + c); y[0] += bb.x; y[1] += bb.y; y[2] += bb.z; y[3] += bb.w; }
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
+        uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&p0); pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(out_bf16 + (long long)row * C + c) = pk;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // FlowLM attention (reference modules/transformer.h:157-199, src/torch.h:128-150: scale 1/8, causal, softmax with f32
 // probabilities, f32 PV). Two kernels share the work:
