@@ -67,6 +67,11 @@ struct b200_engine {
     bool debug_skip_mimi = getenv("PTTS_B200_DEBUG_SKIP_MIMI") != nullptr;   // diagnosis only: time the FlowLM graph alone
     int af_splits_override = getenv("PTTS_B200_AF_SPLITS") ? atoi(getenv("PTTS_B200_AF_SPLITS")) : 0;   // tuning hook
     void set_pdl(bool on) { pdl_active = on; if (tc) tc->pdl = on; }
+    // "Light" PDL: above 128 utterances only the small glue kernels (norms, split-K reductions, stop rule, state shifts: a few hundred threads, no
+    // TMEM, little shared memory) are launched programmatically. Their early-resident CTAs cost nothing while the previous GEMM drains; the heavy
+    // kernels keep plain stream order (with PDL on everything the waiting GEMM / attention CTAs of one stream starve the other: 1.09 ms per step).
+    bool pdl_light = false, pdl_light_allowed = getenv("PTTS_B200_PDL_LIGHT") ? atoi(getenv("PTTS_B200_PDL_LIGHT")) != 0 : true;
+    bool pdl_l() const { return pdl_active || pdl_light; }
     long long launches = 0;
     uint64_t seed = 0; unsigned long long* d_seed = nullptr;
     // CUDA graphs of the per-frame step, keyed by (kind, slot0, n, injected); first use runs eagerly (warm-up), second captures
@@ -469,7 +474,7 @@ struct b200_engine {
         LnFuse f2; f2.w = L.n2w; f2.b = L.n2b; f2.eps = 1e-5f; f2.out = n_bf;
         const bool fuse = ln_in_gemv(R);
         if (!lin(att_bf, L.out_proj, R, eo, &f2) && !fuse) {
-            launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
+            launch_k(pdl_l(), layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, L.n2w, L.n2b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
         }
         Epi e1; e1.out2 = ff_bf; e1.out2_map = rows(D_FF); e1.out2_type = OUT2_BF16; e1.act = ACT_GELU;
         if (fuse) { LnArgs a; a.w = L.n2w; a.b = L.n2b; a.eps = 1e-5f; lin_ln(h, a, L.lin1, R, e1); }
@@ -478,7 +483,7 @@ struct b200_engine {
         if (l + 1 < N_LAYERS) {
             LnFuse f1; f1.w = fl[l + 1].n1w; f1.b = fl[l + 1].n1b; f1.eps = 1e-5f; f1.out = n_bf;
             if (!lin(ff_bf, L.lin2, R, e2, &f1) && !fuse) {    // fused: the next in_proj normalises h itself (flow_attn_part)
-                launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, fl[l + 1].n1w, fl[l + 1].n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
+                launch_k(pdl_l(), layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, fl[l + 1].n1w, fl[l + 1].n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++;
             }
         } else {
             lin(ff_bf, L.lin2, R, e2);
@@ -487,7 +492,7 @@ struct b200_engine {
     }
     void flow_forward(int R, bool ln1_done = false) {              // ln1_done: layer 0's norm1 already in n_bf (decode: flow_in_kernel)
         const int BIG = 1 << 30;
-        if (!ln1_done) { launch_k(pdl_active, layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, fl[0].n1w, fl[0].n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++; }
+        if (!ln1_done) { launch_k(pdl_l(), layernorm_kernel<D_MODEL>, dim3(R), dim3(D_MODEL / 4), (size_t)(0), stream, h, rows(D_MODEL), BIG, R, 1e-5f, fl[0].n1w, fl[0].n1b, nullptr, nullptr, 0, n_bf, nullptr); launches++; }
         for (int l = 0; l < N_LAYERS; l++) { flow_attn_part(l, R); flow_chain_part(l, R); }
     }
 
@@ -497,7 +502,7 @@ struct b200_engine {
     // out_norm + EOS + 1-step LSD head over R rows of `h` (reference models/flow_lm.h:114-142, modules/mlp.h:233-251).
     void flow_head(int R) {
         const int BIG = 1 << 30;
-        launch_k(pdl_active, head_pre_kernel, dim3(R), dim3(256), (size_t)(0), stream, h, R, onw, onb, w_eos, b_eos, c_bf, eos);
+        launch_k(pdl_l(), head_pre_kernel, dim3(R), dim3(256), (size_t)(0), stream, h, R, onw, onb, w_eos, b_eos, c_bf, eos);
         // y = t_combined + cond_embed(c); sy = silu(y)
         Epi ec; ec.resid = t_combined; ec.resid_map = RowMap{}; ec.out2 = sy_bf; ec.out2_map = rows(D_FLOW); ec.out2_type = OUT2_BF16; ec.act = ACT_SILU;
         lin(c_bf, cond_embed, R, ec);
@@ -519,7 +524,7 @@ struct b200_engine {
             Epi e0; e0.out2 = h1_bf; e0.out2_map = rows(D_FLOW); e0.out2_type = OUT2_BF16; e0.act = ACT_SILU;
             if (ln_in_gemv(R)) { LnArgs a; a.w = rb[r].lnw; a.b = rb[r].lnb; a.eps = 1e-6f; a.shift = m; a.scale = m + D_FLOW; a.mod_ld = ada_all.out; lin_ln(xh, a, rb[r].mlp0, R, e0); }
             else {
-                launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3(R), dim3(D_FLOW / 4), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, rb[r].lnw, rb[r].lnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
+                launch_k(pdl_l(), layernorm_kernel<D_FLOW>, dim3(R), dim3(D_FLOW / 4), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, rb[r].lnw, rb[r].lnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
                 launches++;
                 lin(hn_bf, rb[r].mlp0, R, e0);
             }
@@ -530,7 +535,7 @@ struct b200_engine {
         Epi ef; ef.resid = noise_f32; ef.resid_map = rows(LDIM); ef.out = latent; ef.out_map = rows(LDIM);
         if (ln_in_gemv(R)) { LnArgs a; a.w = fnw; a.b = fnb; a.eps = 1e-6f; a.shift = m; a.scale = m + D_FLOW; a.mod_ld = ada_all.out; lin_ln(xh, a, final_lin, R, ef); }
         else {
-            launch_k(pdl_active, layernorm_kernel<D_FLOW>, dim3(R), dim3(D_FLOW / 4), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, fnw, fnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
+            launch_k(pdl_l(), layernorm_kernel<D_FLOW>, dim3(R), dim3(D_FLOW / 4), (size_t)(0), stream, xh, rows(D_FLOW), BIG, R, 1e-6f, fnw, fnb, m, m + D_FLOW, ada_all.out, hn_bf, nullptr);
             launches++;
             lin(hn_bf, final_lin, R, ef);
         }
@@ -539,7 +544,7 @@ struct b200_engine {
 
     // Mimi front end (latent -> 16 transformer input rows, written to `xbuf`), reference models/mimi.h:77-83 + modules/conv.h:283-331.
     void mimi_front(int slot0, int n, float* xbuf) {
-        launch_k(pdl_active, mimi_front_kernel, dim3(n), dim3(M_DIM), (size_t)(0), stream, slot0, lat_f32, emb_std, emb_mean, wq, wup, bup, e_prev, xbuf);
+        launch_k(pdl_l(), mimi_front_kernel, dim3(n), dim3(M_DIM), (size_t)(0), stream, slot0, lat_f32, emb_std, emb_mean, wq, wup, bup, e_prev, xbuf);
         launches++;
     }
     // Mimi decoder body for slots [slot0, slot0+n) from the front end's rows in `xbuf` (reference models/mimi.h:85-104).
@@ -547,14 +552,14 @@ struct b200_engine {
     static constexpr int N_MCHUNK = 6;
     void mimi_ln(const float* x, int R, const float* w, const float* b) {      // LayerNorm(eps 0) of the Mimi transformer rows -> mn_bf
         const int BIG = 1 << 30;
-        if (R >= 512) launch_k(pdl_active, layernorm_rows_kernel<M_DIM>, dim3((R + 7) / 8), dim3(256), (size_t)0, stream, x, R, 0.0f, w, b, mn_bf);
-        else launch_k(pdl_active, layernorm_kernel<M_DIM>, dim3(R), dim3(M_DIM / 4), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, w, b, nullptr, nullptr, 0, mn_bf, nullptr);
+        if (R >= 512) launch_k(pdl_l(), layernorm_rows_kernel<M_DIM>, dim3((R + 7) / 8), dim3(256), (size_t)0, stream, x, R, 0.0f, w, b, mn_bf);
+        else launch_k(pdl_l(), layernorm_kernel<M_DIM>, dim3(R), dim3(M_DIM / 4), (size_t)(0), stream, x, rows(M_DIM), BIG, R, 0.0f, w, b, nullptr, nullptr, 0, mn_bf, nullptr);
     }
     void mimi(int slot0, int n, float* xbuf, int chunk = -1) {
         const int BIG = 1 << 30, R = n * M_T;
         auto on = [&](int c) { return chunk < 0 || chunk == c; };
         if (on(0)) {
-            launch_k(pdl_active, prepare_mimi_kernel, dim3((n * M_T * 32 + 255) / 256), dim3(256), (size_t)(0), stream, slot0, n, (const int*)mimi_off, (const float*)freq_mimi, mrow_slot, mrow_pos, mcs);
+            launch_k(pdl_l(), prepare_mimi_kernel, dim3((n * M_T * 32 + 255) / 256), dim3(256), (size_t)(0), stream, slot0, n, (const int*)mimi_off, (const float*)freq_mimi, mrow_slot, mrow_pos, mcs);
             launches++;
         }
         float* x = xbuf + (long long)slot0 * M_T * M_DIM;
@@ -631,9 +636,9 @@ struct b200_engine {
             const int sms = tc ? tc->num_sms : 148;
             const int grid = tail_ipw > 0 ? (int)((items + ST_WARPS * tail_ipw - 1) / (ST_WARPS * tail_ipw)) : (int)std::min<long long>((long long)tail_ctas_per_sm * sms, (items + ST_WARPS - 1) / ST_WARPS);
             launch_k(pdl_active, seanet_tail_kernel, dim3(grid), dim3(ST_THREADS), ST_SMEM_BYTES, stream, sp);
-            launch_k(pdl_active, pcm_combine_kernel, dim3((unsigned)(((long long)n * T3 + 255) / 256)), dim3(256), (size_t)0, stream, (const float*)dtail, 1922LL * ST_DROW, slot0, n, T3,
+            launch_k(pdl_l(), pcm_combine_kernel, dim3((unsigned)(((long long)n * T3 + 255) / 256)), dim3(256), (size_t)0, stream, (const float*)dtail, 1922LL * ST_DROW, slot0, n, T3,
                      (const float*)c11.b, pcm_out);
-            launch_k(pdl_active, shift_states_kernel, dim3(n, shifts.n), dim3(128), (size_t)(0), stream, shifts, slot0, mimi_off);
+            launch_k(pdl_l(), shift_states_kernel, dim3(n, shifts.n), dim3(128), (size_t)(0), stream, shifts, slot0, mimi_off);
             launches += 3;
         } else if (on(5)) {
         { Epi e; e.rps = T3; e.bias = r9a.b; e.act = ACT_ELU; e.out2 = buf9b + slot0 * s9b; e.out2_map = smap(s9b, 64, 0); e.out2_type = OUT2_F16;
@@ -642,8 +647,8 @@ struct b200_engine {
           e.act = ACT_ELU; e.out2 = buf11 + slot0 * s11; e.out2_map = smap(s11, 64, 2 * 64); e.out2_type = OUT2_F16;
           gemm<__half>(buf9b + slot0 * s9b, smap(s9b, 64, 0), T3, r9b.w, r9b.wk, n * T3, r9b.N, r9b.K, e); }
             const int Rr = n * T3;
-            launch_k(pdl_active, conv_n1_kernel, dim3((Rr * 4 + 255) / 256), dim3(256), (size_t)(0), stream, buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm_out + (long long)slot0 * FRAME);
-            launch_k(pdl_active, shift_states_kernel, dim3(n, shifts.n), dim3(128), (size_t)(0), stream, shifts, slot0, mimi_off);
+            launch_k(pdl_l(), conv_n1_kernel, dim3((Rr * 4 + 255) / 256), dim3(256), (size_t)(0), stream, buf11 + slot0 * s11, smap(s11, 64, 0), T3, c11.w, c11.b, Rr, c11.K, pcm_out + (long long)slot0 * FRAME);
+            launch_k(pdl_l(), shift_states_kernel, dim3(n, shifts.n), dim3(128), (size_t)(0), stream, shifts, slot0, mimi_off);
             launches += 2;
         }
         seg_end(s_sea);
@@ -699,7 +704,7 @@ struct b200_engine {
         for (int sg = 0; sg < N_SEG; sg++) {
             if (seg >= 0 && sg != seg) continue;
             if (sg == 0) {
-                launch_k(pdl_active, flow_in_kernel, dim3(n), dim3(256), (size_t)0, stream, slot0, n, (const __nv_bfloat16*)lat_in_bf16, (const __nv_bfloat16*)input_linear_t,
+                launch_k(pdl_l(), flow_in_kernel, dim3(n), dim3(256), (size_t)0, stream, slot0, n, (const __nv_bfloat16*)lat_in_bf16, (const __nv_bfloat16*)input_linear_t,
                          (const float*)input_linear.b, (const float*)fl[0].n1w, (const float*)fl[0].n1b, h, n_bf, (const int*)cur_len, (const int*)active, (const float*)freq_flow, row_slot, row_pos, cs);
                 launches++;
             } else {
@@ -710,14 +715,14 @@ struct b200_engine {
         if (seg >= 0 && seg != N_SEG - 1) return;
         seg_end(s_flow);
         const int s_head = seg_begin(2);
-        launch_k(pdl_active, noise_inproj_kernel, dim3(n), dim3(128), (size_t)(0), stream, slot0, n, (const float*)(injected ? noise_src : nullptr), (const unsigned long long*)d_seed,
+        launch_k(pdl_l(), noise_inproj_kernel, dim3(n), dim3(128), (size_t)(0), stream, slot0, n, (const float*)(injected ? noise_src : nullptr), (const unsigned long long*)d_seed,
                  (const float*)temp, (const int*)gen_step, (const unsigned int*)rng_id, noise_f32, (const __nv_bfloat16*)input_proj_t, (const float*)input_proj.b, xh);
         flow_head(n);
         launches += 1;
         seg_end(s_head);
         set_pdl(pdl_small);
         // stop rule + latent hand-off + Mimi front end (writes the 16 transformer input rows of every slot to xbuf)
-        launch_k(pdl_active, step_front_kernel, dim3(n), dim3(M_DIM), (size_t)(0), stream, slot0, n, (const float*)eos, (const float*)latent, cur_len, gen_step, eos_step, (const int*)max_gen,
+        launch_k(pdl_l(), step_front_kernel, dim3(n), dim3(M_DIM), (size_t)(0), stream, slot0, n, (const float*)eos, (const float*)latent, cur_len, gen_step, eos_step, (const int*)max_gen,
                  (const int*)fae, active, lat_in_bf16, lat_f32, produced, eos_out, (const float*)emb_std, (const float*)emb_mean, (const __half*)wq, (const float*)wup, (const float*)bup, e_prev, xbuf);
         launches++;
     }
@@ -736,9 +741,12 @@ struct b200_engine {
     void run_graphed(int kind, int slot0, int n, bool injected, int par = 0, int part = 0) {
         // PDL overlaps each kernel's prologue (barrier init, TMEM allocation, weight prefetch) with its predecessor's tail: a win while
         // the step is launch/latency bound (measured +2..7 % at batch 16-128), a loss once the kernels fill the machine (-10 % at 256).
-        pdl_small = cfg.pdl >= 2 || (cfg.pdl == 1 && n <= 128);  // every kernel of the step
-        pdl_chain = cfg.pdl >= 2;
+        // cfg.pdl: 0 never, 1 up to 128 utterances, 2 always, 3 = FlowLM graph always / Mimi graph up to 128, 4 = Mimi graph always / FlowLM up to 128 (experiments)
+        const bool side = kind == 3 || kind == 1;
+        pdl_small = cfg.pdl == 2 || (cfg.pdl >= 1 && n <= 128) || (cfg.pdl == 3 && !side) || (cfg.pdl == 4 && side);
+        pdl_chain = cfg.pdl == 2 || (cfg.pdl == 3 && !side) || (cfg.pdl == 4 && side);
         set_pdl(pdl_small);
+        pdl_light = pdl_light_allowed && cfg.pdl >= 1 && !pdl_small; tc->pdl_light = pdl_light;
         // TMA-store epilogue for the large Mimi GEMMs only when no second stream runs beside them (see EPI_CLASSES in gemm_tc.cuh)
         tc->tma_epilogue = tma_epilogue_allowed && (kind == 0 || kind == 1);
         auto body = [&]() {

@@ -679,6 +679,7 @@ struct TcPlanCache {
     PFN_tmapEncodeTiled encode = nullptr;
     std::map<std::tuple<const void*, long long, long long, long long, long long, long long, int, int>, CUtensorMap> maps;   // see tc_get_map
     int num_sms = 148;
+    bool pdl_light = false;     // programmatic launch for the split-K reduction kernels only (see b200_engine::pdl_light)
     bool coreside = false;      // see tc_gemm_launch; switched on by the engine while it enqueues the two-stream pipeline
     bool coreside_allowed = true;   // PTTS_B200_CORESIDE=0: never (deep rings / two Mimi CTAs per SM everywhere)
     bool pdl = false;
@@ -913,12 +914,12 @@ inline int tc_gemm_launch(TcPlanCache* c, const T* A, RowMap amap, int a_rps, co
     if (ln_done) *ln_done = false;
     if (splits > 1) {
         if (ln_ok) {
-            if (N == 1024) launch_k(c->pdl, splitk_reduce_ln_kernel<1024>, dim3(R), dim3(256), 0, stream, (const float*)c->ws_buf[c->cur_ws], splits, (long long)R * N, R, epi, *ln);
-            else launch_k(c->pdl, splitk_reduce_ln_kernel<512>, dim3(R), dim3(128), 0, stream, (const float*)c->ws_buf[c->cur_ws], splits, (long long)R * N, R, epi, *ln);
+            if (N == 1024) launch_k(c->pdl || c->pdl_light, splitk_reduce_ln_kernel<1024>, dim3(R), dim3(256), 0, stream, (const float*)c->ws_buf[c->cur_ws], splits, (long long)R * N, R, epi, *ln);
+            else launch_k(c->pdl || c->pdl_light, splitk_reduce_ln_kernel<512>, dim3(R), dim3(128), 0, stream, (const float*)c->ws_buf[c->cur_ws], splits, (long long)R * N, R, epi, *ln);
             if (ln_done) *ln_done = true;
         } else {
             const long long quads = (long long)R * N / 4;
-            launch_k(c->pdl, splitk_reduce_kernel, dim3((unsigned)((quads + 255) / 256)), dim3(256), 0, stream, (const float*)c->ws_buf[c->cur_ws], splits, (long long)R * N, R, N, epi);
+            launch_k(c->pdl || c->pdl_light, splitk_reduce_kernel, dim3((unsigned)((quads + 255) / 256)), dim3(256), 0, stream, (const float*)c->ws_buf[c->cur_ws], splits, (long long)R * N, R, N, epi);
         }
         return 2;
     }
