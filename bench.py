@@ -263,7 +263,13 @@ def run_mode(env: Env, name: str, share: int, kv_f32: int, n_voices: int = 1, pr
 
     sampler = None
     if primary:   # clocks are sampled from the warm-up through the timed region (the timed region alone can be shorter than one sample period)
-        sampler = ClockSampler(env.local); sampler.start(); time.sleep(0.3)
+        sampler = ClockSampler(env.local); sampler.start()
+        # nvidia-smi needs 0.1-0.5 s before its first row: keep the GPU under the same load until rows arrive, then start the sentences again so
+        # that the cache length of the timed region is the configured one
+        t_s = time.time()
+        while len(sampler.rows) < 3 and time.time() - t_s < 3.0:
+            eng.steps_enqueue(0, B, 25); eng.join(); eng.sync()
+        begin(); eng.sync()
     steps_done = 0
     for _ in range(args.untimed):
         eng.step_enqueue(0, B); steps_done += 1
