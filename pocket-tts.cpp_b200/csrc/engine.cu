@@ -10,6 +10,7 @@
 #include "persistent.cuh"
 #include "head_fused.cuh"
 #include "seanet_tail.cuh"
+#include "seanet_res.cuh"
 
 #include <cuda_profiler_api.h>
 #include <nvtx3/nvToolsExt.h>
@@ -168,6 +169,11 @@ struct b200_engine {
     bool fused_tail_allowed = getenv("PTTS_B200_FUSED_TAIL") ? atoi(getenv("PTTS_B200_FUSED_TAIL")) != 0 : true;   // tuning hook
     // The tap "seanet.res9" reads the f16 a3 rows, which only the unfused launches produce. (Switching taps in the middle of a sentence leaves a
     // stale two-row output-conv state for one frame: the two paths carry it in different buffers. Debug only.)
+    // Off by default: correct (82-84 dB against the unfused launches, state handling unchanged) but SLOWER, Mimi decode 0.484 -> 0.494 ms at batch
+    // 256: at this stage the 64-channel intermediate (31 MB) and the skip tensor stay in L2 between the two tcgen05 GEMMs, so fusing them saves
+    // no HBM traffic and trades tcgen05 for mma.sync. (Stage 3, where the tensors are 4x larger than L2 can hold, is where seanet_tail.cuh pays.)
+    bool fused_res6_allowed = getenv("PTTS_B200_FUSED_RES6") ? atoi(getenv("PTTS_B200_FUSED_RES6")) != 0 : false;
+    bool use_fused_res6() const { return fused_res6_allowed && cfg.gemm_path == 0 && !cfg.convt_split; }
     int tail_ipw = getenv("PTTS_B200_TAIL_IPW") ? atoi(getenv("PTTS_B200_TAIL_IPW")) : 0;   // tuning hook: work items per warp of seanet_tail_kernel (0 = persistent)
     int tail_ctas_per_sm = getenv("PTTS_B200_TAIL_CTAS") ? atoi(getenv("PTTS_B200_TAIL_CTAS")) : 2;   // tuning hook: persistent CTAs per SM of seanet_tail_kernel
     bool use_fused_tail() const { return fused_tail_allowed && cfg.gemm_path == 0 && !taps_on; }
@@ -618,11 +624,21 @@ struct b200_engine {
         if (on(4)) { Epi e; e.rps = T1; e.bias = t5.b; e.out = y6 + slot0 * 480LL * 128; e.out_map = smap(480LL * 128, 640, 0);
           e.act = ACT_ELU; e.out2 = buf6a + slot0 * s6a; e.out2_map = smap(s6a, 640, 2 * 128); e.out2_type = OUT2_F16;
           gemm<__half>(buf5 + slot0 * s5, smap(s5, C5, 0), T1, t5.w, t5.wk, n * T1, t5.N, t5.K, e); }
-        if (on(4)) { Epi e; e.rps = T2; e.bias = r6a.b; e.act = ACT_ELU; e.out2 = buf6b + slot0 * s6b; e.out2_map = smap(s6b, 64, 0); e.out2_type = OUT2_F16;
+        if (on(4) && use_fused_res6()) {
+            // resnet block 6 in one streaming kernel (seanet_res.cuh): no 64-channel intermediate, the result lands in the next transposed conv's input rows
+            SrParams sp{};
+            sp.a1 = buf6a; sp.a1_slot_stride = s6a; sp.y = y6; sp.y_slot_stride = 480LL * 128; sp.out = buf8; sp.out_slot_stride = s8; sp.out_row0 = 1;
+            sp.w3 = r6a.w; sp.b3 = r6a.b; sp.w1 = r6b.w; sp.w1_ld = r6b.K; sp.b1 = r6b.b; sp.slot0 = slot0; sp.n_slots = n; sp.T = T2;
+            const long long items = (long long)n * (T2 / SR_ROWS);
+            launch_k(pdl_active, seanet_res_kernel, dim3((unsigned)std::min<long long>(tc ? tc->num_sms : 148, (items + SR_WARPS - 1) / SR_WARPS)), dim3(SR_THREADS), SR_SMEM_BYTES, stream, sp);
+            launches++;
+        } else if (on(4)) {
+        { Epi e; e.rps = T2; e.bias = r6a.b; e.act = ACT_ELU; e.out2 = buf6b + slot0 * s6b; e.out2_map = smap(s6b, 64, 0); e.out2_type = OUT2_F16;
           gemm<__half>(buf6a + slot0 * s6a, smap(s6a, 128, 0), T2, r6a.w, r6a.wk, n * T2, r6a.N, r6a.K, e); }
-        if (on(4)) { Epi e; e.rps = T2; e.bias = r6b.b; e.resid = y6 + slot0 * 480LL * 128; e.resid_map = smap(480LL * 128, 128, 0);
+        { Epi e; e.rps = T2; e.bias = r6b.b; e.resid = y6 + slot0 * 480LL * 128; e.resid_map = smap(480LL * 128, 128, 0);
           e.act = ACT_ELU; e.out2 = buf8 + slot0 * s8; e.out2_map = smap(s8, C8, C8); e.out2_type = o2t; e.split_off = 128;
           gemm<__half>(buf6b + slot0 * s6b, smap(s6b, 64, 0), T2, r6b.w, r6b.wk, n * T2, r6b.N, r6b.K, e); }
+        }
         if (on(5)) { Epi e; e.rps = T2; e.bias = t8.b; e.out = y9 + slot0 * 1920LL * 64; e.out_map = smap(1920LL * 64, 256, 0);
           e.act = ACT_ELU; e.out2 = buf9a + slot0 * s9a; e.out2_map = smap(s9a, 256, 2 * 64); e.out2_type = OUT2_F16;
           gemm<__half>(buf8 + slot0 * s8, smap(s8, C8, 0), T2, t8.w, t8.wk, n * T2, t8.N, t8.K, e); }
@@ -1218,6 +1234,7 @@ int b200_finalize_weights(b200_engine* e) {
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(flow_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM_BYTES));
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(head_res_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HF_SMEM_BYTES));
     PTTS_CUDA_CHECK(cudaFuncSetAttribute(seanet_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES));
+    PTTS_CUDA_CHECK(cudaFuncSetAttribute(seanet_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM_BYTES));
     e->actx.row_slot = e->row_slot; e->actx.row_pos = e->row_pos; e->actx.cs = e->cs;
     PTTS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     e->finalized = true;

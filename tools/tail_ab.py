@@ -9,7 +9,7 @@ d = default_model_dir(eos_mode="never")
 B = int(os.environ.get("B", "37"))
 out = {}
 for mode in ("0", "1"):
-    os.environ["PTTS_B200_FUSED_TAIL"] = mode
+    os.environ[os.environ.get("AB_VAR", "PTTS_B200_FUSED_TAIL")] = mode
     ctx = P.Context(d, max_slots=B, kv_capacity=64)
     eng = ctx.engine
     rng = np.random.default_rng(3)
