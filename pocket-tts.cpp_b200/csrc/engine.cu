@@ -680,7 +680,7 @@ struct b200_engine {
         PfParams p{};
         const int sms = tc ? tc->num_sms : 148;
         p.slot0 = slot0; p.R = n;
-        p.n_splits = std::max(std::max(1, sms / (n * N_HEADS)), (cfg.kv_capacity + PF_MAX_KEYS - 1) / PF_MAX_KEYS);
+        p.n_splits = std::min(16, std::max(std::max(1, sms / (n * N_HEADS)), (cfg.kv_capacity + PF_MAX_KEYS - 1) / PF_MAX_KEYS));   // <= 16: merge scratch of the kernel
         p.lat_in = lat_in_bf16; p.cur_len = cur_len; p.active = active; p.freq = freq_flow;
         p.kc = (__nv_bfloat16*)kc; p.vc = (__nv_bfloat16*)vc; p.kv_slot_stride = kv_slot_stride; p.kv_layer_stride = kv_layer_stride;
         p.pfx_slot = pfx_slot; p.pfx_len = pfx_len;
