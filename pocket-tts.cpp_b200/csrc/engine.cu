@@ -964,7 +964,7 @@ extern "C" {
 void b200_default_config(b200_config* c) {
     memset(c, 0, sizeof(*c));
     c->device = 0; c->max_slots = 1; c->max_voices = 8; c->kv_capacity = 2048; c->kv_f32 = 0; c->mimi_mask_mode = 0;
-    c->convt_split = 0; c->gemm_path = 0; c->max_prefill_rows = 2048; c->cuda_graphs = 1; c->pdl = 1; c->overlap = 1; c->prefix_share = 1;
+    c->convt_split = 0; c->gemm_path = 0; c->max_prefill_rows = 4096; c->cuda_graphs = 1; c->pdl = 1; c->overlap = 1; c->prefix_share = 1;
 }
 
 int b200_engine_create(const b200_config* cfg, b200_engine** out) {
@@ -975,7 +975,7 @@ int b200_engine_create(const b200_config* cfg, b200_engine** out) {
         return B200_ESTATE;
     }
     auto* e = new b200_engine; e->cfg = *cfg;
-    if (e->cfg.max_prefill_rows <= 0) e->cfg.max_prefill_rows = 2048;
+    if (e->cfg.max_prefill_rows <= 0) e->cfg.max_prefill_rows = 4096;
     if (e->cfg.max_voices < 1) e->cfg.max_voices = 1;
     PTTS_CUDA_CHECK(cudaSetDevice(cfg->device));
     {   // the FlowLM chain is the critical path of a frame: it gets the higher priority, the Mimi decode fills the gaps
